@@ -1,0 +1,130 @@
+"""Deterministic synthetic inputs for the novel-view-completion hot path.
+
+No Pascal3D CAD YAMLs, checkpoints or videos are available offline, so tests, bench.py and
+smoke() all draw from this generator: a 5 m box-car with the 12 Pascal3D car keypoints
+(utils/keypoint_utils.py:9-13 order), a pinhole camera looking at the origin, and uniform-noise
+source crops (the worst case for interpolation parity; bandwidth is data independent).
+
+Everything is numpy on the host -- this module produces inputs, it computes nothing on the path.
+"""
+import numpy as np
+
+KP_NAMES = ['left_back_trunk', 'left_back_wheel', 'left_front_light',
+            'left_front_wheel', 'right_back_trunk', 'right_back_wheel',
+            'right_front_light', 'right_front_wheel', 'upper_left_rearwindow',
+            'upper_left_windshield', 'upper_right_rearwindow',
+            'upper_right_windshield']
+
+# CAD axes: x = left(-)/right(+), y = back(-)/front(+), z = up
+_BOX_CAR = {
+    'left_back_trunk': (-0.9, -2.5, 0.9), 'right_back_trunk': (0.9, -2.5, 0.9),
+    'left_back_wheel': (-0.9, -1.5, 0.3), 'right_back_wheel': (0.9, -1.5, 0.3),
+    'left_front_wheel': (-0.9, 1.5, 0.3), 'right_front_wheel': (0.9, 1.5, 0.3),
+    'left_front_light': (-0.9, 2.5, 0.7), 'right_front_light': (0.9, 2.5, 0.7),
+    'upper_left_rearwindow': (-0.7, -1.2, 1.5), 'upper_right_rearwindow': (0.7, -1.2, 1.5),
+    'upper_left_windshield': (-0.7, 0.6, 1.5), 'upper_right_windshield': (0.7, 0.6, 1.5),
+}
+
+
+def cad_keypoints(cad_id: int = 0) -> np.ndarray:
+    """(12,3) fp64 keypoints of synthetic CAD `cad_id` (per-id jitter of +-5 %)."""
+    base = np.array([_BOX_CAR[k] for k in KP_NAMES], np.float64)
+    jit = np.random.default_rng(cad_id).uniform(-0.05, 0.05, base.shape)
+    return base * (1.0 + jit)
+
+
+def intrinsic(h: int = 256, w: int = 256) -> np.ndarray:
+    f = 300.0 * w / 256.0
+    return np.array([[f, 0, w / 2.0], [0, f, h / 2.0], [0, 0, 1.0]], np.float64)
+
+
+def look_at_extrinsic(azimuth_deg: float, elevation_deg: float, distance: float) -> np.ndarray:
+    """World->camera 4x4 for a camera on a sphere around the origin, looking at it, z up."""
+    az, el = np.deg2rad(azimuth_deg), np.deg2rad(elevation_deg)
+    c = distance * np.array([np.cos(el) * np.sin(az), -np.cos(el) * np.cos(az), np.sin(el)])
+    fwd = -c / np.linalg.norm(c)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0]))
+    right /= np.linalg.norm(right)
+    down = np.cross(fwd, right)
+    R = np.stack([right, down, fwd])           # rows: camera x, y(down), z(forward)
+    E = np.eye(4)
+    E[:3, :3] = R
+    E[:3, 3] = -R @ c
+    return E
+
+
+def project(K: np.ndarray, E: np.ndarray, X: np.ndarray) -> np.ndarray:
+    """The reference's pinhole model (warp_learn/online_visibility.py:28-56), vectorised."""
+    Xh = np.concatenate([X, np.ones((len(X), 1))], 1)
+    p = K @ E[:3] @ Xh.T
+    p = p / p[2]
+    return p.T[:, :2]
+
+
+def make_pose_pair(idx: int, h: int = 256, w: int = 256, max_tries: int = 200):
+    """Source/destination poses for crop `idx` with every projected keypoint inside the frame.
+
+    Returns dict(K, E_src, E_dst, kp3d, kp2d_src, kp2d_dst, src_kp, dst_kp) where kp2d_* are the
+    normalised (12,2) arrays the reference passes to get_planes and *_kp their int32 truncation
+    (planes_utils.py:22-27).
+    """
+    rng = np.random.default_rng(1234 + idx)
+    K = intrinsic(h, w)
+    kp3d = cad_keypoints(idx % 10)
+    for _ in range(max_tries):
+        az = rng.uniform(0, 360)
+        el = rng.uniform(5, 40)
+        E_src = look_at_extrinsic(az, el, rng.uniform(8, 11))
+        E_dst = look_at_extrinsic(az + rng.uniform(-20, 20), el, rng.uniform(8, 11))
+        p_src, p_dst = project(K, E_src, kp3d), project(K, E_dst, kp3d)
+        ok = True
+        for p in (p_src, p_dst):
+            if p[:, 0].min() < 0 or p[:, 0].max() > w - 1 or p[:, 1].min() < 0 or p[:, 1].max() > h - 1:
+                ok = False
+        if ok:
+            break
+    else:
+        raise RuntimeError("no in-frame pose found")
+    out = dict(K=K, E_src=E_src, E_dst=E_dst, kp3d=kp3d)
+    for name, p in (("src", p_src), ("dst", p_dst)):
+        norm = p / np.array([w, h], np.float64)
+        out[f"kp2d_{name}"] = norm
+        px = norm.copy()
+        px[:, 0] *= w
+        px[:, 1] *= h
+        out[f"{name}_kp"] = np.int32(px)
+    return out
+
+
+def make_crop(idx: int, h: int = 256, w: int = 256) -> np.ndarray:
+    """Uniform-noise uint8 source crop (h,w,3) for crop `idx`."""
+    return np.random.default_rng(77_000 + idx).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def make_warp_batch(start: int, count: int, h: int = 256, w: int = 256, crops: bool = True):
+    """Stacked arrays for crops [start, start+count): the layout the C ABI takes (include/fusg.h)."""
+    poses = [make_pose_pair(start + i, h, w) for i in range(count)]
+    batch = dict(
+        K=np.stack([p["K"] for p in poses]),
+        E_src=np.stack([p["E_src"][:3] for p in poses]),
+        E_dst=np.stack([p["E_dst"][:3] for p in poses]),
+        kp3d=np.stack([p["kp3d"] for p in poses]),
+        src_kp=np.stack([p["src_kp"] for p in poses]),
+        dst_kp=np.stack([p["dst_kp"] for p in poses]),
+    )
+    if crops:
+        batch["src"] = np.stack([make_crop(start + i, h, w) for i in range(count)])
+    return batch
+
+
+def make_vunet_inputs(start: int, count: int, res: int = 256):
+    """(x (B,6,res,res), y_tilde (B,3,res,res)) fp32 in [-1,1] = to_tensor of uint8 noise
+    (utils/misc_utils.py:35-50)."""
+    xs, ys = [], []
+    for i in range(count):
+        rng = np.random.default_rng(55_000 + start + i)
+        x8 = rng.integers(0, 256, (6, res, res), dtype=np.uint8)
+        y8 = rng.integers(0, 256, (3, res, res), dtype=np.uint8)
+        xs.append(np.float32(x8) / 255 * 2.0 - 1.0)
+        ys.append(np.float32(y8) / 255 * 2.0 - 1.0)
+    return np.stack(xs).astype(np.float32), np.stack(ys).astype(np.float32)
