@@ -1,0 +1,80 @@
+"""ctypes binding of the C-ABI library libfusg.so (include/fusg.h).
+
+The product path has no CPU fallback: importing this module without the built library, or
+calling into it without a CUDA device, raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfusg.so")
+
+ERRORS = {-1: "FUSG_ERR_ARG", -2: "FUSG_ERR_UNSUPPORTED", -3: "FUSG_ERR_CUDA", -4: "FUSG_ERR_WORKSPACE"}
+
+
+class FusgError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise FusgError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    sigs = {
+        "fusg_version": ([], i),
+        "fusg_last_error": ([], C.c_char_p),
+        "fusg_kernel_launches": ([], i),
+        "fusg_warp_workspace_bytes": ([i], sz),
+        "fusg_warp_fused": ([vp] * 11 + [vp, sz, i, i, i, vp], i),
+        "fusg_visibility": ([vp] * 6 + [i, i, i, vp], i),
+        "fusg_get_planes": ([vp] * 3 + [i, i, i, vp], i),
+        "fusg_find_homography": ([vp, vp, i, vp, vp, i, vp], i),
+        "fusg_warp_perspective": ([vp] * 3 + [i, i, i, vp], i),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().fusg_last_error().decode() if rc == -3 else ""
+        raise FusgError(f"{what} failed: {ERRORS.get(rc, rc)} {msg}")
+
+
+def kernel_launches():
+    return lib().fusg_kernel_launches()
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise FusgError("no CUDA device: the B200 path has no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

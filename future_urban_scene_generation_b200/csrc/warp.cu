@@ -1,0 +1,579 @@
+// warp.cu -- fused planar-warp stage for sm_100a: visibility, per-plane homographies and the
+// masked fixed-point bilinear gather, behind the C ABI of include/fusg.h.
+//
+// Reference path (file:line in the reference repo): trajectory_inference.py:165-174 =
+//   compute_visibility (warp_learn/online_visibility.py:105-150) for both poses,
+//   get_planes        (warp_learn/planes_utils.py:11-37),
+//   warp_unwarp_planes(warp_learn/planes_utils.py:40-82), first return value.
+//
+// Three launches per batch, one C call:
+//   k_visibility   one CTA per (crop, pose): polygon scanline coverage as 32-pixel bit words,
+//                  painter's-order occlusion, area ratio test -> 7 flags.
+//   k_homography   one thread per (crop, plane): gating, DLT (OpenCV Jacobi) + LM, inverse map.
+//   k_warp         one CTA per crop: source crop staged in shared memory by TMA bulk copies,
+//                  per-plane polygon bit mask in shared memory, per-row conservative active
+//                  span, cv2-exact 1/32-px fixed-point bilinear gather, rows written back with
+//                  128-bit coalesced stores.  HBM traffic = read crop once + write 5 planes.
+//
+// Compiled with -fmad=false (see warp_geom.cuh).
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/fusg.h"
+#include "fusg_common.h"
+#include "warp_geom.cuh"
+
+namespace fusg {
+
+// ============================================================================================
+// k_visibility
+// ============================================================================================
+struct VisShared {
+    int vx[N_KP], vy[N_KP];
+    double dist[N_VIS];
+    int area[2 * N_VIS];
+    int oob;
+};
+
+// one pose: fills sm.area / sm.oob; all threads of the CTA participate
+__device__ void visibility_pose(VisShared &sm, const double *K, const double *E, const double *kp3d, int H, int W) {
+    const int tid = threadIdx.x;
+    if (tid < N_KP) {
+        double u, v;
+        project_point(K, E, kp3d + 3 * tid, &u, &v);
+        // int(): truncation toward zero; values far outside int range are clamped (they are
+        // rejected as out-of-frame below anyway)
+        u = fmin(fmax(u, -1.0e9), 1.0e9);
+        v = fmin(fmax(v, -1.0e9), 1.0e9);
+        sm.vx[tid] = (int)u;
+        sm.vy[tid] = (int)v;
+    } else if (tid >= 32 && tid < 32 + N_VIS) {
+        sm.dist[tid - 32] = plane_distance(E, kp3d, tid - 32);
+    } else if (tid >= 64 && tid < 64 + 2 * N_VIS) {
+        sm.area[tid - 64] = 0;
+    } else if (tid == 96) {
+        sm.oob = 0;
+    }
+    __syncthreads();
+    if (tid < N_KP) {
+        if (sm.vx[tid] < 0 || sm.vx[tid] >= W || sm.vy[tid] < 0 || sm.vy[tid] >= H) sm.oob = 1;
+    }
+    __syncthreads();
+    if (sm.oob) return;
+
+    // occluder sets: planes strictly nearer to the camera
+    unsigned nearer[N_VIS];
+    for (int p = 0; p < N_VIS; ++p) {
+        unsigned mk = 0;
+        for (int q = 0; q < N_VIS; ++q)
+            if (sm.dist[q] < sm.dist[p]) mk |= 1u << q;
+        nearer[p] = mk;
+    }
+    int px[N_VIS][6], py[N_VIS][6];
+    for (int p = 0; p < N_VIS; ++p)
+        for (int k = 0; k < c_plane_n[p]; ++k) {
+            px[p][k] = sm.vx[c_plane_kp[p][k]];
+            py[p][k] = sm.vy[c_plane_kp[p][k]];
+        }
+    int cnt_abs[N_VIS], cnt_occ[N_VIS];
+    for (int p = 0; p < N_VIS; ++p) cnt_abs[p] = cnt_occ[p] = 0;
+    const int nwords = (W + 31) >> 5;
+    for (int y = tid; y < H; y += blockDim.x) {
+        int lo[N_VIS][MAX_RANGES], hi[N_VIS][MAX_RANGES], rc[N_VIS];
+        for (int p = 0; p < N_VIS; ++p) rc[p] = poly_row_ranges(px[p], py[p], c_plane_n[p], y, lo[p], hi[p]);
+        for (int w = 0; w < nwords; ++w) {
+            unsigned bits[N_VIS];
+            for (int p = 0; p < N_VIS; ++p) bits[p] = ranges_word(lo[p], hi[p], rc[p], w);
+            for (int p = 0; p < N_VIS; ++p) {
+                unsigned occl = 0;
+                for (int q = 0; q < N_VIS; ++q)
+                    if ((nearer[p] >> q) & 1u) occl |= bits[q];
+                cnt_abs[p] += __popc(bits[p]);
+                cnt_occ[p] += __popc(bits[p] & ~occl);
+            }
+        }
+    }
+    for (int p = 0; p < N_VIS; ++p) {
+        int a = cnt_abs[p], o = cnt_occ[p];
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            o += __shfl_xor_sync(0xffffffffu, o, off);
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(&sm.area[2 * p], a);
+            atomicAdd(&sm.area[2 * p + 1], o);
+        }
+    }
+    __syncthreads();
+}
+
+// grid.x = number of poses.  Pose g reads K[g / poses_per_K], E[g], kp3d[g / poses_per_K].
+// E is addressed as E0 (even g) / E1 (odd g) when E1 != nullptr (the fused src/dst layout).
+__global__ void __launch_bounds__(256) k_visibility(const double *__restrict__ K, const double *__restrict__ E0,
+                                                    const double *__restrict__ E1, const double *__restrict__ kp3d,
+                                                    uint8_t *__restrict__ vis, int32_t *__restrict__ pts,
+                                                    int32_t *__restrict__ areas, int H, int W) {
+    __shared__ VisShared sm;
+    const int g = blockIdx.x;
+    const double *Kp, *Ep, *Xp;
+    if (E1) {
+        const int b = g >> 1;
+        Kp = K + 9 * b; Xp = kp3d + 36 * b;
+        Ep = ((g & 1) ? E1 : E0) + 12 * b;
+    } else {
+        Kp = K + 9 * g; Xp = kp3d + 36 * g; Ep = E0 + 12 * g;
+    }
+    visibility_pose(sm, Kp, Ep, Xp, H, W);
+    const int tid = threadIdx.x;
+    if (tid < N_VIS) {
+        uint8_t v = 0;
+        if (!sm.oob) v = (double)sm.area[2 * tid + 1] > 0.9 * (double)sm.area[2 * tid] ? 1 : 0;
+        else v = 0xff;                                    // out-of-frame marker
+        vis[N_VIS * g + tid] = v;
+    }
+    if (pts && tid < N_KP) { pts[(N_KP * g + tid) * 2] = sm.vx[tid]; pts[(N_KP * g + tid) * 2 + 1] = sm.vy[tid]; }
+    if (areas && tid < 2 * N_VIS) areas[2 * N_VIS * g + tid] = sm.oob ? -1 : sm.area[tid];
+}
+
+// ============================================================================================
+// k_homography: thread per (crop, source plane)
+// workspace layout per crop: Minv[5][9] f64 (inverse maps indexed by SOURCE plane i)
+// ============================================================================================
+__global__ void __launch_bounds__(128) k_homography(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                    const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j,
+                                                    double *__restrict__ H12, double *__restrict__ Minv, int B, int H, int W) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * N_TEX) return;
+    const int b = t / N_TEX, i = t % N_TEX;
+    const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
+    int j = -1;
+    bool bad = sv[0] == 0xff || dv[0] == 0xff;            // projected keypoint out of frame
+    const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
+    for (int k = 0; k < N_KP && !bad; ++k) {
+        if (sk[2 * k] < 0 || sk[2 * k] >= W || sk[2 * k + 1] < 0 || sk[2 * k + 1] >= H) bad = true;
+        if (dk[2 * k] < 0 || dk[2 * k] >= W || dk[2 * k + 1] < 0 || dk[2 * k + 1] >= H) bad = true;
+    }
+    double Hm[9], Mi[9];
+    for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
+    if (bad) {
+        j = -2;
+    } else {
+        j = plane_target(i, sv, dv);
+        if (j >= 0) {
+            const int n = c_plane_n[i];
+            int s[12], d[12];
+            for (int k = 0; k < n; ++k) {
+                s[2 * k] = sk[2 * c_plane_kp[i][k]]; s[2 * k + 1] = sk[2 * c_plane_kp[i][k] + 1];
+                d[2 * k] = dk[2 * c_plane_kp[j][k]]; d[2 * k + 1] = dk[2 * c_plane_kp[j][k] + 1];
+            }
+            // H21 is only ever used through its "is None" test, which is the same degeneracy
+            // test as H12's (symmetric in src/dst) -- planes_utils.py:72-74
+            if (!find_homography(s, d, n, Hm)) {
+                j = -1;
+                for (int k = 0; k < 9; ++k) Hm[k] = 0;
+            } else {
+                invert3(Hm, Mi);
+            }
+        }
+    }
+    plane_j[t] = (int8_t)j;
+    for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
+    if (H12) for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
+}
+
+__global__ void k_find_homography(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
+                                  double *__restrict__ H, uint8_t *__restrict__ ok, int N) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    int s[12], d[12];
+    for (int k = 0; k < 2 * n; ++k) { s[k] = src[2 * n * t + k]; d[k] = dst[2 * n * t + k]; }
+    double Hm[9];
+    const bool good = find_homography(s, d, n, Hm);
+    for (int k = 0; k < 9; ++k) H[9 * t + k] = good ? Hm[k] : 0.0;
+    ok[t] = good ? 1 : 0;
+}
+
+// ============================================================================================
+// The gather: cv2.warpPerspective INTER_LINEAR / BORDER_CONSTANT(0) for one destination pixel.
+// M is the inverse map; (bx,y) the start of OpenCV's 64-wide processing block containing x.
+// ============================================================================================
+struct RowBase { double X0, Y0, W0; };
+
+__device__ __forceinline__ RowBase row_base(const double *M, int bx, int y) {
+    RowBase r;
+    r.X0 = M[0] * bx + M[1] * y + M[2];
+    r.Y0 = M[3] * bx + M[4] * y + M[5];
+    r.W0 = M[6] * bx + M[7] * y + M[8];
+    return r;
+}
+
+__device__ __forceinline__ void src_coord(const double *M, const RowBase &rb, int x1, int &X, int &Y) {
+    double Wv = rb.W0 + M[6] * x1;
+    Wv = Wv ? 32. / Wv : 0;
+    const double fX = fmax((double)INT_MIN, fmin((double)INT_MAX, (rb.X0 + M[0] * x1) * Wv));
+    const double fY = fmax((double)INT_MIN, fmin((double)INT_MAX, (rb.Y0 + M[3] * x1) * Wv));
+    X = __double2int_rn(fX);      // cvRound: round half to even
+    Y = __double2int_rn(fY);
+}
+
+// OpenCV's block width for warpPerspective (BLOCK_SZ = 32)
+__host__ __device__ inline int warp_block_w(int H, int W) {
+    const int bh0 = 16 < H ? 16 : H;
+    const int bw0 = 32 * 32 / bh0;
+    return bw0 < W ? bw0 : W;
+}
+
+template <bool MASKED, typename SrcPtr>
+__device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask, int mask_words, int H, int W, int X, int Y) {
+    int sx = X >> 5, sy = Y >> 5;
+    const int a = X & 31, b = Y & 31;
+    sx = max(-32768, min(32767, sx));
+    sy = max(-32768, min(32767, sy));
+    const int w00 = (32 - a) * (32 - b) * 32, w01 = a * (32 - b) * 32, w10 = (32 - a) * b * 32, w11 = a * b * 32;
+    const bool xin0 = (unsigned)sx < (unsigned)W, xin1 = (unsigned)(sx + 1) < (unsigned)W;
+    const bool yin0 = (unsigned)sy < (unsigned)H, yin1 = (unsigned)(sy + 1) < (unsigned)H;
+    bool t00 = xin0 && yin0, t01 = xin1 && yin0, t10 = xin0 && yin1, t11 = xin1 && yin1;
+    if (MASKED) {
+        if (t00) t00 = (mask[sy * mask_words + (sx >> 5)] >> (sx & 31)) & 1u;
+        if (t01) t01 = (mask[sy * mask_words + ((sx + 1) >> 5)] >> ((sx + 1) & 31)) & 1u;
+        if (t10) t10 = (mask[(sy + 1) * mask_words + (sx >> 5)] >> (sx & 31)) & 1u;
+        if (t11) t11 = (mask[(sy + 1) * mask_words + ((sx + 1) >> 5)] >> ((sx + 1) & 31)) & 1u;
+    }
+    int acc0 = 1 << 14, acc1 = 1 << 14, acc2 = 1 << 14;
+    if (t00) { const auto *p = src + (sy * W + sx) * 3;           acc0 += p[0] * w00; acc1 += p[1] * w00; acc2 += p[2] * w00; }
+    if (t01) { const auto *p = src + (sy * W + sx + 1) * 3;       acc0 += p[0] * w01; acc1 += p[1] * w01; acc2 += p[2] * w01; }
+    if (t10) { const auto *p = src + ((sy + 1) * W + sx) * 3;     acc0 += p[0] * w10; acc1 += p[1] * w10; acc2 += p[2] * w10; }
+    if (t11) { const auto *p = src + ((sy + 1) * W + sx + 1) * 3; acc0 += p[0] * w11; acc1 += p[1] * w11; acc2 += p[2] * w11; }
+    return make_uchar3((unsigned char)(acc0 >> 15), (unsigned char)(acc1 >> 15), (unsigned char)(acc2 >> 15));
+}
+
+// ============================================================================================
+// k_warp: one CTA (512 threads) per crop
+// ============================================================================================
+constexpr int WARP_THREADS = 512;
+constexpr int WARP_NWARPS = WARP_THREADS / 32;
+constexpr int MAX_HW = 256;
+constexpr int ROW_BYTES_MAX = MAX_HW * 3;          // 768
+constexpr int MASK_WORDS = MAX_HW / 32;            // 8 words per row
+
+struct WarpSmemHeader {
+    unsigned long long mbar;
+    double Minv[N_TEX][9];
+    int sel[N_TEX];                                // source plane feeding output plane j, or -1
+    int polyx[6], polyy[6], polyn;
+    int bbox[4];                                   // xmin,xmax,ymin,ymax of the source polygon
+    short span_lo[MAX_HW], span_hi[MAX_HW];        // conservative active span per output row
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// conservative x-span of output row y whose source footprint can touch the polygon bbox
+__device__ __forceinline__ void row_active_span(const double *M, int y, int W, const int *bbox, int &xlo, int &xhi) {
+    // u = (M0 x + cu) / (M6 x + cd), v = (M3 x + cv) / (M6 x + cd);  need u in [ulo,uhi], v in [vlo,vhi]
+    const double cu = M[1] * y + M[2], cv = M[4] * y + M[5], cd = M[7] * y + M[8];
+    const double d0 = cd, d1 = M[6] * (W - 1) + cd;
+    xlo = 0; xhi = W - 1;
+    if (!(d0 > 0 && d1 > 0) && !(d0 < 0 && d1 < 0)) return;         // sign change / zero / NaN: keep full row
+    const double sgn = d0 > 0 ? 1.0 : -1.0;
+    const double ulo = bbox[0] - 2.0, uhi = bbox[1] + 2.0, vlo = bbox[2] - 2.0, vhi = bbox[3] + 2.0;
+    double l = 0.0, h = (double)(W - 1);
+    // each constraint: sgn * (a x + c) >= 0
+    const double ca[4] = {sgn * (M[0] - ulo * M[6]), -sgn * (M[0] - uhi * M[6]), sgn * (M[3] - vlo * M[6]), -sgn * (M[3] - vhi * M[6])};
+    const double cc[4] = {sgn * (cu - ulo * cd), -sgn * (cu - uhi * cd), sgn * (cv - vlo * cd), -sgn * (cv - vhi * cd)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double a = ca[k], c = cc[k];
+        if (!(a == a) || !(c == c)) return;                        // NaN: full row
+        if (fabs(a) < 1e-300) {
+            if (c < 0) { l = 1; h = 0; }                            // infeasible (up to rounding: c<0 strictly)
+        } else {
+            const double r = -c / a;
+            if (!(fabs(r) < 1e15)) { if (a > 0 ? r > 0 : r < 0) { l = 1; h = 0; } continue; }
+            if (a > 0) l = fmax(l, r - 1.5); else h = fmin(h, r + 1.5);
+        }
+    }
+    if (l > h) { xlo = 1; xhi = 0; return; }
+    xlo = max(0, (int)floor(l) - 1);
+    xhi = min(W - 1, (int)ceil(h) + 1);
+}
+
+__global__ void __launch_bounds__(WARP_THREADS, 1)
+k_warp(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
+       const double *__restrict__ Minv, uint8_t *__restrict__ warped, int H, int W) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int crop_bytes = H * W * 3;
+    const int row_bytes = W * 3;
+    // smem carve-up
+    uint8_t *s_src = smem;                                                    // crop_bytes (padded to 128)
+    const int src_pad = (crop_bytes + 127) & ~127;
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + src_pad);          // H * MASK_WORDS words
+    uint8_t *s_rows = reinterpret_cast<uint8_t *>(s_mask + MAX_HW * MASK_WORDS);  // WARP_NWARPS * 768
+    WarpSmemHeader *hd = reinterpret_cast<WarpSmemHeader *>(s_rows + WARP_NWARPS * ROW_BYTES_MAX);
+
+    const uint8_t *gsrc = src + (size_t)b * crop_bytes;
+    uint8_t *gout = warped + (size_t)b * N_TEX * crop_bytes;
+    const bool use_tma = (crop_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0);
+
+    if (tid == 0) {
+        mbar_init(&hd->mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < N_TEX) hd->sel[tid] = -1;
+    __syncthreads();
+    if (tid == 0) {
+        // last writer wins (planes_utils.py:79): ascending i
+        for (int i = 0; i < N_TEX; ++i) {
+            const int j = plane_j[b * N_TEX + i];
+            if (j >= 0) hd->sel[j] = i;
+        }
+        if (use_tma) {
+            mbar_expect_tx(&hd->mbar, (uint32_t)crop_bytes);
+            const int CH = 32768;
+            for (int off = 0; off < crop_bytes; off += CH)
+                bulk_g2s(s_src + off, gsrc + off, (uint32_t)min(CH, crop_bytes - off), &hd->mbar);
+        }
+    }
+    if (tid >= 32 && tid < 32 + N_TEX * 9) hd->Minv[0][tid - 32] = Minv[(size_t)b * N_TEX * 9 + (tid - 32)];
+    if (!use_tma) {
+        for (int i = tid; i < crop_bytes; i += WARP_THREADS) s_src[i] = gsrc[i];
+    }
+    __syncthreads();
+
+    // ---- pass 1: planes nobody writes -> zeros (no source needed; overlaps the TMA load)
+    const int4 z4 = make_int4(0, 0, 0, 0);
+    for (int j = 0; j < N_TEX; ++j) {
+        if (hd->sel[j] >= 0) continue;
+        uint8_t *o = gout + (size_t)j * crop_bytes;
+        if ((crop_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            int4 *o4 = reinterpret_cast<int4 *>(o);
+            for (int i = tid; i < crop_bytes / 16; i += WARP_THREADS) o4[i] = z4;
+        } else {
+            for (int i = tid; i < crop_bytes; i += WARP_THREADS) o[i] = 0;
+        }
+    }
+    if (use_tma) mbar_wait(&hd->mbar, 0);
+
+    // ---- pass 2: written planes
+    const int bw = warp_block_w(H, W);
+    const bool vec_rows = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+    uint8_t *my_row = s_rows + warp * ROW_BYTES_MAX;
+    for (int j = 0; j < N_TEX; ++j) {
+        const int i = hd->sel[j];
+        if (i < 0) continue;
+        __syncthreads();                                  // previous plane done with mask / spans
+        if (tid == 0) {
+            const int n = c_plane_n[i];
+            int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+            for (int k = 0; k < n; ++k) {
+                const int vx = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2], vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
+                hd->polyx[k] = vx; hd->polyy[k] = vy;
+                x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
+            }
+            hd->polyn = n;
+            hd->bbox[0] = x0; hd->bbox[1] = x1; hd->bbox[2] = y0; hd->bbox[3] = y1;
+        }
+        __syncthreads();
+        const double *M = hd->Minv[i];
+        // polygon bit mask of source plane i + active span of every output row
+        for (int y = tid; y < H; y += WARP_THREADS) {
+            int px[6], py[6], lo[MAX_RANGES], hi[MAX_RANGES];
+            const int n = hd->polyn;
+            for (int k = 0; k < n; ++k) { px[k] = hd->polyx[k]; py[k] = hd->polyy[k]; }
+            const int rc = poly_row_ranges(px, py, n, y, lo, hi);
+            for (int w = 0; w < MASK_WORDS; ++w) s_mask[y * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
+            int xlo, xhi;
+            row_active_span(M, y, W, hd->bbox, xlo, xhi);
+            hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
+        }
+        __syncthreads();
+        uint8_t *oplane = gout + (size_t)j * crop_bytes;
+        for (int y = warp; y < H; y += WARP_NWARPS) {
+            const int xlo = hd->span_lo[y], xhi = hd->span_hi[y];
+            uint8_t *orow = oplane + (size_t)y * row_bytes;
+            if (xlo > xhi) {                               // whole row is zero
+                if (vec_rows) { int4 *o4 = reinterpret_cast<int4 *>(orow); for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = z4; }
+                else for (int k = lane; k < row_bytes; k += 32) orow[k] = 0;
+                continue;
+            }
+            // zero the staging row, then fill the active 32-pixel groups
+            for (int k = lane; k < (row_bytes + 15) / 16; k += 32) reinterpret_cast<int4 *>(my_row)[k] = z4;
+            __syncwarp();
+            for (int g = xlo >> 5; g <= (xhi >> 5); ++g) {
+                const int x = g * 32 + lane;
+                if (x < W) {
+                    const int bx = (x / bw) * bw;
+                    const RowBase rb = row_base(M, bx, y);
+                    int X, Y;
+                    src_coord(M, rb, x - bx, X, Y);
+                    const uchar3 v = bilinear_tap4<true>(s_src, s_mask, MASK_WORDS, H, W, X, Y);
+                    my_row[3 * x] = v.x; my_row[3 * x + 1] = v.y; my_row[3 * x + 2] = v.z;
+                }
+            }
+            __syncwarp();
+            if (vec_rows) {
+                int4 *o4 = reinterpret_cast<int4 *>(orow);
+                for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = reinterpret_cast<const int4 *>(my_row)[k];
+            } else {
+                for (int k = lane; k < row_bytes; k += 32) orow[k] = my_row[k];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// crops with out-of-frame keypoints (plane_j == -2): k_warp already zero-filled them because no
+// plane has a writer; nothing else to do.
+
+// ============================================================================================
+// Stand-alone kernels for the per-function drop-ins
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_get_planes(const uint8_t *__restrict__ img, const int32_t *__restrict__ kp,
+                                                    uint8_t *__restrict__ planes, int H, int W) {
+    // grid: (rows, 5 planes, B).  One CTA per image row.
+    const int y = blockIdx.x, p = blockIdx.y, b = blockIdx.z;
+    __shared__ int lo[MAX_RANGES], hi[MAX_RANGES], rc;
+    if (threadIdx.x == 0) {
+        int px[6], py[6];
+        const int n = c_plane_n[p];
+        for (int k = 0; k < n; ++k) { px[k] = kp[(b * N_KP + c_plane_kp[p][k]) * 2]; py[k] = kp[(b * N_KP + c_plane_kp[p][k]) * 2 + 1]; }
+        int l[MAX_RANGES], h[MAX_RANGES];
+        const int c = poly_row_ranges(px, py, n, y, l, h);
+        for (int k = 0; k < c; ++k) { lo[k] = l[k]; hi[k] = h[k]; }
+        rc = c;
+    }
+    __syncthreads();
+    const uint8_t *irow = img + ((size_t)b * H + y) * W * 3;
+    uint8_t *orow = planes + (((size_t)b * N_TEX + p) * H + y) * W * 3;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        bool in = false;
+        for (int k = 0; k < rc; ++k) in = in || (x >= lo[k] && x <= hi[k]);
+        orow[3 * x] = in ? irow[3 * x] : 0;
+        orow[3 * x + 1] = in ? irow[3 * x + 1] : 0;
+        orow[3 * x + 2] = in ? irow[3 * x + 2] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_warp_perspective(const uint8_t *__restrict__ img, const double *__restrict__ Hm,
+                                                          uint8_t *__restrict__ out, int H, int W) {
+    const int n = blockIdx.z;
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double M[9];
+    if (threadIdx.x == 0) { double T[9]; invert3(Hm + 9 * n, T); for (int k = 0; k < 9; ++k) M[k] = T[k]; }
+    __syncthreads();
+    if (x >= W) return;
+    const int bw = warp_block_w(H, W);
+    const int bx = (x / bw) * bw;
+    const RowBase rb = row_base(M, bx, y);
+    int X, Y;
+    src_coord(M, rb, x - bx, X, Y);
+    const uint8_t *s = img + (size_t)n * H * W * 3;
+    const uchar3 v = bilinear_tap4<false>(s, nullptr, 0, H, W, X, Y);
+    uint8_t *o = out + (((size_t)n * H + y) * W + x) * 3;
+    o[0] = v.x; o[1] = v.y; o[2] = v.z;
+}
+
+}  // namespace fusg
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace fusg;
+
+static size_t warp_smem_bytes(int H, int W) {
+    const int crop_bytes = H * W * 3;
+    const int src_pad = (crop_bytes + 127) & ~127;
+    return (size_t)src_pad + (size_t)MAX_HW * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + sizeof(WarpSmemHeader) + 128;
+}
+
+extern "C" size_t fusg_warp_workspace_bytes(int B) {
+    if (B <= 0) return 0;
+    return (size_t)B * N_TEX * 9 * sizeof(double);
+}
+
+extern "C" int fusg_visibility(const double *K, const double *E, const double *kp3d, uint8_t *vis, int32_t *pts,
+                               int32_t *areas, int B, int H, int W, void *stream) {
+    if (!K || !E || !kp3d || !vis || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_visibility<<<B, 256, 0, st>>>(K, E, nullptr, kp3d, vis, pts, areas, H, W);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_get_planes(const uint8_t *img, const int32_t *kp, uint8_t *planes, int B, int H, int W, void *stream) {
+    if (!img || !kp || !planes || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
+    if (H > 65535 || B > 65535) return FUSG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_get_planes<<<dim3(H, N_TEX, B), 256, 0, st>>>(img, kp, planes, H, W);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_find_homography(const int32_t *src, const int32_t *dst, int n, double *Hm, uint8_t *ok, int N, void *stream) {
+    if (!src || !dst || !Hm || !ok || N <= 0) return FUSG_ERR_ARG;
+    if (n < 4 || n > 6) return FUSG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_find_homography<<<(N + 63) / 64, 64, 0, st>>>(src, dst, n, Hm, ok, N);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8_t *out, int N, int H, int W, void *stream) {
+    if (!img || !Hm || !out || N <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
+    if (H > 65535 || N > 65535) return FUSG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_warp_perspective<<<dim3((W + 255) / 256, H, N), 256, 0, st>>>(img, Hm, out, H, W);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp, const double *K,
+                               const double *E_src, const double *E_dst, const double *kp3d, uint8_t *warped, uint8_t *vis,
+                               int8_t *plane_j, double *H12, void *workspace, size_t workspace_bytes, int B, int H, int W,
+                               void *stream) {
+    if (!src || !src_kp || !dst_kp || !K || !E_src || !E_dst || !kp3d || !warped || !vis || !plane_j || !workspace) return FUSG_ERR_ARG;
+    if (B <= 0) return FUSG_ERR_ARG;
+    if (H < 8 || W < 8 || H > MAX_HW || W > MAX_HW) return FUSG_ERR_UNSUPPORTED;
+    if (workspace_bytes < fusg_warp_workspace_bytes(B)) return FUSG_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *Minv = reinterpret_cast<double *>(workspace);
+    static bool attr_set = false;
+    const size_t smem = warp_smem_bytes(H, W);
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW, MAX_HW)) != cudaSuccess)
+            return fusg_check_launch();
+        attr_set = true;
+    }
+    k_visibility<<<2 * B, 256, 0, st>>>(K, E_src, E_dst, kp3d, vis, nullptr, nullptr, H, W);
+    k_homography<<<(B * N_TEX + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
+    k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);
+    fusg_count_launch(3);
+    return fusg_check_launch();
+}
