@@ -1,0 +1,666 @@
+// conv.cu -- VUNet convolution engine for sm_100a (include/fusg.h: fusg_conv2d and helpers).
+//
+// Reference semantics: MyConv2d / NiN / Residual / DownSample / UpSample('subpixel') / Sampler /
+// DepthToSpace / SpaceToDepth of vunet/layers.py:21-221, as they are composed by
+// vunet/models.py:17-484.  One launch = one convolution with everything the reference wraps
+// around it fused in: channel concat of two inputs (K-loop over two TMA descriptors), bias,
+// residual add, Sampler noise, ELU for the next pre-activated layer, sub-pixel addressing.
+//
+// Two kernels, same epilogue:
+//   k_conv_tc      implicit GEMM on the 5th-gen tensor cores: M = 128 output pixels
+//                  (Wt x Ht x Bt box), N = up to 128 output channels, K = taps x channels.
+//                  A tiles are fetched by 4-D tiled TMA straight from the NHWC activation with the
+//                  tap offset folded into the box coordinate -- out-of-bounds zero fill IS the
+//                  convolution padding (and elementStrides = 2 IS the stride) -- B tiles by 2-D TMA
+//                  from the folded weight matrix; both land 128B/64B-swizzled, K-major, and are
+//                  consumed by tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator in
+//                  TMEM (double buffered).  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM
+//                  alloc), 2..5 = epilogue (tcgen05.ld -> registers -> global).  Persistent over tiles.
+//   k_conv_direct  CUDA-core direct convolution with fp32 accumulation; used for the fp32
+//                  verification build and as the in-library cross-check of k_conv_tc.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/fusg.h"
+#include "fusg_common.h"
+
+namespace fusg {
+
+// ------------------------------------------------------------------------------------------------
+// shared epilogue
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+struct OutAddr { size_t pix; int ch; int Ct, Ht, Wt, py, px; };
+
+// logical destination of output channel group starting at n (16-aligned) for pixel (y,x)
+__device__ __forceinline__ OutAddr out_address(const fusg_conv_out &o, int cout, int Ho, int Wo, int b, int y, int x, int n) {
+    OutAddr a;
+    switch (o.mode) {
+        default:
+        case FUSG_OUT_PLAIN: a.Ct = cout; a.Ht = Ho; a.Wt = Wo; a.py = y; a.px = x; a.ch = n; break;
+        case FUSG_OUT_D2S: {
+            const int cq = cout >> 2, blk = n / cq;
+            a.Ct = cq; a.Ht = 2 * Ho; a.Wt = 2 * Wo; a.py = 2 * y + (blk >> 1); a.px = 2 * x + (blk & 1); a.ch = n - blk * cq;
+            break;
+        }
+        case FUSG_OUT_S2D:
+            a.Ct = 4 * cout; a.Ht = Ho >> 1; a.Wt = Wo >> 1; a.py = y >> 1; a.px = x >> 1; a.ch = (((y & 1) << 1) + (x & 1)) * cout + n;
+            break;
+        case FUSG_OUT_D2S_BLOCK:
+            a.Ct = cout; a.Ht = 2 * Ho; a.Wt = 2 * Wo; a.py = 2 * y + (o.blk >> 1); a.px = 2 * x + (o.blk & 1); a.ch = n;
+            break;
+    }
+    a.pix = ((size_t)b * a.Ht + a.py) * a.Wt + a.px;
+    return a;
+}
+
+// v[16]: fp32 accumulators of channels n..n+15 of output pixel (b,y,x); applies bias, residual,
+// noise and writes every output slot.
+template <typename T>
+__device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, int Ho, int Wo, int b, int y, int x, int n, float *v) {
+    const int nvalid = min(16, d.cout - n);
+    if (nvalid <= 0) return;
+    const size_t opix = ((size_t)b * Ho + y) * Wo + x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(d.bias + n + i);
+    if (d.residual) {
+        const T *r = reinterpret_cast<const T *>(d.residual) + opix * d.cout + n;
+        if (nvalid == 16) {
+            if constexpr (sizeof(T) == 2) {
+                const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(r)), q1 = __ldg(reinterpret_cast<const uint4 *>(r) + 1);
+                const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+                    v[2 * i] += __bfloat162float(h.x);
+                    v[2 * i + 1] += __bfloat162float(h.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += (float)r[i];
+            }
+        } else {
+            for (int i = 0; i < nvalid; ++i) v[i] += (float)r[i];
+        }
+    }
+    float z[16];
+    bool need_z = false;
+#pragma unroll
+    for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s) need_z = need_z || (d.outs[s].ptr != nullptr && d.outs[s].source == 1);
+    if (need_z) {
+        const float *e = d.noise + opix * d.cout + n;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = v[i] + (i < nvalid ? __ldg(e + i) : 0.f);
+    }
+#pragma unroll
+    for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s) {
+        const fusg_conv_out &o = d.outs[s];
+        if (o.ptr == nullptr) continue;
+        const float *val = o.source == 1 ? z : v;
+        const OutAddr a = out_address(o, d.cout, Ho, Wo, b, y, x, n);
+        if (o.layout == 1) {                                 // NCHW fp32, unrounded
+            float *p = reinterpret_cast<float *>(o.ptr);
+            const size_t plane = (size_t)a.Ht * a.Wt;
+            const size_t base = ((size_t)b * a.Ct + a.ch) * plane + (size_t)a.py * a.Wt + a.px;
+            for (int i = 0; i < nvalid; ++i) p[base + (size_t)i * plane] = o.elu ? elu1(val[i]) : val[i];
+        } else if constexpr (sizeof(T) == 2) {
+            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(o.ptr) + a.pix * a.Ct + a.ch;
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // ELU is taken of the bf16-rounded raw value, so a consumer that re-derives it from
+                // the stored raw tensor gets the same bits.
+                float f0 = __bfloat162float(__float2bfloat16_rn(val[2 * i])), f1 = __bfloat162float(__float2bfloat16_rn(val[2 * i + 1]));
+                if (o.elu) { f0 = elu1(f0); f1 = elu1(f1); }
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                w[i] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+            if (nvalid == 16) {
+                reinterpret_cast<uint4 *>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+                for (int i = 0; i < nvalid; ++i) p[i] = reinterpret_cast<const __nv_bfloat16 *>(w)[i];
+            }
+        } else {
+            float *p = reinterpret_cast<float *>(o.ptr) + a.pix * a.Ct + a.ch;
+            for (int i = 0; i < nvalid; ++i) p[i] = o.elu ? elu1(val[i]) : val[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_conv_direct: thread = (output pixel, group of 16 output channels)
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+constexpr int DC_CHUNK = 32;   // channels staged per step
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_direct(const __grid_constant__ fusg_conv_desc d, int Ho, int Wo) {
+    __shared__ float s_w[16][DC_CHUNK + 1];
+    const long long total = (long long)d.B * Ho * Wo;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n0 = blockIdx.y * 16;
+    const bool active = pix < total;
+    int b = 0, y = 0, x = 0;
+    if (active) { b = (int)(pix / ((long long)Ho * Wo)); const int r = (int)(pix - (long long)b * Ho * Wo); y = r / Wo; x = r - y * Wo; }
+    const int pad = d.ksize >> 1, ctot = d.c0 + d.c1, taps = d.ksize * d.ksize;
+    const T *wbase = reinterpret_cast<const T *>(d.weight);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / d.ksize, kx = tap - ky * d.ksize;
+        const int iy = y * d.stride + ky - pad, ix = x * d.stride + kx - pad;
+        const bool inb = active && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+        for (int c0 = 0; c0 < ctot; c0 += DC_CHUNK) {
+            const int cn = min(DC_CHUNK, ctot - c0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < 16 * DC_CHUNK; i += blockDim.x) {
+                const int n = i / DC_CHUNK, c = i - n * DC_CHUNK;
+                float w = 0.f;
+                if (c < cn && n0 + n < d.cout_pad) w = to_f<T>(wbase[((size_t)(n0 + n) * taps + tap) * ctot + c0 + c]);
+                s_w[n][c] = w;
+            }
+            __syncthreads();
+            if (inb) {
+                for (int c = 0; c < cn; ++c) {
+                    const int cc = c0 + c;
+                    float a;
+                    if (cc < d.c0) a = to_f<T>(reinterpret_cast<const T *>(d.in0)[(((size_t)b * d.H + iy) * d.W + ix) * d.pitch0 + cc]);
+                    else a = to_f<T>(reinterpret_cast<const T *>(d.in1)[(((size_t)b * d.H + iy) * d.W + ix) * d.pitch1 + (cc - d.c0)]);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) acc[n] = fmaf(a, s_w[n][c], acc[n]);
+                }
+            }
+        }
+    }
+    if (active) epilogue16<T>(d, Ho, Wo, b, y, x, n0, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / TMA / mbarrier)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            s_addr(dst)),
+        "l"(tm), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s_addr(dst)),
+        "l"(tm), "r"(s_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t desc = 0;
+    desc |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    desc |= (uint64_t)1 << 16;                          // LBO (ignored for swizzled K-major; canonical value 1)
+    desc |= (uint64_t)(sbo_bytes >> 4) << 32;
+    desc |= (uint64_t)1 << 46;
+    desc |= (uint64_t)layout_type << 61;
+    return desc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_conv_tc
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 192;
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_MAX_STAGES = 6;
+
+struct alignas(64) ConvTcParams {
+    CUtensorMap tmA0, tmA1, tmW;
+    fusg_conv_desc d;
+    int Ho, Wo;
+    int Wt, Ht, Bt;                 // tile box (output pixels)
+    int tiles_x, tiles_y, tiles_b;  // M-tile grid
+    int n_tiles, block_n;           // N tiling
+    int kc;                         // channels per k-block (64: 128B swizzle, 32: 64B swizzle)
+    int chunks0, chunks1;           // k-blocks per tap from in0 / in1
+    int num_kblocks;                // taps * (chunks0 + chunks1)
+    int stages;
+    int a_bytes, b_bytes;           // per stage
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned base (swizzle atoms)
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)p.stages * p.a_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * p.b_bytes);
+    uint64_t *full_bar = bars, *empty_bar = bars + TC_MAX_STAGES, *tfull_bar = bars + 2 * TC_MAX_STAGES, *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const fusg_conv_desc &d = p.d;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA0);
+        if (d.in1) tma_prefetch_desc(&p.tmA1);
+        tma_prefetch_desc(&p.tmW);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int taps = d.ksize * d.ksize, pad = d.ksize >> 1;
+    const int ctot = d.c0 + d.c1;
+    const int cpt = p.chunks0 + p.chunks1;        // k-blocks per tap
+
+    if (warp == 0) {
+        // =================== TMA producer ===================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+                const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt;
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    const int tap = kb / cpt, cidx = kb - tap * cpt;
+                    const int ky = tap / d.ksize, kx = tap - ky * d.ksize;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + p.b_bytes));
+                    const int ix0 = ox0 * d.stride + kx - pad, iy0 = oy0 * d.stride + ky - pad;
+                    int kcol;                                  // column in the [cout][taps*ctot] weight matrix
+                    if (cidx < p.chunks0) {
+                        tma_load_4d(sA + (size_t)stage * p.a_bytes, &p.tmA0, &full_bar[stage], cidx * p.kc, ix0, iy0, b0);
+                        kcol = tap * ctot + cidx * p.kc;
+                    } else {
+                        tma_load_4d(sA + (size_t)stage * p.a_bytes, &p.tmA1, &full_bar[stage], (cidx - p.chunks0) * p.kc, ix0, iy0, b0);
+                        kcol = tap * ctot + d.c0 + (cidx - p.chunks0) * p.kc;
+                    }
+                    tma_load_2d(sB + (size_t)stage * p.b_bytes, &p.tmW, &full_bar[stage], kcol, nt * p.block_n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =================== MMA issuer ===================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, K-major both, N, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+            const uint32_t layout_type = p.kc == 64 ? 2u : 4u;     // SWIZZLE_128B : SWIZZLE_64B
+            const uint32_t sbo = (uint32_t)p.kc * 2u * 8u;          // 8 rows of one swizzle span
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = s_addr(sA + (size_t)stage * p.a_bytes), b_addr = s_addr(sB + (size_t)stage * p.b_bytes);
+                    const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
+                    for (int ks = 0; ks < p.kc / 16; ++ks) {
+                        // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
+                        umma_bf16(d_tmem, a_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =================== epilogue warps (2..5) ===================
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;                         // tile row == TMEM lane
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+            const int wt = row % p.Wt, ht = (row / p.Wt) % p.Ht, bt = row / (p.Wt * p.Ht);
+            const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+            for (int c = 0; c < p.block_n; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_base + (uint32_t)c, r);
+                tmem_ld_wait();
+                if (b < d.B) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    epilogue16<__nv_bfloat16>(d, p.Ho, p.Wo, b, oy, ox, nt * p.block_n + c, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout / weight helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void k_fold_weightnorm(const float *__restrict__ v, const float *__restrict__ g, T *__restrict__ w, int cout, int cin, int ks,
+                                  int cout_pad, int cin_pad) {
+    // one CTA per (padded) output channel
+    const int n = blockIdx.x;
+    const int taps = ks * ks, len = cin * taps;
+    __shared__ float red[32];
+    float ss = 0.f;
+    if (n < cout) for (int i = threadIdx.x; i < len; i += blockDim.x) { const float a = v[(size_t)n * len + i]; ss += a * a; }
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    const float scale = n < cout ? g[n] / sqrtf(red[0]) : 0.f;
+    for (int i = threadIdx.x; i < taps * cin_pad; i += blockDim.x) {
+        const int tap = i / cin_pad, c = i - tap * cin_pad;
+        float val = 0.f;
+        if (n < cout && c < cin) val = v[((size_t)n * cin + c) * taps + tap] * scale;
+        w[((size_t)n * taps + tap) * cin_pad + c] = from_f<T>(val);
+    }
+}
+
+template <typename T>
+__global__ void k_nchw_to_nhwc(const float *__restrict__ in, T *__restrict__ out, int C, int HW, int cpad, int elu, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*HW*cpad
+    if (i >= total) return;
+    const int c = (int)(i % cpad);
+    const size_t bp = i / cpad;
+    const size_t b = bp / HW, pix = bp % HW;
+    float v = 0.f;
+    if (c < C) { v = in[(b * C + c) * HW + pix]; if (elu) v = elu1(v); }
+    out[i] = from_f<T>(v);
+}
+
+template <typename T>
+__global__ void k_nhwc_to_nchw(const T *__restrict__ in, float *__restrict__ out, int C, int HW, int pitch, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*C*HW (output order)
+    if (i >= total) return;
+    const size_t pix = i % HW;
+    const size_t bc = i / HW;
+    const size_t b = bc / C, c = bc % C;
+    out[i] = to_f<T>(in[(b * HW + pix) * pitch + c]);
+}
+
+template <typename T>
+__global__ void k_elu(const T *__restrict__ in, T *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = from_f<T>(elu1(to_f<T>(in[i])));
+}
+
+}  // namespace fusg
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace fusg;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static int conv_out_size(int in, int ks, int stride) { return (in + 2 * (ks / 2) - ks) / stride + 1; }
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static bool tc_supported(const fusg_conv_desc &d, int Ho, int Wo) {
+    if (d.dtype != FUSG_DTYPE_BF16) return false;
+    if (d.c0 % 32 != 0 || (d.in1 && d.c1 % 32 != 0)) return false;
+    if (d.cout_pad % 16 != 0) return false;
+    if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
+    if (d.cout_pad > 128 && d.cout_pad % 128 != 0) return false;
+    if (d.pitch0 % 8 != 0 || (d.in1 && d.pitch1 % 8 != 0)) return false;   // 16-byte global strides for TMA
+    return get_encode() != nullptr;
+}
+
+static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
+    ConvTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = d;
+    p.Ho = Ho; p.Wo = Wo;
+    p.Wt = Wo < 128 ? Wo : 128;
+    p.Ht = (128 / p.Wt) < Ho ? (128 / p.Wt) : Ho;
+    p.Bt = 128 / (p.Wt * p.Ht);
+    p.tiles_x = Wo / p.Wt; p.tiles_y = Ho / p.Ht; p.tiles_b = (d.B + p.Bt - 1) / p.Bt;
+    p.block_n = d.cout_pad < 128 ? d.cout_pad : 128;
+    p.n_tiles = d.cout_pad / p.block_n;
+    const bool k64 = (d.c0 % 64 == 0) && (!d.in1 || d.c1 % 64 == 0);
+    p.kc = k64 ? 64 : 32;
+    p.chunks0 = d.c0 / p.kc;
+    p.chunks1 = d.in1 ? d.c1 / p.kc : 0;
+    const int taps = d.ksize * d.ksize;
+    p.num_kblocks = taps * (p.chunks0 + p.chunks1);
+    p.a_bytes = TC_BLOCK_M * p.kc * 2;
+    p.b_bytes = p.block_n * p.kc * 2;
+    // B tiles must start 1024-aligned too (swizzle atom): round the per-stage size up
+    p.b_bytes = (p.b_bytes + 1023) & ~1023;
+    int stages = (200 * 1024) / (p.a_bytes + p.b_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages > p.num_kblocks) stages = p.num_kblocks < 2 ? 2 : p.num_kblocks;
+    p.stages = stages;
+    int cols = 2 * p.block_n;
+    p.tmem_cols = cols < 32 ? 32 : cols;
+
+    PFN_encodeTiled enc = get_encode();
+    const CUtensorMapSwizzle sw = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    auto encodeA = [&](CUtensorMap *tm, const void *ptr, int c, int pitch) -> bool {
+        cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)d.W * pitch * 2, (cuuint64_t)d.H * d.W * pitch * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.Wt * d.stride), (cuuint32_t)(p.Ht * d.stride), (cuuint32_t)p.Bt};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+        return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!encodeA(&p.tmA0, d.in0, d.c0, d.pitch0)) return FUSG_ERR_UNSUPPORTED;
+    if (d.in1 && !encodeA(&p.tmA1, d.in1, d.c1, d.pitch1)) return FUSG_ERR_UNSUPPORTED;
+    {
+        const int ktot = taps * (d.c0 + d.c1);
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.cout_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.block_n};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.weight), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FUSG_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    k_conv_tc<<<grid, TC_THREADS, smem, st>>>(p);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
+    if (!desc || !desc->in0 || !desc->weight || !desc->bias) return FUSG_ERR_ARG;
+    const fusg_conv_desc &d = *desc;
+    if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.c0 <= 0 || d.cout <= 0 || d.cout_pad < d.cout) return FUSG_ERR_ARG;
+    if ((d.ksize != 1 && d.ksize != 3) || (d.stride != 1 && d.stride != 2)) return FUSG_ERR_UNSUPPORTED;
+    if (d.in1 == nullptr && d.c1 != 0) return FUSG_ERR_ARG;
+    if (d.dtype != FUSG_DTYPE_BF16 && d.dtype != FUSG_DTYPE_F32) return FUSG_ERR_ARG;
+    bool any_out = false, need_noise = false;
+    for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s) {
+        if (!d.outs[s].ptr) continue;
+        any_out = true;
+        if (d.outs[s].source == 1) need_noise = true;
+        if (d.outs[s].mode == FUSG_OUT_D2S && (d.cout % 4 != 0 || (d.cout / 4) % 16 != 0)) return FUSG_ERR_UNSUPPORTED;
+    }
+    if (!any_out || (need_noise && !d.noise)) return FUSG_ERR_ARG;
+    const int Ho = conv_out_size(d.H, d.ksize, d.stride), Wo = conv_out_size(d.W, d.ksize, d.stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    int impl = d.impl;
+    if (impl == FUSG_IMPL_AUTO) impl = tc_supported(d, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT;
+    if (impl == FUSG_IMPL_TCGEN05) {
+        if (!tc_supported(d, Ho, Wo)) return FUSG_ERR_UNSUPPORTED;
+        return launch_tc(d, Ho, Wo, st);
+    }
+    const long long total = (long long)d.B * Ho * Wo;
+    dim3 grid((unsigned)((total + 127) / 128), (unsigned)((d.cout_pad + 15) / 16));
+    if (d.dtype == FUSG_DTYPE_BF16) k_conv_direct<__nv_bfloat16><<<grid, 128, 0, st>>>(d, Ho, Wo);
+    else k_conv_direct<float><<<grid, 128, 0, st>>>(d, Ho, Wo);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_fold_weightnorm(const float *v, const float *g, void *w_out, int cout, int cin, int ksize, int cout_pad, int cin_pad,
+                                    int dtype, void *stream) {
+    if (!v || !g || !w_out || cout <= 0 || cin <= 0 || cout_pad < cout || cin_pad < cin) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FUSG_DTYPE_BF16) k_fold_weightnorm<__nv_bfloat16><<<cout_pad, 256, 0, st>>>(v, g, (__nv_bfloat16 *)w_out, cout, cin, ksize, cout_pad, cin_pad);
+    else k_fold_weightnorm<float><<<cout_pad, 256, 0, st>>>(v, g, (float *)w_out, cout, cin, ksize, cout_pad, cin_pad);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_nchw_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int cpad, int elu, int dtype, void *stream) {
+    if (!in || !out || B <= 0 || C <= 0 || cpad < C) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t total = (size_t)B * H * W * cpad;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == FUSG_DTYPE_BF16) k_nchw_to_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16 *)out, C, H * W, cpad, elu, total);
+    else k_nchw_to_nhwc<float><<<grid, 256, 0, st>>>(in, (float *)out, C, H * W, cpad, elu, total);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_nhwc_to_nchw(const void *in, float *out, int B, int C, int H, int W, int pitch, int dtype, void *stream) {
+    if (!in || !out || B <= 0 || C <= 0 || pitch < C) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t total = (size_t)B * C * H * W;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == FUSG_DTYPE_BF16) k_nhwc_to_nchw<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)in, out, C, H * W, pitch, total);
+    else k_nhwc_to_nchw<float><<<grid, 256, 0, st>>>((const float *)in, out, C, H * W, pitch, total);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream) {
+    if (!in || !out || n == 0) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == FUSG_DTYPE_BF16) k_elu<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, n);
+    else k_elu<float><<<grid, 256, 0, st>>>((const float *)in, (float *)out, n);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}

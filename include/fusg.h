@@ -97,6 +97,77 @@ int fusg_find_homography(const int32_t *src, const int32_t *dst, int n, double *
  */
 int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8_t *out, int N, int H, int W, void *stream);
 
+
+/* ====================================================================================== */
+/* VUNet convolution engine                                                                */
+/* ====================================================================================== */
+
+#define FUSG_DTYPE_BF16 0
+#define FUSG_DTYPE_F32 1          /* fp32 verification build: direct kernels only */
+
+#define FUSG_IMPL_AUTO 0
+#define FUSG_IMPL_TCGEN05 1       /* implicit-GEMM tcgen05/TMEM kernel fed by TMA (bf16 only) */
+#define FUSG_IMPL_DIRECT 2        /* CUDA-core direct convolution (any dtype; the in-library check) */
+
+#define FUSG_OUT_PLAIN 0          /* out[b, y, x, n]                                              */
+#define FUSG_OUT_D2S 1            /* DepthToSpace(2), vunet/layers.py:173-194 (block-major):      */
+                                  /*   out[b, 2y+blk/2, 2x+blk%2, n % (cout/4)], blk = n/(cout/4) */
+#define FUSG_OUT_S2D 2            /* SpaceToDepth(2), vunet/layers.py:197-221:                    */
+                                  /*   out[b, y/2, x/2, ((y%2)*2 + x%2)*cout + n]                 */
+#define FUSG_OUT_D2S_BLOCK 3      /* one block of a DepthToSpace of a channel concat              */
+                                  /*   (vunet/models.py:85-86): out[b, 2y+blk/2, 2x+blk%2, n]     */
+
+#define FUSG_CONV_MAX_OUTS 6
+
+/* One output of a convolution launch.  value = conv + bias (+ residual); source 1 adds the
+ * Sampler noise (vunet/layers.py:163-167). */
+typedef struct fusg_conv_out {
+    void *ptr;          /* NULL = unused slot                                                    */
+    int32_t source;     /* 0: value, 1: value + noise                                            */
+    int32_t elu;        /* 0: raw, 1: ELU(raw) -- pre-activation for the next layer              */
+    int32_t layout;     /* 0: NHWC in the activation dtype, 1: NCHW fp32 (API-visible tensors)   */
+    int32_t mode;       /* FUSG_OUT_*                                                            */
+    int32_t blk;        /* block index for FUSG_OUT_D2S_BLOCK                                    */
+    int32_t reserved;
+} fusg_conv_out;
+
+/*
+ * One fused convolution: MyConv2d (vunet/layers.py:21-39) together with whatever the reference
+ * wraps around it -- channel concat of two inputs (torch.cat([x, skip], 1)), bias, residual add
+ * (Residual, layers.py:98-102), Sampler noise (layers.py:163-167), ELU of the result for the next
+ * pre-activated layer (Activation, layers.py:6-18), DepthToSpace / SpaceToDepth addressing
+ * (layers.py:173-221).  Activations are NHWC; a channel-sliced view is expressed by pitch > c.
+ */
+typedef struct fusg_conv_desc {
+    const void *in0, *in1;      /* NHWC inputs, activation dtype; in1 may be NULL                */
+    int32_t c0, c1;             /* channels read from in0 / in1 (multiples of 16 for tcgen05)    */
+    int32_t pitch0, pitch1;     /* elements between consecutive pixels (>= c)                    */
+    int32_t B, H, W;            /* input batch / height / width                                  */
+    int32_t ksize, stride;      /* 1 or 3 (padding ksize/2); 1 or 2                              */
+    const void *weight;         /* [cout_pad][ksize*ksize][c0+c1], activation dtype (folded w_norm) */
+    const float *bias;          /* [cout_pad] fp32                                               */
+    int32_t cout, cout_pad;     /* real / stored output channels                                 */
+    const void *residual;       /* NHWC [B,Ho,Wo,cout] activation dtype, or NULL                 */
+    const float *noise;         /* NHWC fp32 [B,Ho,Wo,cout] or NULL                              */
+    fusg_conv_out outs[FUSG_CONV_MAX_OUTS];
+    int32_t dtype;              /* FUSG_DTYPE_*                                                  */
+    int32_t impl;               /* FUSG_IMPL_*                                                   */
+} fusg_conv_desc;
+
+int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
+
+/* weight_norm fold (vunet/layers.py:29-31): w = g * v / ||v||, repacked from [cout][cin][k][k]
+ * fp32 to [cout_pad][k*k][cin_pad] in `dtype` (zero padded).  Run once per load_state_dict. */
+int fusg_fold_weightnorm(const float *v, const float *g, void *w_out, int cout, int cin, int ksize,
+                         int cout_pad, int cin_pad, int dtype, void *stream);
+
+/* NCHW fp32 [B,C,H,W] -> NHWC [B,H,W,cpad] in `dtype` (zero padded channels), optional ELU. */
+int fusg_nchw_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int cpad, int elu, int dtype, void *stream);
+/* NHWC `dtype` [B,H,W,pitch] (first C channels) -> NCHW fp32 [B,C,H,W]. */
+int fusg_nhwc_to_nchw(const void *in, float *out, int B, int C, int H, int W, int pitch, int dtype, void *stream);
+/* NHWC elementwise ELU (activation dtype) over n elements. */
+int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
