@@ -33,6 +33,13 @@ def _load():
         "fusg_get_planes": ([vp] * 3 + [i, i, i, vp], i),
         "fusg_find_homography": ([vp, vp, i, vp, vp, i, vp], i),
         "fusg_warp_perspective": ([vp] * 3 + [i, i, i, vp], i),
+        "fusg_conv2d": ([vp, vp], i),
+        "fusg_conv2d_select": ([vp], i),
+        "fusg_fold_weightnorm": ([vp, vp, vp, i, i, i, i, i, i, vp], i),
+        "fusg_nchw_to_nhwc": ([vp, vp, i, i, i, i, i, i, i, vp], i),
+        "fusg_nhwc_to_nchw": ([vp, vp, i, i, i, i, i, i, vp], i),
+        "fusg_to_image": ([vp, vp, i, i, i, vp], i),
+        "fusg_elu": ([vp, vp, sz, i, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     const int total_tiles = m_tiles * p.n_tiles;
-    const int taps = d.ksize * d.ksize, pad = d.ksize >> 1;
+    const int pad = d.ksize >> 1;
     const int ctot = d.c0 + d.c1;
     const int cpt = p.chunks0 + p.chunks1;        // k-blocks per tap
 
@@ -486,6 +486,18 @@ __global__ void k_elu(const T *__restrict__ in, T *__restrict__ out, size_t n) {
     if (i < n) out[i] = from_f<T>(elu1(to_f<T>(in[i])));
 }
 
+__global__ void k_to_image(const float *__restrict__ in, uint8_t *__restrict__ out, int HW, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*HW*3 (output order)
+    if (i >= total) return;
+    const int c = (int)(i % 3);
+    const size_t bp = i / 3;
+    const size_t b = bp / HW, pix = bp % HW;
+    // numpy evaluates (x + 1.) / 2 * 255 in fp32 for a float32 array
+    float v = (in[(b * 3 + c) * HW + pix] + 1.f) / 2.f * 255.f;
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[i] = (uint8_t)v;                                               // astype(np.uint8): truncation
+}
+
 }  // namespace fusg
 
 // ================================================================================================
@@ -592,6 +604,12 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     return fusg_check_launch();
 }
 
+extern "C" int fusg_conv2d_select(const fusg_conv_desc *desc) {
+    if (!desc) return FUSG_ERR_ARG;
+    const int Ho = conv_out_size(desc->H, desc->ksize, desc->stride), Wo = conv_out_size(desc->W, desc->ksize, desc->stride);
+    return tc_supported(*desc, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT;
+}
+
 extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
     if (!desc || !desc->in0 || !desc->weight || !desc->bias) return FUSG_ERR_ARG;
     const fusg_conv_desc &d = *desc;
@@ -651,6 +669,15 @@ extern "C" int fusg_nhwc_to_nchw(const void *in, float *out, int B, int C, int H
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (dtype == FUSG_DTYPE_BF16) k_nhwc_to_nchw<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)in, out, C, H * W, pitch, total);
     else k_nhwc_to_nchw<float><<<grid, 256, 0, st>>>((const float *)in, out, C, H * W, pitch, total);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_to_image(const float *in, uint8_t *out, int B, int H, int W, void *stream) {
+    if (!in || !out || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t total = (size_t)B * H * W * 3;
+    k_to_image<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, H * W, total);
     fusg_count_launch(1);
     return fusg_check_launch();
 }

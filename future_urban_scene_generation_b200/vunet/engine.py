@@ -69,6 +69,8 @@ class VunetEngine:
         self._wkey = None
         self._w = {}
         self.launches = 0
+        self.profile = None            # list -> per-launch (path, impl, flops, start, end) CUDA-event records
+        self.noise_provider = None     # callable(B,C,H,W) -> NHWC fp32 device tensor; None = CPU torch.randn (reference semantics)
         self.raw_skips = True          # also keep raw copies of NiN skips (needed by the sub-forward API)
 
     # ------------------------------------------------------------------ plumbing
@@ -165,8 +167,20 @@ class VunetEngine:
             d.outs[i].mode, d.outs[i].blk = o.mode, o.blk
         d.dtype = self.cdtype
         d.impl = self.impl if self.dtype == "bf16" else IMPL_DIRECT
+        prof = self.profile
+        if prof is not None:
+            torch = self.torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            impl = d.impl if d.impl != IMPL_AUTO else _lib.lib().fusg_conv2d_select(C.byref(d))
+            Ho, Wo = (a0.H - 1) // stride + 1, (a0.W - 1) // stride + 1
+            e0.record()
         rc = _lib.lib().fusg_conv2d(C.byref(d), self._stream())
         _lib.check(rc, f"fusg_conv2d({path})")
+        if prof is not None:
+            e1.record()
+            # algorithmic FLOPs of the reference conv (real channels)
+            conv = self.m.convs[path]
+            prof.append((path, impl, 2.0 * B * Ho * Wo * conv.cout * conv.cin * k * k, e0, e1))
         self.launches += 1
 
     # ------------------------------------------------------------------ helpers building Acts
@@ -235,6 +249,8 @@ class VunetEngine:
     def draw_noise(self, B, Cn, H, W):
         """Sampler noise (layers.py:166): torch.randn on the CPU default generator, in the reference's
         order and NCHW shape; shipped to the device as NHWC fp32 for the conv epilogue."""
+        if self.noise_provider is not None:
+            return self.noise_provider(B, Cn, H, W)
         torch = self.torch
         eps = torch.randn(B, Cn, H, W)
         return eps.permute(0, 2, 3, 1).contiguous().to(self.device(), non_blocking=True)

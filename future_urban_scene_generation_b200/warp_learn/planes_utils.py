@@ -120,3 +120,16 @@ def to_image(x: Union[np.ndarray, "torch.Tensor"], from_LAB: bool):
         import cv2
         x = cv2.cvtColor(x, cv2.COLOR_LAB2BGR)
     return x
+
+
+def to_image_batch(x):
+    """to_image for a batch on the device: (B,3,H,W) fp32 CUDA tensor in [-1,1] -> (B,H,W,3) uint8 CUDA tensor
+    (same arithmetic as `to_image(..., from_LAB=False)`, libfusg.so: fusg_to_image)."""
+    torch = _lib.require_cuda()
+    assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
+    x = x.float().contiguous()
+    B, _, H, W = x.shape
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fusg_to_image(_lib.ptr(x), _lib.ptr(out), B, H, W, _lib.stream_ptr(torch)), "fusg_to_image")
+    return out

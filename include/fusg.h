@@ -155,6 +155,8 @@ typedef struct fusg_conv_desc {
 } fusg_conv_desc;
 
 int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
+/* Which kernel FUSG_IMPL_AUTO resolves to for this descriptor (FUSG_IMPL_TCGEN05 or FUSG_IMPL_DIRECT). */
+int fusg_conv2d_select(const fusg_conv_desc *desc);
 
 /* weight_norm fold (vunet/layers.py:29-31): w = g * v / ||v||, repacked from [cout][cin][k][k]
  * fp32 to [cout_pad][k*k][cin_pad] in `dtype` (zero padded).  Run once per load_state_dict. */
@@ -165,6 +167,10 @@ int fusg_fold_weightnorm(const float *v, const float *g, void *w_out, int cout, 
 int fusg_nchw_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int cpad, int elu, int dtype, void *stream);
 /* NHWC `dtype` [B,H,W,pitch] (first C channels) -> NCHW fp32 [B,C,H,W]. */
 int fusg_nhwc_to_nchw(const void *in, float *out, int B, int C, int H, int W, int pitch, int dtype, void *stream);
+/* to_image (warp_learn/planes_utils.py:96-118, from_LAB=False): NCHW fp32 in [-1,1] ->
+ * HWC uint8, x = clip((x + 1) / 2 * 255, 0, 255) with the reference's truncating cast.
+ *   in [B,3,H,W] f32 -> out [B,H,W,3] u8 */
+int fusg_to_image(const float *in, uint8_t *out, int B, int H, int W, void *stream);
 /* NHWC elementwise ELU (activation dtype) over n elements. */
 int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
 
