@@ -32,7 +32,9 @@ namespace fusg {
 // ------------------------------------------------------------------------------------------------
 // shared epilogue
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(x) = x > 0 ? x : exp(x) - 1.  __expf (ex2.approx) has ~2 ulp error at 1.0, i.e. an absolute error of
+// ~2e-7 on the negative branch: far below bf16 resolution and below the 1e-4 fp32 verification bar.
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
 struct OutAddr { size_t pix; int ch; int Ct, Ht, Wt, py, px; };
 
@@ -61,12 +63,12 @@ __device__ __forceinline__ OutAddr out_address(const fusg_conv_out &o, int cout,
 // v[16]: fp32 accumulators of channels n..n+15 of output pixel (b,y,x); applies bias, residual,
 // noise and writes every output slot.
 template <typename T>
-__device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, int Ho, int Wo, int b, int y, int x, int n, float *v) {
+__device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float *bias, int Ho, int Wo, int b, int y, int x, int n, float *v) {
     const int nvalid = min(16, d.cout - n);
     if (nvalid <= 0) return;
     const size_t opix = ((size_t)b * Ho + y) * Wo + x;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __ldg(d.bias + n + i);
+    for (int i = 0; i < 16; ++i) v[i] += bias[n + i];
     if (d.residual) {
         const T *r = reinterpret_cast<const T *>(d.residual) + opix * d.cout + n;
         if (nvalid == 16) {
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(128) k_conv_direct(const __grid_constant__ fus
             }
         }
     }
-    if (active) epilogue16<T>(d, Ho, Wo, b, y, x, n0, acc);
+    if (active) epilogue16<T>(d, d.bias, Ho, Wo, b, y, x, n0, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -273,7 +275,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // ------------------------------------------------------------------------------------------------
 // k_conv_tc
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_MAX_STAGES = 6;
 
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * p.b_bytes);
     uint64_t *full_bar = bars, *empty_bar = bars + TC_MAX_STAGES, *tfull_bar = bars + 2 * TC_MAX_STAGES, *tempty_bar = tfull_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    float *s_bias = reinterpret_cast<float *>(tmem_slot + 4);        // cout_pad floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fusg_conv_desc &d = p.d;
@@ -310,10 +314,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         if (d.in1) tma_prefetch_desc(&p.tmA1);
         tma_prefetch_desc(&p.tmW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.d.cout_pad; i += TC_THREADS) s_bias[i] = p.d.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -386,9 +391,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
         __syncwarp();
     } else {
-        // =================== epilogue warps (2..5) ===================
-        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        // =================== epilogue warps (2..9) ===================
+        // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share a lane quadrant and split the columns
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;                         // tile row == TMEM lane
+        const int ncols = p.block_n >= 32 ? p.block_n / 2 : (half == 0 ? p.block_n : 0);
+        const int c_begin = p.block_n >= 32 ? half * ncols : 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -398,16 +407,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-            for (int c = 0; c < p.block_n; c += 16) {
+            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c_begin);
+            if (ncols > 0) {
                 uint32_t r[16];
-                tmem_ld16(t_base + (uint32_t)c, r);
-                tmem_ld_wait();
-                if (b < d.B) {
+                tmem_ld16(t_base, r);
+                for (int c = 0; c < ncols; c += 16) {
+                    tmem_ld_wait();
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                    epilogue16<__nv_bfloat16>(d, p.Ho, p.Wo, b, oy, ox, nt * p.block_n + c, v);
+                    if (c + 16 < ncols) tmem_ld16(t_base + (uint32_t)(c + 16), r);      // prefetch the next chunk
+                    if (b < d.B) epilogue16<__nv_bfloat16>(d, s_bias, p.Ho, p.Wo, b, oy, ox, nt * p.block_n + c_begin + c, v);
                 }
             }
             tc_fence_before();
@@ -555,7 +565,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.b_bytes = p.block_n * p.kc * 2;
     // B tiles must start 1024-aligned too (swizzle atom): round the per-stage size up
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
-    int stages = (200 * 1024) / (p.a_bytes + p.b_bytes);
+    int stages = (196 * 1024) / (p.a_bytes + p.b_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages > p.num_kblocks) stages = p.num_kblocks < 2 ? 2 : p.num_kblocks;
     p.stages = stages;
@@ -584,7 +594,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FUSG_ERR_UNSUPPORTED;
     }
-    const size_t smem = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 /*align slack*/ + 256 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
