@@ -1,0 +1,62 @@
+"""Micro-benchmark of single VUNet layers through the engine (for ncu captures).
+usage: python scripts/conv_micro.py <layer> [B] [reps]
+  layer: nin6 | res128 | res128raw | res32 | cat64 | down128"""
+import os
+import sys
+from argparse import Namespace
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+
+layer = sys.argv[1] if len(sys.argv) > 1 else "res128"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+torch.manual_seed(0)
+m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).cuda().eval()
+e = m.engine()
+
+
+def rnd(c, h):
+    a = e._act(B, c, h, h)
+    a.raw.normal_()
+    a.elu.normal_()
+    return a
+
+
+if layer == "nin6":
+    x = rnd(32, 256)
+    fn = lambda: e.init_block("app_encoder_1", x, B)          # nin + 2 residuals
+    fn = lambda: e.conv("app_encoder_1.nin.layers.1", [(x, "elu")], outs=e._plain_outs(e._act(B, 128, 256, 256)), B=B)
+    flops = 2.0 * B * 65536 * 128 * 6
+elif layer == "res128":
+    x = rnd(128, 256)
+    fn = lambda: e.residual("app_encoder_1.residual_0", x, B=B)
+    flops = 2.0 * B * 65536 * 128 * 128 * 9
+elif layer == "res128raw":
+    x = rnd(128, 256)
+    fn = lambda: e.residual("app_encoder_1.residual_1", x, B=B, elu=False)
+    flops = 2.0 * B * 65536 * 128 * 128 * 9
+elif layer == "res32":
+    x = rnd(32, 256)
+    fn = lambda: e.residual("shape_encoder_1.residual_0", x, B=B)
+    flops = 2.0 * B * 65536 * 32 * 32 * 9
+elif layer == "cat64":
+    x, s = rnd(32, 256), rnd(32, 256)
+    fn = lambda: e.residual("shape_decoder_6.residual_0", x, s, B=B)
+    flops = 2.0 * B * 65536 * 64 * 32 * 9
+elif layer == "down128":
+    x = rnd(128, 256)
+    fn = lambda: e.down_block("app_encoder_1_a", x, B)
+    flops = 0
+for _ in range(2):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    fn()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"{layer} B={B}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s")
