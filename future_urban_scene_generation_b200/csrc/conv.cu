@@ -359,7 +359,7 @@ __device__ __forceinline__ void fast_chunk16(const FastEpi &fe, const float *s_b
 constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_BLOCK_M = 128;
-constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_STAGES = 16;
 
 struct alignas(64) ConvTcParams {
     CUtensorMap tmA0, tmA1, tmW;
@@ -372,7 +372,9 @@ struct alignas(64) ConvTcParams {
     int chunks0, chunks1;           // k-blocks per tap from in0 / in1
     int num_kblocks;                // taps * (chunks0 + chunks1)
     int stages;
-    int a_bytes, b_bytes;           // per stage
+    int a_bytes, b_bytes;           // per k-block
+    int group;                      // k-blocks per pipeline stage (one barrier round trip)
+    int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
     int tmem_cols;
     int fast_epi;                   // 1: lean epilogue applies
     FastEpi fe;
@@ -382,12 +384,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (swizzle atoms)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // [stages][group] A k-blocks | B k-blocks ([stages][group] streamed, or [num_kblocks] resident) | barriers | bias
     uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)p.stages * p.a_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * p.b_bytes);
+    uint8_t *sB = smem + (size_t)p.stages * p.group * p.a_bytes;
+    const size_t b_region = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + b_region);
     uint64_t *full_bar = bars, *empty_bar = bars + TC_MAX_STAGES, *tfull_bar = bars + 2 * TC_MAX_STAGES, *tempty_bar = tfull_bar + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-    float *s_bias = reinterpret_cast<float *>(tmem_slot + 4);        // cout_pad floats
+    uint64_t *w_bar = tempty_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
+    float *s_bias = reinterpret_cast<float *>(tmem_slot + 6);        // cout_pad floats, 16-byte aligned (float4 reads)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fusg_conv_desc &d = p.d;
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         tma_prefetch_desc(&p.tmW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+        mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -410,33 +416,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     const int total_tiles = m_tiles * p.n_tiles;
     const int pad = d.ksize >> 1;
-    const int ctot = d.c0 + d.c1;
     const int cpt = p.chunks0 + p.chunks1;        // k-blocks per tap
 
     if (warp == 0) {
         // =================== TMA producer ===================
         if (lane == 0) {
+            const int groups = p.num_kblocks / p.group;
+            const uint32_t stage_tx = (uint32_t)(p.group * (p.a_bytes + (p.w_resident ? 0 : p.b_bytes)));
+            if (p.w_resident) {
+                // the weight matrix of this N tile is loaded once per CTA
+                mbar_arrive_expect_tx(w_bar, (uint32_t)(p.num_kblocks * p.b_bytes));
+                for (int kb = 0; kb < p.num_kblocks; ++kb) tma_load_2d(sB + (size_t)kb * p.b_bytes, &p.tmW, w_bar, kb * p.kc, 0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
                 const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt;
-                for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                    const int tap = kb / cpt, cidx = kb - tap * cpt;
-                    const int ky = tap / d.ksize, kx = tap - ky * d.ksize;
+                const int ixb = ox0 * d.stride - pad, iyb = oy0 * d.stride - pad, n0 = nt * p.block_n;
+                int ky = 0, kx = 0, cidx = 0, kcol = 0;            // running k-block coordinates (no div/mod in the loop)
+                for (int grp = 0; grp < groups; ++grp) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + p.b_bytes));
-                    const int ix0 = ox0 * d.stride + kx - pad, iy0 = oy0 * d.stride + ky - pad;
-                    int kcol;                                  // column in the [cout][taps*ctot] weight matrix
-                    if (cidx < p.chunks0) {
-                        tma_load_4d(sA + (size_t)stage * p.a_bytes, &p.tmA0, &full_bar[stage], cidx * p.kc, ix0, iy0, b0);
-                        kcol = tap * ctot + cidx * p.kc;
-                    } else {
-                        tma_load_4d(sA + (size_t)stage * p.a_bytes, &p.tmA1, &full_bar[stage], (cidx - p.chunks0) * p.kc, ix0, iy0, b0);
-                        kcol = tap * ctot + d.c0 + (cidx - p.chunks0) * p.kc;
+                    mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                    uint8_t *a_dst = sA + (size_t)stage * p.group * p.a_bytes;
+                    uint8_t *b_dst = sB + (size_t)stage * p.group * p.b_bytes;
+                    for (int g = 0; g < p.group; ++g) {
+                        if (cidx < p.chunks0) tma_load_4d(a_dst, &p.tmA0, &full_bar[stage], cidx * p.kc, ixb + kx, iyb + ky, b0);
+                        else tma_load_4d(a_dst, &p.tmA1, &full_bar[stage], (cidx - p.chunks0) * p.kc, ixb + kx, iyb + ky, b0);
+                        if (!p.w_resident) { tma_load_2d(b_dst, &p.tmW, &full_bar[stage], kcol, n0); b_dst += p.b_bytes; }
+                        a_dst += p.a_bytes;
+                        kcol += p.kc;                              // weight columns are ordered (tap, in0 channels, in1 channels)
+                        if (++cidx == cpt) { cidx = 0; if (++kx == d.ksize) { kx = 0; ++ky; } }
                     }
-                    tma_load_2d(sB + (size_t)stage * p.b_bytes, &p.tmW, &full_bar[stage], kcol, nt * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -452,20 +464,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const int groups = p.num_kblocks / p.group;
+            if (p.w_resident) mbar_wait(w_bar, 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                for (int grp = 0; grp < groups; ++grp) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = s_addr(sA + (size_t)stage * p.a_bytes), b_addr = s_addr(sB + (size_t)stage * p.b_bytes);
-                    const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
-                    for (int ks = 0; ks < p.kc / 16; ++ks) {
-                        // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
-                        umma_bf16(d_tmem, a_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+                    uint32_t a_addr = s_addr(sA + (size_t)stage * p.group * p.a_bytes);
+                    uint32_t b_addr = p.w_resident ? s_addr(sB + (size_t)grp * p.group * p.b_bytes) : s_addr(sB + (size_t)stage * p.group * p.b_bytes);
+                    for (int g = 0; g < p.group; ++g) {
+                        const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
+                        for (int ks = 0; ks < p.kc / 16; ++ks) {
+                            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
+                            umma_bf16(d_tmem, a_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, (grp | g | ks) != 0 ? 1u : 0u);
+                        }
+                        a_addr += (uint32_t)p.a_bytes;
+                        b_addr += (uint32_t)p.b_bytes;
                     }
-                    umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+                    umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);                  // accumulator complete
@@ -656,11 +675,27 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.num_kblocks = taps * (p.chunks0 + p.chunks1);
     p.a_bytes = TC_BLOCK_M * p.kc * 2;
     p.b_bytes = p.block_n * p.kc * 2;
-    // B tiles must start 1024-aligned too (swizzle atom): round the per-stage size up
+    // B k-blocks must start 1024-aligned too (swizzle atom): round the size up
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
-    int stages = (196 * 1024) / (p.a_bytes + p.b_bytes);
+    const int smem_budget = 196 * 1024;
+    // weights resident when the whole (single) N tile fits next to a useful pipeline
+    p.w_resident = (p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
+    const int avail = smem_budget - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
+    const int kb_bytes = p.a_bytes + (p.w_resident ? 0 : p.b_bytes);
+    // group = k-blocks per barrier round trip: the largest divisor of num_kblocks that keeps the
+    // stage <= 64 KB and leaves >= 3 stages
+    int group = 1;
+    for (int g = 1; g <= p.num_kblocks; ++g) {
+        if (p.num_kblocks % g) continue;
+        if (g * kb_bytes > 64 * 1024) break;
+        if (avail / (g * kb_bytes) >= 3) group = g;
+    }
+    p.group = group;
+    int stages = avail / (group * kb_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    if (stages > p.num_kblocks) stages = p.num_kblocks < 2 ? 2 : p.num_kblocks;
+    const int groups_per_tile = p.num_kblocks / group;
+    if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile < 2 ? 2 : 2 * groups_per_tile;
+    if (stages < 2) stages = 2;
     p.stages = stages;
     int cols = 2 * p.block_n;
     p.tmem_cols = cols < 32 ? 32 : cols;
@@ -712,7 +747,8 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FUSG_ERR_UNSUPPORTED;
     }
-    const size_t smem = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 /*align slack*/ + 256 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/;
+    const size_t smem = (size_t)p.stages * p.group * p.a_bytes + (p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes) +
+                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
