@@ -151,6 +151,7 @@ def run_ours(args):
     from future_urban_scene_generation_b200.warp_learn import warp_batch
     from future_urban_scene_generation_b200.warp_learn.planes_utils import to_image_batch
     from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from future_urban_scene_generation_b200.parallel import shard_range, gather_crops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,7 +172,8 @@ def run_ours(args):
     eng = model.engine()
 
     # ---- synthetic inputs for this rank's contiguous shard of crops (SURVEY.md §8d generators)
-    first = rank * B
+    first, last = shard_range(world * B, rank, world)
+    assert last - first == B
     wb = synth.make_warp_batch(first, B)
     xs, ys = synth.make_vunet_inputs(first, B)
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
@@ -192,15 +194,12 @@ def run_ours(args):
         return noise_bank[key]
     staged_noise.i = 0
 
-    gathered = torch.empty((world * B, 256, 256, 3), dtype=torch.uint8, device=dev) if world > 1 else None
-
     def step(inp):
         res = warp_batch(inp["src"], inp["src_kp"], inp["dst_kp"], inp["K"], inp["E_src"], inp["E_dst"], inp["kp3d"], device=dev)
         x_tilde, _, _ = model(inp["y"], inp["x"])
         crops = to_image_batch(x_tilde)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, crops)
-        return res, crops
+        allc = gather_crops(crops, world * B)          # NCCL all-gather of completed crops (N > 1), the only collective
+        return res, (allc[first:last] if world > 1 else allc)
 
     def barrier():
         torch.cuda.synchronize()

@@ -35,6 +35,7 @@ def _load():
         "fusg_warp_perspective": ([vp] * 3 + [i, i, i, vp], i),
         "fusg_conv2d": ([vp, vp], i),
         "fusg_conv2d_select": ([vp], i),
+        "fusg_sizeof_conv_desc": ([], sz),
         "fusg_fold_weightnorm": ([vp, vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_nchw_to_nhwc": ([vp, vp, i, i, i, i, i, i, i, vp], i),
         "fusg_nhwc_to_nchw": ([vp, vp, i, i, i, i, i, i, vp], i),

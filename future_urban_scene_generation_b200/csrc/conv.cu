@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "../../include/fusg.h"
 #include "fusg_common.h"
 
@@ -508,9 +509,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int wt = row % p.Wt, ht = (row / p.Wt) % p.Ht, bt = row / (p.Wt * p.Ht);
             const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
             const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c_begin);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c_begin);
             if (ncols > 0) {
                 uint32_t r[16];
                 tmem_ld16(t_base, r);
@@ -677,7 +678,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.b_bytes = p.block_n * p.kc * 2;
     // B k-blocks must start 1024-aligned too (swizzle atom): round the size up
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
-    const int smem_budget = 196 * 1024;
+    const int smem_budget = 200 * 1024;
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
     const int avail = smem_budget - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
@@ -693,8 +694,6 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.group = group;
     int stages = avail / (group * kb_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    const int groups_per_tile = p.num_kblocks / group;
-    if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile < 2 ? 2 : 2 * groups_per_tile;
     if (stages < 2) stages = 2;
     p.stages = stages;
     int cols = 2 * p.block_n;
@@ -767,6 +766,8 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     fusg_count_launch(1);
     return fusg_check_launch();
 }
+
+extern "C" size_t fusg_sizeof_conv_desc(void) { return sizeof(fusg_conv_desc); }
 
 extern "C" int fusg_conv2d_select(const fusg_conv_desc *desc) {
     if (!desc) return FUSG_ERR_ARG;

@@ -155,6 +155,8 @@ typedef struct fusg_conv_desc {
 } fusg_conv_desc;
 
 int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
+/* sizeof(fusg_conv_desc) as this library was compiled (binding self-check). */
+size_t fusg_sizeof_conv_desc(void);
 /* Which kernel FUSG_IMPL_AUTO resolves to for this descriptor (FUSG_IMPL_TCGEN05 or FUSG_IMPL_DIRECT). */
 int fusg_conv2d_select(const fusg_conv_desc *desc);
 

@@ -1,0 +1,66 @@
+"""Runs the imported reference (cv2 + numpy, /root/reference) on seeded synthetic crops and commits
+what the oracle must reproduce: tests/golden/warp_golden.json
+
+  per crop: visibility dicts of both poses, get_planes sha1 per plane, plane vertices,
+            warp_unwarp_planes()[0] sha1 per plane, and -- because OpenCV's LM refinement of the
+            6-point side planes cannot be reproduced bit for bit -- whether the oracle's
+            plane was identical to the reference's when this file was generated.
+Only runs where /root/reference exists (the build container)."""
+import hashlib
+import json
+import os
+import sys
+
+os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.append("/root/reference")
+import cv2
+import numpy as np
+from warp_learn.online_visibility import compute_visibility, pascal_texture_planes
+from warp_learn.planes_utils import get_planes, warp_unwarp_planes
+
+from oracle import warp_oracle as O
+from future_urban_scene_generation_b200 import synth
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+N = 160
+H = W = 256
+cases = []
+n_planes = n_equal = 0
+for idx in range(N):
+    p = synth.make_pose_pair(idx)
+    img = synth.make_crop(idx)
+    kp3d = {k: p["kp3d"][i] for i, k in enumerate(synth.KP_NAMES)}
+    vs = compute_visibility(p["E_src"], p["K"], kp3d, H, W)
+    vd = compute_visibility(p["E_dst"], p["K"], kp3d, H, W)
+    ks = {k: p["kp2d_src"][i] for i, k in enumerate(synth.KP_NAMES)}
+    kd = {k: p["kp2d_dst"][i] for i, k in enumerate(synth.KP_NAMES)}
+    sp, skp, sv = get_planes(img, ks, 'car', vs)
+    dp, dkp, dv = get_planes(img, kd, 'car', vd)
+    wr, _ = warp_unwarp_planes(sp, skp, dkp, sv, dv, 'car', pascal_texture_planes)
+    wo, vis, pj, H12 = O.warp_fused(img, p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
+    assert [bool(vs[k]) for k in O.PLANE_NAMES] == [bool(v) for v in vis[0]], idx
+    assert [bool(vd[k]) for k in O.PLANE_NAMES] == [bool(v) for v in vis[1]], idx
+    assert np.array_equal(sp, O.get_planes(img, p["src_kp"])), idx
+    equal = [bool(np.array_equal(wr[j], wo[j])) for j in range(5)]
+    written = [bool(wr[j].any()) for j in range(5)]
+    n_planes += sum(written)
+    n_equal += sum(e for e, w in zip(equal, written) if w)
+    cases.append({
+        "idx": idx,
+        "vis_src": [int(bool(vs[k])) for k in O.PLANE_NAMES], "vis_dst": [int(bool(vd[k])) for k in O.PLANE_NAMES],
+        "src_kp": p["src_kp"].tolist(), "dst_kp": p["dst_kp"].tolist(),
+        "planes_sha1": [sha(sp[j]) for j in range(5)],
+        "warped_sha1": [sha(wr[j]) for j in range(5)],
+        "warped_nonzero": written,
+        "oracle_identical": equal,
+        "plane_j": [int(v) for v in pj],
+    })
+gold = {"cv2_version": cv2.__version__, "n": N, "hw": [H, W], "written_planes": n_planes, "oracle_identical_planes": n_equal, "cases": cases}
+json.dump(gold, open(os.path.join(ROOT, "tests", "golden", "warp_golden.json"), "w"))
+print(f"{N} crops: {n_planes} written planes, oracle identical on {n_equal} ({100.0 * n_equal / n_planes:.1f}%)")

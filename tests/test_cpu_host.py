@@ -1,0 +1,155 @@
+"""CPU suite, part 2: host logic and the C-ABI boundary (no compute calls without a GPU)."""
+import ctypes
+import hashlib
+import os
+import re
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from future_urban_scene_generation_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fusg.h")).read()
+    names = sorted(set(re.findall(r"\b(fusg_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    L = _lib.lib()
+    assert L.fusg_version() >= 100
+    assert L.fusg_warp_workspace_bytes(3) == 3 * 5 * 9 * 8
+    assert L.fusg_kernel_launches() >= 0
+
+
+def test_ctypes_struct_matches_c_layout():
+    from future_urban_scene_generation_b200 import _lib
+    from future_urban_scene_generation_b200.vunet.engine import ConvDesc, ConvOut
+    assert ctypes.sizeof(ConvOut) == 32
+    assert ctypes.sizeof(ConvDesc) == _lib.lib().fusg_sizeof_conv_desc()
+
+
+def test_argument_validation_without_gpu():
+    from future_urban_scene_generation_b200 import _lib
+    L = _lib.lib()
+    assert L.fusg_warp_fused(None, None, None, None, None, None, None, None, None, None, None, None, 0, 1, 256, 256, None) == -1
+    assert L.fusg_conv2d(None, None) == -1
+    assert L.fusg_visibility(None, None, None, None, None, None, 1, 256, 256, None) == -1
+    assert L.fusg_find_homography(None, None, 4, None, None, 1, None) == -1
+
+
+def test_vunet_module_checkpoint_contract():
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from future_urban_scene_generation_b200._lib import FusgError
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True))
+    sd = m.state_dict()
+    keys = list(sd.keys())
+    assert len(keys) == 336
+    assert hashlib.sha1("\n".join(keys).encode()).hexdigest() == "6a36f5dfc3dc8ab32fb79a78d759d8d28e09d940"
+    assert keys[:3] == ["app_encoder_1.nin.layers.1.conv.bias", "app_encoder_1.nin.layers.1.conv.weight_g", "app_encoder_1.nin.layers.1.conv.weight_v"]
+    assert sd["shape_decoder_1.residual_0.layers.2.conv.weight_v"].shape == (512, 1024, 3, 3)
+    assert sd["shape_decoder_6.conv.conv.weight_g"].shape == (3, 1, 1, 1)
+    assert sum(v.numel() for v in sd.values()) == 45225158
+    # weight_norm initialisation: g = ||v||
+    v, g = sd["app_bottleneck.conv.weight_v"], sd["app_bottleneck.conv.weight_g"]
+    assert torch.allclose(v.flatten(1).norm(dim=1), g.flatten())
+    from oracle import vunet_oracle as VO
+    res = m.load_state_dict(VO.make_state_dict(3), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    bad = dict(VO.make_state_dict(3))
+    bad.pop("app_bottleneck.conv.bias")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    with pytest.raises(NotImplementedError):
+        Vunet_fix_res(Namespace(up_mode='conv2d_t', w_norm=True, drop_prob=0.2, vunet_256=True))
+    with pytest.raises(NotImplementedError):
+        Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=False))
+    # no CPU fallback: a CPU module refuses to run
+    with pytest.raises(FusgError):
+        m.eval()(torch.zeros(1, 3, 256, 256), torch.zeros(1, 6, 256, 256))
+    # training mode (active Dropout2d) is refused, not silently different
+    if torch.cuda.is_available():
+        with pytest.raises(NotImplementedError):
+            m.cuda().train()(torch.zeros(1, 3, 256, 256).cuda(), torch.zeros(1, 6, 256, 256).cuda())
+
+
+def test_warp_mirror_surface_and_constants():
+    from future_urban_scene_generation_b200.warp_learn import online_visibility as ov, planes_utils as pu
+    assert list(ov.pascal_texture_planes['car'].keys()) == ['left', 'right', 'roof', 'front', 'back']
+    assert [len(v) for v in ov.pascal_texture_planes['car'].values()] == [6, 6, 4, 4, 4]
+    assert ov.pascal_texture_planes['chair'] == {}
+    for fn in (ov.compute_visibility, pu.get_planes, pu.warp_unwarp_planes, pu.planes_to_torch, pu.to_image):
+        assert callable(fn)
+    # host-side pieces that need no GPU
+    x = torch.linspace(-1.2, 1.2, 3 * 4 * 5).view(3, 4, 5)
+    img = pu.to_image(x, from_LAB=False)
+    want = np.clip((np.transpose(x.numpy(), (1, 2, 0)) + 1.) / 2 * 255, 0, 255).astype(np.uint8)
+    assert img.dtype == np.uint8 and np.array_equal(img, want)
+    planes = np.random.default_rng(0).integers(0, 256, (5, 8, 8, 3), dtype=np.uint8)
+    t = pu.planes_to_torch(planes, to_LAB=False)
+    assert t.shape == (5, 3, 8, 8) and t.dtype == torch.float32
+    assert torch.allclose(t, (torch.from_numpy(np.transpose(np.float32(planes) / 255., (0, 3, 1, 2))) - 0.5) / 0.5)
+    with pytest.raises(ValueError):
+        ov._extrinsic34(np.ones((4, 4)))
+    if not torch.cuda.is_available():
+        from future_urban_scene_generation_b200._lib import FusgError
+        with pytest.raises(FusgError):
+            ov.compute_visibility(np.eye(4), np.eye(3), {k: np.zeros(3) for k in ov._KP_NAMES}, 256, 256)
+
+
+def test_synthetic_inputs_are_deterministic_and_in_frame():
+    from future_urban_scene_generation_b200 import synth
+    a, b = synth.make_warp_batch(5, 6), synth.make_warp_batch(5, 6)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    assert a["src"].shape == (6, 256, 256, 3) and a["src_kp"].dtype == np.int32
+    for k in ("src_kp", "dst_kp"):
+        assert a[k].min() >= 0 and a[k].max() <= 255
+    x, y = synth.make_vunet_inputs(0, 2)
+    assert x.shape == (2, 6, 256, 256) and y.shape == (2, 3, 256, 256) and x.dtype == np.float32
+    assert -1.0 <= x.min() and x.max() <= 1.0
+
+
+def test_shard_range_partitions_contiguously():
+    from future_urban_scene_generation_b200.parallel import shard_range
+    for n in (0, 1, 7, 64, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+                assert e0 == b1
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    from future_urban_scene_generation_b200.parallel import shard_range, gather_crops
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full = torch.arange(n_total * 4 * 4 * 3, dtype=torch.int64).remainder(251).to(torch.uint8).view(n_total, 4, 4, 3)
+    b, e = shard_range(n_total, rank, world)
+    out = gather_crops(full[b:e].clone(), n_total)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_gather_crops_world_size_2_gloo(n_total):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + n_total
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=10) for _ in range(2))
+    assert res == {0: True, 1: True}

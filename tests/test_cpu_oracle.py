@@ -1,0 +1,176 @@
+"""CPU suite, part 1: the oracle against OpenCV and against the committed reference goldens."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from future_urban_scene_generation_b200 import synth
+from oracle import warp_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+cv2 = pytest.importorskip("cv2")
+
+
+def _sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_fillpoly_matches_cv2_in_frame():
+    rng = np.random.default_rng(0)
+    for t in range(1500):
+        H, W = (256, 256) if t % 2 else (96, 160)
+        n = 4 if t % 3 else 6
+        pts = np.stack([rng.integers(0, W, n), rng.integers(0, H, n)], 1).astype(np.int32)
+        if t % 7 == 0:
+            pts[1] = pts[0]                    # duplicate vertex
+        if t % 11 == 0:
+            pts[:, 1] = pts[0, 1]              # all horizontal
+        if t % 13 == 0:
+            pts[:, 0] = pts[0, 0]              # all vertical
+        ref = cv2.fillPoly(np.zeros((H, W), np.uint8), [pts], 1)
+        got = O.fill_poly(np.zeros((H, W), np.uint8), pts, 1)
+        assert np.array_equal(ref, got), pts.tolist()
+
+
+def test_jacobi_eig_solve_invert_are_bit_exact():
+    rng = np.random.default_rng(1)
+    for t in range(100):
+        n = 9 if t % 2 else 8
+        A = rng.standard_normal((n, n))
+        A = A @ A.T
+        ok, w, v = cv2.eigen(A)
+        W_, V_ = O.jacobi(A)
+        assert np.array_equal(w.ravel(), W_) and np.array_equal(v, V_)
+    for t in range(100):
+        J = rng.standard_normal((12, 8)) * np.array([1e2, 1e2, 1, 1e2, 1e2, 1, 1e4, 1e4])
+        A = cv2.mulTransposed(J, True)
+        b = rng.standard_normal(8)
+        assert np.array_equal(cv2.solve(A, b.reshape(8, 1), flags=cv2.DECOMP_EIG)[1].ravel(), O.solve_eig(A, b))
+        assert np.array_equal(cv2.invert(A, flags=cv2.DECOMP_EIG)[1], O.invert_eig(A))
+        M = rng.standard_normal((3, 3))
+        assert np.array_equal(cv2.invert(M)[1], O.invert3(M))
+
+
+def _perspective_pair(rng, n):
+    src = rng.integers(20, 236, (n, 2)).astype(np.int32)
+    Ht = np.array([[1 + rng.uniform(-.2, .2), rng.uniform(-.2, .2), rng.uniform(-15, 15)],
+                   [rng.uniform(-.2, .2), 1 + rng.uniform(-.2, .2), rng.uniform(-15, 15)],
+                   [rng.uniform(-5e-4, 5e-4), rng.uniform(-5e-4, 5e-4), 1]])
+    p = np.c_[src, np.ones(n)] @ Ht.T
+    return src, np.int32(p[:, :2] / p[:, 2:] + rng.uniform(-1, 1, (n, 2)))
+
+
+def test_findhomography_4pt_bit_exact_6pt_close():
+    rng = np.random.default_rng(2)
+    for t in range(400):
+        src, dst = _perspective_pair(rng, 4)
+        Hc, _ = cv2.findHomography(src, dst)
+        Ho = O.find_homography(src, dst)
+        assert (Hc is None) == (Ho is None)
+        if Hc is not None:
+            assert np.array_equal(Hc, Ho)
+    # None <=> all src or all dst points share an x or a y
+    for deg in range(4):
+        src, dst = _perspective_pair(rng, 4)
+        (src if deg < 2 else dst)[:, deg % 2] = 7
+        assert cv2.findHomography(src, dst)[0] is None and O.find_homography(src, dst) is None
+    # 6 points: OpenCV's LM refinement stops on a step-size test and cannot be matched bit for bit;
+    # the mapped pixel coordinates agree far below the 1/32-px warp grid in the bulk of cases
+    errs = []
+    pts = np.array([[0, 0, 1], [255, 0, 1], [0, 255, 1], [255, 255, 1], [128, 128, 1.]])
+    for t in range(300):
+        src, dst = _perspective_pair(rng, 6)
+        Hc, _ = cv2.findHomography(src, dst)
+        Ho = O.find_homography(src, dst)
+        a, b = pts @ Hc.T, pts @ Ho.T
+        errs.append(np.abs(a[:, :2] / a[:, 2:] - b[:, :2] / b[:, 2:]).max())
+    assert np.median(errs) < 1e-5, np.median(errs)
+
+
+def test_warpperspective_bit_exact_given_h():
+    rng = np.random.default_rng(3)
+    for t in range(8):
+        H, W = (256, 256) if t % 2 else (90, 130)
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        src, dst = _perspective_pair(rng, 4)
+        Hm, _ = cv2.findHomography(np.minimum(src, [W - 1, H - 1]), np.minimum(dst, [W - 1, H - 1]))
+        if Hm is None:
+            continue
+        ref = cv2.warpPerspective(img, Hm, dsize=(W, H))
+        assert np.array_equal(ref, O.warp_perspective(img, Hm))
+
+
+def test_oracle_reproduces_reference_goldens():
+    """tests/golden/warp_golden.json was written by scripts/make_golden_warp.py from the imported
+    reference (cv2 4.13.0): visibility, get_planes and 4-point warped planes are identical;
+    LM-refined planes are identical except for the handful recorded at generation time."""
+    gold = json.load(open(os.path.join(GOLD, "warp_golden.json")))
+    H, W = gold["hw"]
+    n_written = n_equal = 0
+    for case in gold["cases"][:60]:
+        idx = case["idx"]
+        p = synth.make_pose_pair(idx, H, W)
+        img = synth.make_crop(idx, H, W)
+        assert p["src_kp"].tolist() == case["src_kp"] and p["dst_kp"].tolist() == case["dst_kp"]
+        warped, vis, pj, _ = O.warp_fused(img, p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
+        assert vis[0].tolist() == case["vis_src"] and vis[1].tolist() == case["vis_dst"]
+        assert pj.tolist() == case["plane_j"]
+        planes = O.get_planes(img, p["src_kp"])
+        assert [_sha(planes[j]) for j in range(5)] == case["planes_sha1"]
+        for j in range(5):
+            same = _sha(warped[j]) == case["warped_sha1"][j]
+            if case["oracle_identical"][j]:
+                assert same, (idx, j)
+            if case["warped_nonzero"][j]:
+                n_written += 1
+                n_equal += same
+            if j >= 2:                                  # 4-point planes never differ
+                assert same, (idx, j)
+    assert n_equal >= 0.97 * n_written
+
+
+def test_fused_equals_stepwise_reference_order():
+    """orc_warp_fused == compute_visibility x2 -> get_planes -> warp_unwarp_planes()[0]."""
+    for idx in range(6):
+        p = synth.make_pose_pair(idx, 128, 128)
+        img = synth.make_crop(idx, 128, 128)
+        warped, vis, pj, H12 = O.warp_fused(img, p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
+        vs = O.compute_visibility(p["E_src"], p["K"], p["kp3d"], 128, 128)
+        vd = O.compute_visibility(p["E_dst"], p["K"], p["kp3d"], 128, 128)
+        sv = np.array([vs[n] for n in O.PLANE_NAMES[:5]], np.uint8)
+        dv = np.array([vd[n] for n in O.PLANE_NAMES[:5]], np.uint8)
+        planes = O.get_planes(img, p["src_kp"])
+        w2, _, pj2, _ = O.warp_unwarp_planes(planes, p["src_kp"], p["dst_kp"], sv, dv)
+        assert np.array_equal(warped, w2) and np.array_equal(pj, pj2)
+
+
+def test_vunet_oracle_matches_golden_fingerprint():
+    import torch
+    from oracle import vunet_oracle as VO
+    gold = json.load(open(os.path.join(GOLD, "vunet_golden.json")))
+    sd = VO.make_state_dict(0)
+    assert hashlib.sha1("\n".join(sd.keys()).encode()).hexdigest() == gold["key_sha1"] == "6a36f5dfc3dc8ab32fb79a78d759d8d28e09d940"
+    assert sum(v.numel() for v in sd.values()) == gold["n_params"] == 45225158
+    case = gold["cases"][0]
+    x, y = synth.make_vunet_inputs(case["start"], case["B"])
+    torch.manual_seed(case["noise_seed"])
+    with torch.no_grad():
+        o_x, o_mua, o_mus = VO.forward(sd, torch.from_numpy(y), torch.from_numpy(x))
+    for name, t in (("x_tilde", o_x), ("mu_app0", o_mua[0]), ("mu_shape1", o_mus[1])):
+        flat = t.flatten()
+        idx = torch.linspace(0, flat.numel() - 1, 64).long()
+        assert (flat[idx] - torch.tensor(case[name]["samples"])).abs().max().item() < 1e-4, name
+
+
+def test_space_depth_permutations_are_block_major():
+    import torch
+    from oracle import vunet_oracle as VO
+    x = torch.arange(2 * 3 * 4 * 6, dtype=torch.float32).view(2, 3, 4, 6)
+    s = VO.space_to_depth(x)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                assert torch.equal(s[:, (dy * 2 + dx) * 3 + c], x[:, c, dy::2, dx::2])
+    assert torch.equal(VO.depth_to_space(s), x)
