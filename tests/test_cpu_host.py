@@ -153,3 +153,29 @@ def test_gather_crops_world_size_2_gloo(n_total):
         assert p.exitcode == 0
     res = dict(q.get(timeout=10) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def test_import_shim_serves_reference_import_sites():
+    """with the shim first on sys.path the reference's own import statements
+    resolve to the B200 modules (and, where the reference checkout is present, its untouched
+    submodules keep resolving to the reference)."""
+    import subprocess
+    import sys
+    shim = os.path.join(ROOT, "future_urban_scene_generation_b200", "shim")
+    ref = "/root/reference"
+    code = (
+        "import sys, warnings; warnings.filterwarnings('ignore');"
+        f"sys.path[:0] = [{ROOT!r}, {shim!r}];"
+        + (f"sys.path.append({ref!r});" if os.path.isdir(ref) else "")
+        + "from vunet.models import Vunet_fix_res;"
+        "from warp_learn.online_visibility import pascal_texture_planes, compute_visibility;"
+        "from warp_learn.planes_utils import to_image, warp_unwarp_planes, get_planes, planes_to_torch;"
+        "assert Vunet_fix_res.__module__.startswith('future_urban_scene_generation_b200');"
+        "assert get_planes.__module__.startswith('future_urban_scene_generation_b200');"
+        + ("from warp_learn.models import G_Resnet, get_icn_inputs; import warp_learn.models as wm;"
+           "assert wm.__file__.startswith('/root/reference');"
+           "assert wm.planes_to_torch.__module__.startswith('future_urban_scene_generation_b200');" if os.path.isdir(ref) else "")
+        + "print('ok')")
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
