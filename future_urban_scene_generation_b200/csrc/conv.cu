@@ -581,16 +581,30 @@ __global__ void k_fold_weightnorm(const float *__restrict__ v, const float *__re
     }
 }
 
+// NCHW fp32 -> NHWC (zero-padded channels, optional ELU).  One thread per pixel: the per-channel reads
+// are coalesced across the warp, the writes are 16-byte pieces of the thread's own contiguous pixel row.
 template <typename T>
-__global__ void k_nchw_to_nhwc(const float *__restrict__ in, T *__restrict__ out, int C, int HW, int cpad, int elu, size_t total) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*HW*cpad
-    if (i >= total) return;
-    const int c = (int)(i % cpad);
-    const size_t bp = i / cpad;
-    const size_t b = bp / HW, pix = bp % HW;
-    float v = 0.f;
-    if (c < C) { v = in[(b * C + c) * HW + pix]; if (elu) v = elu1(v); }
-    out[i] = from_f<T>(v);
+__global__ void k_nchw_to_nhwc(const float *__restrict__ in, T *__restrict__ out, int C, int HW, int cpad, int elu, size_t npix) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*HW
+    if (i >= npix) return;
+    const size_t b = i / HW, pix = i - b * HW;
+    const float *src = in + b * C * HW + pix;
+    T *dst = out + i * cpad;
+    for (int c0 = 0; c0 < cpad; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float a = 0.f;
+            if (c0 + k < C) { a = __ldg(src + (size_t)(c0 + k) * HW); if (elu) a = elu1(a); }
+            v[k] = a;
+        }
+        if constexpr (sizeof(T) == 2) {
+            *reinterpret_cast<uint4 *>(dst + c0) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        } else {
+            *reinterpret_cast<float4 *>(dst + c0) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(dst + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
 }
 
 template <typename T>
@@ -818,11 +832,12 @@ extern "C" int fusg_fold_weightnorm(const float *v, const float *g, void *w_out,
 
 extern "C" int fusg_nchw_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int cpad, int elu, int dtype, void *stream) {
     if (!in || !out || B <= 0 || C <= 0 || cpad < C) return FUSG_ERR_ARG;
+    if (cpad % 8 != 0) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t total = (size_t)B * H * W * cpad;
-    const unsigned grid = (unsigned)((total + 255) / 256);
-    if (dtype == FUSG_DTYPE_BF16) k_nchw_to_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16 *)out, C, H * W, cpad, elu, total);
-    else k_nchw_to_nhwc<float><<<grid, 256, 0, st>>>(in, (float *)out, C, H * W, cpad, elu, total);
+    const size_t npix = (size_t)B * H * W;
+    const unsigned grid = (unsigned)((npix + 255) / 256);
+    if (dtype == FUSG_DTYPE_BF16) k_nchw_to_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16 *)out, C, H * W, cpad, elu, npix);
+    else k_nchw_to_nhwc<float><<<grid, 256, 0, st>>>(in, (float *)out, C, H * W, cpad, elu, npix);
     fusg_count_launch(1);
     return fusg_check_launch();
 }

@@ -9,7 +9,7 @@
 // Three launches per batch, one C call:
 //   k_visibility   one CTA per (crop, pose): polygon scanline coverage as 32-pixel bit words,
 //                  painter's-order occlusion, area ratio test -> 7 flags.
-//   k_homography   one thread per (crop, plane): gating, DLT (OpenCV Jacobi) + LM, inverse map.
+//   k_homography   one warp per (crop, plane): gating, DLT (OpenCV Jacobi) + LM, inverse map.
 //   k_warp         one CTA per crop: source crop staged in shared memory by TMA bulk copies,
 //                  per-plane polygon bit mask in shared memory, per-row conservative active
 //                  span, cv2-exact 1/32-px fixed-point bilinear gather, rows written back with
@@ -23,6 +23,7 @@
 #include "../../include/fusg.h"
 #include "fusg_common.h"
 #include "warp_geom.cuh"
+#include "warp_geom_thread.cuh"
 
 namespace fusg {
 
@@ -78,11 +79,17 @@ __device__ void visibility_pose(VisShared &sm, const double *K, const double *E,
         }
     int cnt_abs[N_VIS], cnt_occ[N_VIS];
     for (int p = 0; p < N_VIS; ++p) cnt_abs[p] = cnt_occ[p] = 0;
-    const int nwords = (W + 31) >> 5;
-    for (int y = tid; y < H; y += blockDim.x) {
+    // every polygon lies inside the bounding box of the 12 projected keypoints: only those rows / words can hold pixels
+    int bx0 = sm.vx[0], bx1 = sm.vx[0], by0 = sm.vy[0], by1 = sm.vy[0];
+    for (int k = 1; k < N_KP; ++k) {
+        bx0 = min(bx0, sm.vx[k]); bx1 = max(bx1, sm.vx[k]);
+        by0 = min(by0, sm.vy[k]); by1 = max(by1, sm.vy[k]);
+    }
+    const int w0 = bx0 >> 5, w1 = bx1 >> 5;
+    for (int y = by0 + tid; y <= by1; y += blockDim.x) {
         int lo[N_VIS][MAX_RANGES], hi[N_VIS][MAX_RANGES], rc[N_VIS];
         for (int p = 0; p < N_VIS; ++p) rc[p] = poly_row_ranges(px[p], py[p], c_plane_n[p], y, lo[p], hi[p]);
-        for (int w = 0; w < nwords; ++w) {
+        for (int w = w0; w <= w1; ++w) {
             unsigned bits[N_VIS];
             for (int p = 0; p < N_VIS; ++p) bits[p] = ranges_word(lo[p], hi[p], rc[p], w);
             for (int p = 0; p < N_VIS; ++p) {
@@ -137,18 +144,80 @@ __global__ void __launch_bounds__(256) k_visibility(const double *__restrict__ K
 }
 
 // ============================================================================================
-// k_homography: thread per (crop, source plane)
+// k_homography: one warp per (crop, source plane)
 // workspace layout per crop: Minv[5][9] f64 (inverse maps indexed by SOURCE plane i)
 // ============================================================================================
-__global__ void __launch_bounds__(128) k_homography(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
-                                                    const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j,
-                                                    double *__restrict__ H12, double *__restrict__ Minv, int B, int H, int W) {
+constexpr int HG_WARPS = 4;
+
+__global__ void __launch_bounds__(HG_WARPS * 32) k_homography(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                             const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j,
+                                                             double *__restrict__ H12, double *__restrict__ Minv, int B, int H, int W) {
+    __shared__ HomogScratch scratch[HG_WARPS];
+    __shared__ int pts[HG_WARPS][24];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * HG_WARPS + warp;
+    if (t >= B * N_TEX) return;
+    const int b = t / N_TEX, i = t % N_TEX;
+    const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
+    const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
+    bool bad = sv[0] == 0xff || dv[0] == 0xff;            // projected keypoint out of frame
+    if (lane < N_KP) {
+        const bool oob = sk[2 * lane] < 0 || sk[2 * lane] >= W || sk[2 * lane + 1] < 0 || sk[2 * lane + 1] >= H ||
+                         dk[2 * lane] < 0 || dk[2 * lane] >= W || dk[2 * lane + 1] < 0 || dk[2 * lane + 1] >= H;
+        bad = bad || oob;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    double Hm[9], Mi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
+    int j;
+    if (bad) {
+        j = -2;
+    } else {
+        j = plane_target(i, sv, dv);
+        if (j >= 0) {
+            const int n = c_plane_n[i];
+            if (lane < n) {
+                pts[warp][2 * lane] = sk[2 * c_plane_kp[i][lane]];
+                pts[warp][2 * lane + 1] = sk[2 * c_plane_kp[i][lane] + 1];
+                pts[warp][12 + 2 * lane] = dk[2 * c_plane_kp[j][lane]];
+                pts[warp][12 + 2 * lane + 1] = dk[2 * c_plane_kp[j][lane] + 1];
+            }
+            __syncwarp();
+            // H21 is only ever used through its "is None" test, which is the same degeneracy
+            // test as H12's (symmetric in src/dst) -- planes_utils.py:72-74
+            if (!find_homography_warp(scratch[warp], lane, pts[warp], pts[warp] + 12, n, Hm)) {
+                j = -1;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Hm[k] = 0;
+            } else {
+                invert3(Hm, Mi);
+            }
+        }
+    }
+    if (lane == 0) {
+        plane_j[t] = (int8_t)j;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
+        if (H12) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
+        }
+    }
+}
+
+
+// thread-per-(crop, plane) variant: same results, better throughput once tens of thousands of
+// solves are in flight (each solve is a long dependent fp64 chain; here 32x more of them overlap)
+__global__ void __launch_bounds__(128) k_homography_thread(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                           const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j,
+                                                           double *__restrict__ H12, double *__restrict__ Minv, int B, int H, int W) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * N_TEX) return;
     const int b = t / N_TEX, i = t % N_TEX;
     const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
     int j = -1;
-    bool bad = sv[0] == 0xff || dv[0] == 0xff;            // projected keypoint out of frame
+    bool bad = sv[0] == 0xff || dv[0] == 0xff;
     const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
     for (int k = 0; k < N_KP && !bad; ++k) {
         if (sk[2 * k] < 0 || sk[2 * k] >= W || sk[2 * k + 1] < 0 || sk[2 * k + 1] >= H) bad = true;
@@ -167,9 +236,7 @@ __global__ void __launch_bounds__(128) k_homography(const int32_t *__restrict__ 
                 s[2 * k] = sk[2 * c_plane_kp[i][k]]; s[2 * k + 1] = sk[2 * c_plane_kp[i][k] + 1];
                 d[2 * k] = dk[2 * c_plane_kp[j][k]]; d[2 * k + 1] = dk[2 * c_plane_kp[j][k] + 1];
             }
-            // H21 is only ever used through its "is None" test, which is the same degeneracy
-            // test as H12's (symmetric in src/dst) -- planes_utils.py:72-74
-            if (!find_homography(s, d, n, Hm)) {
+            if (!find_homography_thread(s, d, n, Hm)) {
                 j = -1;
                 for (int k = 0; k < 9; ++k) Hm[k] = 0;
             } else {
@@ -182,16 +249,22 @@ __global__ void __launch_bounds__(128) k_homography(const int32_t *__restrict__ 
     if (H12) for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
 }
 
-__global__ void k_find_homography(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
-                                  double *__restrict__ H, uint8_t *__restrict__ ok, int N) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(HG_WARPS * 32) k_find_homography(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
+                                                                  double *__restrict__ H, uint8_t *__restrict__ ok, int N) {
+    __shared__ HomogScratch scratch[HG_WARPS];
+    __shared__ int pts[HG_WARPS][24];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * HG_WARPS + warp;
     if (t >= N) return;
-    int s[12], d[12];
-    for (int k = 0; k < 2 * n; ++k) { s[k] = src[2 * n * t + k]; d[k] = dst[2 * n * t + k]; }
+    if (lane < 2 * n) { pts[warp][lane] = src[2 * n * t + lane]; pts[warp][12 + lane] = dst[2 * n * t + lane]; }
+    __syncwarp();
     double Hm[9];
-    const bool good = find_homography(s, d, n, Hm);
-    for (int k = 0; k < 9; ++k) H[9 * t + k] = good ? Hm[k] : 0.0;
-    ok[t] = good ? 1 : 0;
+    const bool good = find_homography_warp(scratch[warp], lane, pts[warp], pts[warp] + 12, n, Hm);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H[9 * t + k] = good ? Hm[k] : 0.0;
+        ok[t] = good ? 1 : 0;
+    }
 }
 
 // ============================================================================================
@@ -522,7 +595,7 @@ extern "C" int fusg_visibility(const double *K, const double *E, const double *k
                                int32_t *areas, int B, int H, int W, void *stream) {
     if (!K || !E || !kp3d || !vis || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    k_visibility<<<B, 256, 0, st>>>(K, E, nullptr, kp3d, vis, pts, areas, H, W);
+    k_visibility<<<B, 128, 0, st>>>(K, E, nullptr, kp3d, vis, pts, areas, H, W);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
@@ -540,7 +613,7 @@ extern "C" int fusg_find_homography(const int32_t *src, const int32_t *dst, int 
     if (!src || !dst || !Hm || !ok || N <= 0) return FUSG_ERR_ARG;
     if (n < 4 || n > 6) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    k_find_homography<<<(N + 63) / 64, 64, 0, st>>>(src, dst, n, Hm, ok, N);
+    k_find_homography<<<(N + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src, dst, n, Hm, ok, N);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
@@ -571,8 +644,10 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
             return fusg_check_launch();
         attr_set = true;
     }
-    k_visibility<<<2 * B, 256, 0, st>>>(K, E_src, E_dst, kp3d, vis, nullptr, nullptr, H, W);
-    k_homography<<<(B * N_TEX + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
+    k_visibility<<<2 * B, 128, 0, st>>>(K, E_src, E_dst, kp3d, vis, nullptr, nullptr, H, W);
+    // small batches: latency matters -> one warp per solve; large batches: throughput -> one thread per solve
+    if (B * N_TEX <= 8192) k_homography<<<(B * N_TEX + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
+    else k_homography_thread<<<(B * N_TEX + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
     k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);
     fusg_count_launch(3);
     return fusg_check_launch();

@@ -151,9 +151,21 @@ __device__ __forceinline__ double plane_distance(const double *E, const double *
 }
 
 // ---------------------------------------------------------------------------------------------
-// OpenCV's Jacobi eigen-solver (cv::eigen on a symmetric matrix), n <= 9.
-// A is destroyed; W = eigenvalues (descending); rows of V = eigenvectors.
+// cv2.findHomography(src, dst), method 0 -- one WARP per point set.
+//
+// The arithmetic is OpenCV's, element for element (normalised DLT -> 9x9 LtL -> cv::eigen's Jacobi
+// with its max-pivot bookkeeping -> de-normalisation -> LMSolver schedule for n > 4), so every
+// matrix entry sees the same fp64 operations in the same order as the scalar oracle; the warp only
+// spreads *independent* entries over its lanes: the 45 LtL entries, the <= 27 element pairs of a
+// Jacobi rotation, the 17 pivot candidates (shuffle arg-max), the 36+8 normal-equation entries and
+// the per-point residual/Jacobian rows.  Matrices live in shared memory (dynamic indices).
 // ---------------------------------------------------------------------------------------------
+struct HomogScratch {
+    double A[81], V[81], W[9];          // Jacobi: matrix, eigenvectors (rows), eigenvalues
+    double J[96], N[64], r[12], v[8];   // LM: Jacobian 12x8, normal matrix, residual, J^T r
+    int indR[9], indC[9], perm[9], pad;
+};
+
 __device__ __forceinline__ double cv_hypot(double a, double b) {
     a = fabs(a); b = fabs(b);
     if (a > b) { b /= a; return a * sqrt(1 + b * b); }
@@ -163,40 +175,53 @@ __device__ __forceinline__ double cv_hypot(double a, double b) {
 
 #define FUSG_ROT(v0, v1) do { const double a0_ = (v0), b0_ = (v1); (v0) = a0_ * c - b0_ * s; (v1) = a0_ * s + b0_ * c; } while (0)
 
-__device__ inline void jacobi_eig(double *A, double *W, double *V, const int n) {
-    const double eps = DBL_EPSILON;
-    int indR[9], indC[9];
-    int i, j, k, m;
-    double mv;
-    for (i = 0; i < n; ++i) { for (j = 0; j < n; ++j) V[i * n + j] = 0; V[i * n + i] = 1; }
-    for (k = 0; k < n; ++k) {
-        W[k] = A[(n + 1) * k];
-        if (k < n - 1) {
-            for (m = k + 1, mv = fabs(A[n * k + m]), i = k + 2; i < n; ++i) {
-                const double val = fabs(A[n * k + i]);
-                if (mv < val) { mv = val; m = i; }
-            }
-            indR[k] = m;
-        }
-        if (k > 0) {
-            for (m = 0, mv = fabs(A[k]), i = 1; i < k; ++i) {
-                const double val = fabs(A[n * i + k]);
-                if (mv < val) { mv = val; m = i; }
-            }
-            indC[k] = m;
-        }
+// first index of the strict maximum over the warp (ties -> lowest position), all lanes get it
+__device__ __forceinline__ void warp_argmax_first(double &val, int &pos) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, off);
+        const int op = __shfl_xor_sync(0xffffffffu, pos, off);
+        if (ov > val || (ov == val && op < pos)) { val = ov; pos = op; }
     }
+}
+
+// row/column maxima bookkeeping of JacobiImpl_ for index idx (A upper triangle, n x n)
+__device__ __forceinline__ int jacobi_row_max(const double *A, int n, int k) {
+    int m = k + 1;
+    double mv = fabs(A[n * k + m]);
+    for (int i = k + 2; i < n; ++i) { const double val = fabs(A[n * k + i]); if (mv < val) { mv = val; m = i; } }
+    return m;
+}
+__device__ __forceinline__ int jacobi_col_max(const double *A, int n, int k) {
+    int m = 0;
+    double mv = fabs(A[k]);
+    for (int i = 1; i < k; ++i) { const double val = fabs(A[n * i + k]); if (mv < val) { mv = val; m = i; } }
+    return m;
+}
+
+// cv::eigen (Jacobi) on sc.A (n = 9); leaves sc.perm = row order after OpenCV's descending sort.
+__device__ inline void jacobi_eig_warp(HomogScratch &sc, const int lane) {
+    constexpr int n = 9;
+    const double eps = DBL_EPSILON;
+    double *A = sc.A, *V = sc.V, *W = sc.W;
+    for (int e = lane; e < n * n; e += 32) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+    if (lane < n) {
+        W[lane] = A[(n + 1) * lane];
+        if (lane < n - 1) sc.indR[lane] = jacobi_row_max(A, n, lane);
+        if (lane > 0) sc.indC[lane] = jacobi_col_max(A, n, lane);
+    }
+    __syncwarp();
     const int maxIters = n * n * 30;
-    if (n > 1) for (int iters = 0; iters < maxIters; ++iters) {
-        for (k = 0, mv = fabs(A[indR[0]]), i = 1; i < n - 1; ++i) {
-            const double val = fabs(A[n * i + indR[i]]);
-            if (mv < val) { mv = val; k = i; }
-        }
-        int l = indR[k];
-        for (i = 1; i < n; ++i) {
-            const double val = fabs(A[n * indC[i] + i]);
-            if (mv < val) { mv = val; k = indC[i]; l = i; }
-        }
+    for (int iters = 0; iters < maxIters; ++iters) {
+        // pivot: first strict maximum over [row candidates 0..n-2, column candidates 1..n-1]
+        double cand = -1.0;
+        int pos = lane;
+        if (lane < n - 1) cand = fabs(A[n * lane + sc.indR[lane]]);
+        else if (lane < 2 * n - 2) { const int i = lane - (n - 1) + 1; cand = fabs(A[n * sc.indC[i] + i]); }
+        warp_argmax_first(cand, pos);
+        int k, l;
+        if (pos < n - 1) { k = pos; l = sc.indR[pos]; }
+        else { l = pos - (n - 1) + 1; k = sc.indC[l]; }
         const double p = A[n * k + l];
         if (fabs(p) <= eps) break;
         const double y = (W[l] - W[k]) * 0.5;
@@ -205,170 +230,203 @@ __device__ inline void jacobi_eig(double *A, double *W, double *V, const int n) 
         const double c = t / s;
         s = p / s; t = (p / t) * p;
         if (y < 0) { s = -s; t = -t; }
-        A[n * k + l] = 0;
-        W[k] -= t;
-        W[l] += t;
-        for (i = 0; i < k; ++i) FUSG_ROT(A[n * i + k], A[n * i + l]);
-        for (i = k + 1; i < l; ++i) FUSG_ROT(A[n * k + i], A[n * i + l]);
-        for (i = l + 1; i < n; ++i) FUSG_ROT(A[n * k + i], A[n * l + i]);
-        for (i = 0; i < n; ++i) FUSG_ROT(V[n * k + i], V[n * l + i]);
-        for (j = 0; j < 2; ++j) {
-            const int idx = j == 0 ? k : l;
-            if (idx < n - 1) {
-                for (m = idx + 1, mv = fabs(A[n * idx + m]), i = idx + 2; i < n; ++i) {
-                    const double val = fabs(A[n * idx + i]);
-                    if (mv < val) { mv = val; m = i; }
-                }
-                indR[idx] = m;
+        __syncwarp();
+        if (lane == 0) { A[n * k + l] = 0; W[k] -= t; W[l] += t; }
+        if (lane < n) {
+            const int i = lane;
+            if (i < k) FUSG_ROT(A[n * i + k], A[n * i + l]);
+            else if (i > k && i < l) FUSG_ROT(A[n * k + i], A[n * i + l]);
+            else if (i > l) FUSG_ROT(A[n * k + i], A[n * l + i]);
+        } else if (lane >= 16 && lane < 16 + n) {
+            const int i = lane - 16;
+            FUSG_ROT(V[n * k + i], V[n * l + i]);
+        }
+        __syncwarp();
+        if (lane == 0 && k < n - 1) sc.indR[k] = jacobi_row_max(A, n, k);
+        if (lane == 1 && k > 0) sc.indC[k] = jacobi_col_max(A, n, k);
+        if (lane == 2 && l < n - 1) sc.indR[l] = jacobi_row_max(A, n, l);
+        if (lane == 3 && l > 0) sc.indC[l] = jacobi_col_max(A, n, l);
+        __syncwarp();
+    }
+    __syncwarp();
+    if (lane == 0) {          // OpenCV's descending selection sort, tracked as a row permutation
+        for (int i = 0; i < n; ++i) sc.perm[i] = i;
+        for (int k = 0; k < n - 1; ++k) {
+            int m = k;
+            for (int i = k + 1; i < n; ++i) if (W[m] < W[i]) m = i;
+            if (k != m) {
+                const double tw = W[m]; W[m] = W[k]; W[k] = tw;
+                const int tp = sc.perm[m]; sc.perm[m] = sc.perm[k]; sc.perm[k] = tp;
             }
-            if (idx > 0) {
-                for (m = 0, mv = fabs(A[idx]), i = 1; i < idx; ++i) {
-                    const double val = fabs(A[n * i + idx]);
-                    if (mv < val) { mv = val; m = i; }
-                }
-                indC[idx] = m;
-            }
         }
     }
-    for (k = 0; k < n - 1; ++k) {
-        m = k;
-        for (i = k + 1; i < n; ++i) if (W[m] < W[i]) m = i;
-        if (k != m) {
-            const double tw = W[m]; W[m] = W[k]; W[k] = tw;
-            for (i = 0; i < n; ++i) { const double tv = V[n * m + i]; V[n * m + i] = V[n * k + i]; V[n * k + i] = tv; }
-        }
-    }
+    __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
-// LM refinement of the 8 free homography parameters (OpenCV LMSolver schedule, maxIters 10,
-// eps FLT_EPSILON); linear systems by square-root-free Cholesky.
-// ---------------------------------------------------------------------------------------------
-__device__ inline void lm_residual(const float *M, const float *m, int count, const double *h, double *err, double *J) {
-    for (int i = 0; i < count; ++i) {
-        const double Mx = M[2 * i], My = M[2 * i + 1];
-        double ww = h[6] * Mx + h[7] * My + 1.;
-        ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
-        const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
-        const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
-        err[2 * i] = xi - m[2 * i];
-        err[2 * i + 1] = yi - m[2 * i + 1];
-        if (J) {
-            double *Jp = J + 16 * i;
-            Jp[0] = Mx * ww; Jp[1] = My * ww; Jp[2] = ww;
-            Jp[3] = Jp[4] = Jp[5] = 0.;
-            Jp[6] = -Mx * ww * xi; Jp[7] = -My * ww * xi;
-            Jp[8] = Jp[9] = Jp[10] = 0.;
-            Jp[11] = Mx * ww; Jp[12] = My * ww; Jp[13] = ww;
-            Jp[14] = -Mx * ww * yi; Jp[15] = -My * ww * yi;
-        }
-    }
+// entry `idx` of the two DLT rows of one correspondence (fundam.cpp runKernel)
+__device__ __forceinline__ double dlt_lx(int idx, double X, double Y, double x) {
+    switch (idx) { case 0: return X; case 1: return Y; case 2: return 1; case 6: return -x * X; case 7: return -x * Y; case 8: return -x; default: return 0; }
+}
+__device__ __forceinline__ double dlt_ly(int idx, double X, double Y, double y) {
+    switch (idx) { case 3: return X; case 4: return Y; case 5: return 1; case 6: return -y * X; case 7: return -y * Y; case 8: return -y; default: return 0; }
 }
 
-__device__ inline void lm_normal_eq(const double *J, const double *r, int rows, double *A, double *v) {
-    for (int i = 0; i < 8; ++i)
-        for (int j = i; j < 8; ++j) {
-            double s = 0;
-            for (int k = 0; k < rows; ++k) s += J[k * 8 + i] * J[k * 8 + j];
-            A[i * 8 + j] = s; A[j * 8 + i] = s;
-        }
-    for (int i = 0; i < 8; ++i) {
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        int k = 0;
-        for (; k <= rows - 4; k += 4) {
-            s0 += J[k * 8 + i] * r[k];
-            s1 += J[(k + 1) * 8 + i] * r[k + 1];
-            s2 += J[(k + 2) * 8 + i] * r[k + 2];
-            s3 += J[(k + 3) * 8 + i] * r[k + 3];
-        }
-        for (; k < rows; ++k) s0 += J[k * 8 + i] * r[k];
-        v[i] = ((s0 + s1) + s2) + s3;
-    }
-}
-
-__device__ inline double dot4(const double *a, const double *b, int n) {
-    double res = 0;
-    int i = 0;
-    for (; i <= n - 4; i += 4)
-        res += a[i] * b[i] + a[i + 1] * b[i + 1] + a[i + 2] * b[i + 2] + a[i + 3] * b[i + 3];
-    for (; i < n; ++i) res += a[i] * b[i];
-    return res;
-}
-
-__device__ inline void ldl_solve8(const double *A, const double *b, double *x) {
+// x = A^-1 b, 8x8 SPD, square-root-free Cholesky; A is read from (shared) memory, everything else
+// stays in registers (all loops have constant bounds).  Same operation order as the oracle's ldl_solve.
+__device__ __forceinline__ void ldl_solve8(const double *A, const double *b, double *x) {
     double L[64], Dg[8], y[8];
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
         double dj = A[j * 8 + j];
+#pragma unroll
         for (int k = 0; k < j; ++k) dj -= L[j * 8 + k] * L[j * 8 + k] * Dg[k];
         Dg[j] = dj;
         const double inv = dj > 0 ? 1. / dj : 0.;
+#pragma unroll
         for (int i = j + 1; i < 8; ++i) {
             double s = A[i * 8 + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) s -= L[i * 8 + k] * L[j * 8 + k] * Dg[k];
             L[i * 8 + j] = s * inv;
         }
     }
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
         double s = b[i];
+#pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i * 8 + k] * y[k];
         y[i] = s;
     }
+#pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = Dg[i] > 0 ? y[i] / Dg[i] : 0.;
+#pragma unroll
     for (int i = 7; i >= 0; --i) {
         double s = y[i];
+#pragma unroll
         for (int k = i + 1; k < 8; ++k) s -= L[k * 8 + i] * x[k];
         x[i] = s;
     }
 }
 
-__device__ inline void lm_refine(const float *M, const float *m, int count, double *h8) {
-    const int lx = 8, rows = 2 * count;
-    const int maxIters = 10;
+// residual (+ Jacobian rows) of correspondence `i` at parameters h (fundam.cpp HomographyRefineCallback)
+__device__ __forceinline__ void lm_point(float Mxf, float Myf, float mxf, float myf, const double *h, double *err, double *Jrows) {
+    const double Mx = Mxf, My = Myf;
+    double ww = h[6] * Mx + h[7] * My + 1.;
+    ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+    const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+    const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+    err[0] = xi - mxf;
+    err[1] = yi - myf;
+    if (Jrows) {
+        Jrows[0] = Mx * ww; Jrows[1] = My * ww; Jrows[2] = ww;
+        Jrows[3] = Jrows[4] = Jrows[5] = 0.;
+        Jrows[6] = -Mx * ww * xi; Jrows[7] = -My * ww * xi;
+        Jrows[8] = Jrows[9] = Jrows[10] = 0.;
+        Jrows[11] = Mx * ww; Jrows[12] = My * ww; Jrows[13] = ww;
+        Jrows[14] = -Mx * ww * yi; Jrows[15] = -My * ww * yi;
+    }
+}
+
+__device__ __forceinline__ double dot4_8(const double *a, const double *b) {
+    double res = 0;
+    res += a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+    res += a[4] * b[4] + a[5] * b[5] + a[6] * b[6] + a[7] * b[7];
+    return res;
+}
+
+// LM refinement (LMSolver schedule, maxIters 10, eps FLT_EPSILON); h8 uniform across the warp.
+// Mf/mf: this lane's correspondence (lane < count).
+__device__ inline void lm_refine_warp(HomogScratch &sc, const int lane, const int count, float Mxf, float Myf, float mxf, float myf, double *h8) {
+    const int rows = 2 * count;
     const double epsx = FLT_EPSILON, epsf = FLT_EPSILON;
-    double x[8], xd[8], r[12], rd[12], J[12 * 8], A[64], Ap[64], v[8], d[8], D[8], temp_d[8];
+    double x[8], xd[8], d[8], D[8], temp_d[8], vv[8];
+#pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = h8[i];
-    lm_residual(M, m, count, x, r, J);
-    double S = 0;
-    for (int i = 0; i < rows; ++i) S += r[i] * r[i];
-    lm_normal_eq(J, r, rows, A, v);
-    for (int i = 0; i < lx; ++i) D[i] = A[i * 8 + i];
+    auto residual = [&](const double *h, double *rdst, bool jac) {
+        __syncwarp();
+        if (lane < count) lm_point(Mxf, Myf, mxf, myf, h, rdst + 2 * lane, jac ? sc.J + 16 * lane : nullptr);
+        __syncwarp();
+    };
+    auto sumsq = [&](const double *rv) { double S = 0; for (int i = 0; i < rows; ++i) S += rv[i] * rv[i]; return S; };
+    auto normal_eq = [&]() {
+        // N = J^T J (sequential over rows), v = J^T r (4 interleaved accumulators) -- one entry per lane
+        for (int e = lane; e < 36 + 8; e += 32) {
+            if (e < 36) {
+                int i = 0, rem = e;
+                while (rem >= 8 - i) { rem -= 8 - i; ++i; }
+                const int j = i + rem;
+                double s = 0;
+                for (int k = 0; k < rows; ++k) s += sc.J[k * 8 + i] * sc.J[k * 8 + j];
+                sc.N[i * 8 + j] = s; sc.N[j * 8 + i] = s;
+            } else {
+                const int i = e - 36;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                int k = 0;
+                for (; k <= rows - 4; k += 4) {
+                    s0 += sc.J[k * 8 + i] * sc.r[k];
+                    s1 += sc.J[(k + 1) * 8 + i] * sc.r[k + 1];
+                    s2 += sc.J[(k + 2) * 8 + i] * sc.r[k + 2];
+                    s3 += sc.J[(k + 3) * 8 + i] * sc.r[k + 3];
+                }
+                for (; k < rows; ++k) s0 += sc.J[k * 8 + i] * sc.r[k];
+                sc.v[i] = ((s0 + s1) + s2) + s3;
+            }
+        }
+        __syncwarp();
+    };
+    double *rd = sc.A;                       // the Jacobi matrix is dead by now: reuse as trial residual
+    residual(x, sc.r, true);
+    double S = sumsq(sc.r);
+    normal_eq();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[i] = sc.N[i * 8 + i];
     const double Rlo = 0.25, Rhi = 0.75;
     double lambda = 1, lc = 0.75;
     int iter = 0;
+    double *Ap = sc.V;                       // eigenvectors are dead too: damped normal matrix
     for (;;) {
-        for (int i = 0; i < 64; ++i) Ap[i] = A[i];
-        for (int i = 0; i < lx; ++i) Ap[i * 8 + i] += lambda * D[i];
-        ldl_solve8(Ap, v, d);
-        for (int i = 0; i < lx; ++i) xd[i] = x[i] - d[i];
-        lm_residual(M, m, count, xd, rd, nullptr);
-        double Sd = 0;
-        for (int i = 0; i < rows; ++i) Sd += rd[i] * rd[i];
-        for (int i = 0; i < lx; ++i) {
+        __syncwarp();
+        for (int e = lane; e < 64; e += 32) Ap[e] = sc.N[e] + ((e >> 3) == (e & 7) ? lambda * D[e & 7] : 0.0);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vv[i] = sc.v[i];
+        ldl_solve8(Ap, vv, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xd[i] = x[i] - d[i];
+        residual(xd, rd, false);
+        const double Sd = sumsq(rd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int k = 0; k < lx; k += 4) {
-                s0 += A[i * 8 + k] * d[k];
-                s1 += A[i * 8 + k + 1] * d[k + 1];
-                s2 += A[i * 8 + k + 2] * d[k + 2];
-                s3 += A[i * 8 + k + 3] * d[k + 3];
+#pragma unroll
+            for (int k = 0; k < 8; k += 4) {
+                s0 += sc.N[i * 8 + k] * d[k];
+                s1 += sc.N[i * 8 + k + 1] * d[k + 1];
+                s2 += sc.N[i * 8 + k + 2] * d[k + 2];
+                s3 += sc.N[i * 8 + k + 3] * d[k + 3];
             }
-            temp_d[i] = -1. * (((s0 + s1) + s2) + s3) + 2. * v[i];
+            temp_d[i] = -1. * (((s0 + s1) + s2) + s3) + 2. * vv[i];
         }
-        const double dS = dot4(d, temp_d, lx);
+        const double dS = dot4_8(d, temp_d);
         const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
         if (R > Rhi) {
             lambda *= 0.5;
             if (lambda < lc) lambda = 0;
         } else if (R < Rlo) {
-            const double t = dot4(d, v, lx);
+            const double t = dot4_8(d, vv);
             double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
             nu = fmin(fmax(nu, 2.), 10.);
             if (lambda == 0) {
                 double maxval = DBL_EPSILON;
-                for (int c = 0; c < lx; ++c) {
-                    double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, col[8];
-                    e[c] = 1.;
-                    ldl_solve8(A, e, col);
-                    maxval = fmax(maxval, fabs(col[c]));
+                for (int c = 0; c < 8; ++c) {
+                    double e[8], col[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) e[q] = (q == c) ? 1. : 0.;
+                    ldl_solve8(sc.N, e, col);
+                    double cc = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cc = (q == c) ? col[q] : cc;
+                    maxval = fmax(maxval, fabs(cc));
                 }
                 lambda = lc = 1. / maxval;
                 nu *= 0.5;
@@ -377,84 +435,83 @@ __device__ inline void lm_refine(const float *M, const float *m, int count, doub
         }
         if (Sd < S) {
             S = Sd;
+#pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = xd[i];
-            lm_residual(M, m, count, x, r, J);
-            lm_normal_eq(J, r, rows, A, v);
+            residual(x, sc.r, true);
+            normal_eq();
         }
         iter++;
         double nd = 0, nr = 0;
-        for (int i = 0; i < lx; ++i) nd = fmax(nd, fabs(d[i]));
-        for (int i = 0; i < rows; ++i) nr = fmax(nr, fabs(r[i]));
-        if (!(iter < maxIters && nd >= epsx && nr >= epsf)) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nd = fmax(nd, fabs(d[i]));
+        for (int i = 0; i < rows; ++i) nr = fmax(nr, fabs(sc.r[i]));
+        if (!(iter < 10 && nd >= epsx && nr >= epsf)) break;
     }
+#pragma unroll
     for (int i = 0; i < 8; ++i) h8[i] = x[i];
 }
 
-// OpenCV's "returns None" test of findHomography: all src or all dst points share an x or a y.
-__device__ inline bool homography_degenerate(const int *s, const int *d, int count) {
-    float M[12], m[12];
-    for (int i = 0; i < 2 * count; ++i) { M[i] = (float)s[i]; m[i] = (float)d[i]; }
+// Whole warp: s/d point to the 2*count int coordinates (uniform pointers).  Returns false where
+// OpenCV returns None; H (9 doubles, identical on every lane) otherwise.
+__device__ inline bool find_homography_warp(HomogScratch &sc, const int lane, const int *s, const int *d, const int count, double *H) {
+    // centroids / mean-absolute-deviation scales: uniform, sequential over points like runKernel
     double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
     for (int i = 0; i < count; ++i) {
-        cmx += m[2 * i]; cmy += m[2 * i + 1];
-        cMx += M[2 * i]; cMy += M[2 * i + 1];
+        cmx += (float)d[2 * i]; cmy += (float)d[2 * i + 1];
+        cMx += (float)s[2 * i]; cMy += (float)s[2 * i + 1];
     }
     cmx /= count; cmy /= count; cMx /= count; cMy /= count;
     for (int i = 0; i < count; ++i) {
-        smx += fabs(m[2 * i] - cmx); smy += fabs(m[2 * i + 1] - cmy);
-        sMx += fabs(M[2 * i] - cMx); sMy += fabs(M[2 * i + 1] - cMy);
+        smx += fabs((float)d[2 * i] - cmx); smy += fabs((float)d[2 * i + 1] - cmy);
+        sMx += fabs((float)s[2 * i] - cMx); sMy += fabs((float)s[2 * i + 1] - cMy);
     }
-    return fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON;
-}
-
-// cv2.findHomography(src, dst), method 0, count in {4..6}.  Returns false where OpenCV returns None.
-__device__ inline bool find_homography(const int *s, const int *d, int count, double *H) {
-    float M[12], m[12];
-    for (int i = 0; i < 2 * count; ++i) { M[i] = (float)s[i]; m[i] = (float)d[i]; }
-    double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
-    for (int i = 0; i < count; ++i) {
-        cmx += m[2 * i]; cmy += m[2 * i + 1];
-        cMx += M[2 * i]; cMy += M[2 * i + 1];
-    }
-    cmx /= count; cmy /= count; cMx /= count; cMy /= count;
-    for (int i = 0; i < count; ++i) {
-        smx += fabs(m[2 * i] - cmx); smy += fabs(m[2 * i + 1] - cmy);
-        sMx += fabs(M[2 * i] - cMx); sMy += fabs(M[2 * i + 1] - cMy);
-    }
-    if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
-        return false;
+    if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) return false;
     smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
+    // LtL: 45 upper-triangle entries over the lanes, each summed over the points in order
+    __syncwarp();
+    for (int e = lane; e < 45; e += 32) {
+        int j = 0, rem = e;
+        while (rem >= 9 - j) { rem -= 9 - j; ++j; }
+        const int k = j + rem;
+        double acc = 0;
+        for (int i = 0; i < count; ++i) {
+            const double x = ((float)d[2 * i] - cmx) * smx, y = ((float)d[2 * i + 1] - cmy) * smy;
+            const double X = ((float)s[2 * i] - cMx) * sMx, Y = ((float)s[2 * i + 1] - cMy) * sMy;
+            acc += dlt_lx(j, X, Y, x) * dlt_lx(k, X, Y, x) + dlt_ly(j, X, Y, y) * dlt_ly(k, X, Y, y);
+        }
+        sc.A[j * 9 + k] = acc;
+        sc.A[k * 9 + j] = acc;
+    }
+    __syncwarp();
+    jacobi_eig_warp(sc, lane);
+    const double *H0 = sc.V + 9 * sc.perm[8];           // eigenvector of the smallest eigenvalue
     const double invHnorm[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
     const double Hnorm2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
-    double LtL[81], W[9], V[81];
-    for (int i = 0; i < 81; ++i) LtL[i] = 0;
-    for (int i = 0; i < count; ++i) {
-        const double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
-        const double X = (M[2 * i] - cMx) * sMx, Y = (M[2 * i + 1] - cMy) * sMy;
-        const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
-        const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
-        for (int j = 0; j < 9; ++j)
-            for (int k = j; k < 9; ++k)
-                LtL[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
-    }
-    for (int j = 0; j < 9; ++j) for (int k = 0; k < j; ++k) LtL[j * 9 + k] = LtL[k * 9 + j];
-    jacobi_eig(LtL, W, V, 9);
-    const double *H0 = V + 72;
     double Ht[9], H1[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double acc = 0;
-        for (int k = 0; k < 3; ++k) acc += invHnorm[i * 3 + k] * H0[k * 3 + j];
-        Ht[i * 3 + j] = acc;
-    }
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double acc = 0;
-        for (int k = 0; k < 3; ++k) acc += Ht[i * 3 + k] * Hnorm2[k * 3 + j];
-        H1[i * 3 + j] = acc;
-    }
-    const double sc = 1. / H1[8];
-    for (int i = 0; i < 9; ++i) H[i] = H1[i] * sc;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc += invHnorm[i * 3 + k] * H0[k * 3 + j];
+            Ht[i * 3 + j] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc += Ht[i * 3 + k] * Hnorm2[k * 3 + j];
+            H1[i * 3 + j] = acc;
+        }
+    const double scl = 1. / H1[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = H1[i] * scl;
     if (count > 4) {
-        lm_refine(M, m, count, H);
+        const int li = lane < count ? lane : 0;
+        lm_refine_warp(sc, lane, count, (float)s[2 * li], (float)s[2 * li + 1], (float)d[2 * li], (float)d[2 * li + 1], H);
         H[8] = 1.;
     }
     return true;
