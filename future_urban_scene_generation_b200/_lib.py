@@ -37,6 +37,7 @@ def _load():
         "fusg_conv2d_select": ([vp], i),
         "fusg_sizeof_conv_desc": ([], sz),
         "fusg_fold_weightnorm": ([vp, vp, vp, i, i, i, i, i, i, vp], i),
+        "fusg_fold_weightnorm_paired": ([vp, vp, vp, vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_nchw_to_nhwc": ([vp, vp, i, i, i, i, i, i, i, vp], i),
         "fusg_nhwc_to_nchw": ([vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_to_image": ([vp, vp, i, i, i, vp], i),

@@ -113,7 +113,14 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
 #pragma unroll
         for (int i = 0; i < 16; ++i) val[i] = o.source == 1 ? z[i] : v[i];
         const OutAddr a = out_address(o, d.cout, Ho, Wo, b, y, x, n);
-        if (o.layout == 1) {                                 // NCHW fp32, unrounded
+        if (o.layout == 1 && o.mode == FUSG_OUT_UNPAIR) {    // pixel-pair packed layer -> NCHW fp32
+            float *p = reinterpret_cast<float *>(o.ptr);
+            const int cq = d.cout >> 1;
+            for (int i = 0; i < nvalid; ++i) {
+                const int nn = n + i, dx = nn / cq, c = nn - dx * cq;
+                p[(((size_t)b * cq + c) * Ho + y) * (2 * Wo) + 2 * x + dx] = o.elu ? elu1(val[i]) : val[i];
+            }
+        } else if (o.layout == 1) {                          // NCHW fp32, unrounded
             float *p = reinterpret_cast<float *>(o.ptr);
             const size_t plane = (size_t)a.Ht * a.Wt;
             const size_t base = ((size_t)b * a.Ct + a.ch) * plane + (size_t)a.py * a.Wt + a.px;
@@ -233,6 +240,13 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, ui
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s_addr(dst)),
         "l"(tm), "r"(s_addr(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// one lane of the (converged) warp; keeps the surrounding control flow warp-uniform so that TMA / MMA
+// operands stay in uniform registers (no per-instruction waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -420,14 +434,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const int cpt = p.chunks0 + p.chunks1;        // k-blocks per tap
 
     if (warp == 0) {
-        // =================== TMA producer ===================
-        if (lane == 0) {
+        // =================== TMA producer (whole warp runs the loop; one elected lane issues) ===================
+        {
             const int groups = p.num_kblocks / p.group;
             const uint32_t stage_tx = (uint32_t)(p.group * (p.a_bytes + (p.w_resident ? 0 : p.b_bytes)));
             if (p.w_resident) {
                 // the weight matrix of this N tile is loaded once per CTA
-                mbar_arrive_expect_tx(w_bar, (uint32_t)(p.num_kblocks * p.b_bytes));
-                for (int kb = 0; kb < p.num_kblocks; ++kb) tma_load_2d(sB + (size_t)kb * p.b_bytes, &p.tmW, w_bar, kb * p.kc, 0);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(w_bar, (uint32_t)(p.num_kblocks * p.b_bytes));
+                    for (int kb = 0; kb < p.num_kblocks; ++kb) tma_load_2d(sB + (size_t)kb * p.b_bytes, &p.tmW, w_bar, kb * p.kc, 0);
+                }
+                __syncwarp();
             }
             int stage = 0;
             uint32_t phase = 0;
@@ -439,24 +456,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 int ky = 0, kx = 0, cidx = 0, kcol = 0;            // running k-block coordinates (no div/mod in the loop)
                 for (int grp = 0; grp < groups; ++grp) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                    const bool leader = elect_one();
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     uint8_t *a_dst = sA + (size_t)stage * p.group * p.a_bytes;
                     uint8_t *b_dst = sB + (size_t)stage * p.group * p.b_bytes;
                     for (int g = 0; g < p.group; ++g) {
-                        if (cidx < p.chunks0) tma_load_4d(a_dst, &p.tmA0, &full_bar[stage], cidx * p.kc, ixb + kx, iyb + ky, b0);
-                        else tma_load_4d(a_dst, &p.tmA1, &full_bar[stage], (cidx - p.chunks0) * p.kc, ixb + kx, iyb + ky, b0);
-                        if (!p.w_resident) { tma_load_2d(b_dst, &p.tmW, &full_bar[stage], kcol, n0); b_dst += p.b_bytes; }
+                        if (leader) {
+                            if (cidx < p.chunks0) tma_load_4d(a_dst, &p.tmA0, &full_bar[stage], cidx * p.kc, ixb + kx, iyb + ky, b0);
+                            else tma_load_4d(a_dst, &p.tmA1, &full_bar[stage], (cidx - p.chunks0) * p.kc, ixb + kx, iyb + ky, b0);
+                            if (!p.w_resident) tma_load_2d(b_dst, &p.tmW, &full_bar[stage], kcol, n0);
+                        }
+                        b_dst += p.b_bytes;
                         a_dst += p.a_bytes;
                         kcol += p.kc;                              // weight columns are ordered (tap, in0 channels, in1 channels)
                         if (++cidx == cpt) { cidx = 0; if (++kx == d.ksize) { kx = 0; ++ky; } }
                     }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // =================== MMA issuer ===================
-        if (lane == 0) {
+        // =================== MMA issuer (whole warp runs the loop; one elected lane issues) ===================
+        {
             // instruction descriptor: D=f32, A=B=bf16, K-major both, N, M=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
             const uint32_t layout_type = p.kc == 64 ? 2u : 4u;     // SWIZZLE_128B : SWIZZLE_64B
@@ -466,6 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             int acc = 0;
             uint32_t acc_phase = 0;
             const int groups = p.num_kblocks / p.group;
+            const int ksteps = p.kc / 16;
             if (p.w_resident) mbar_wait(w_bar, 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -476,23 +499,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     tc_fence_after();
                     uint32_t a_addr = s_addr(sA + (size_t)stage * p.group * p.a_bytes);
                     uint32_t b_addr = p.w_resident ? s_addr(sB + (size_t)grp * p.group * p.b_bytes) : s_addr(sB + (size_t)stage * p.group * p.b_bytes);
-                    for (int g = 0; g < p.group; ++g) {
-                        const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
-                        for (int ks = 0; ks < p.kc / 16; ++ks) {
-                            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
-                            umma_bf16(d_tmem, a_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, (grp | g | ks) != 0 ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int g = 0; g < p.group; ++g) {
+                            const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
+                                umma_bf16(d_tmem, a_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, (grp | g | ks) != 0 ? 1u : 0u);
+                            }
+                            a_addr += (uint32_t)p.a_bytes;
+                            b_addr += (uint32_t)p.b_bytes;
                         }
-                        a_addr += (uint32_t)p.a_bytes;
-                        b_addr += (uint32_t)p.b_bytes;
+                        umma_commit(&empty_bar[stage]);        // frees the smem stage when these MMAs retire
+                        if (grp == groups - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
                     }
-                    umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                  // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-        __syncwarp();
     } else {
         // =================== epilogue warps (2..9) ===================
         // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share a lane quadrant and split the columns
@@ -578,6 +603,48 @@ __global__ void k_fold_weightnorm(const float *__restrict__ v, const float *__re
         float val = 0.f;
         if (n < cout && c < cin) val = v[((size_t)n * cin + c) * taps + tap] * scale;
         w[((size_t)n * taps + tap) * cin_pad + c] = from_f<T>(val);
+    }
+}
+
+// weight_norm fold for pixel-pair packed execution (see fusg.h).  One CTA per padded output channel
+// n' = dx*cout + co; K index = tap' * 2*(c0+c1) + [in0: h*c0 + ci | in1: 2*c0 + h*c1 + ci].
+template <typename T>
+__global__ void k_fold_weightnorm_paired(const float *__restrict__ v, const float *__restrict__ g, const float *__restrict__ bias,
+                                         T *__restrict__ w, float *__restrict__ bias_out, int cout, int c0, int c1, int ks, int cout_pad) {
+    const int np = blockIdx.x;
+    const int cin = c0 + c1, taps = ks * ks, len = cin * taps, kp = 2 * cin;
+    const int dx = np / cout, co = np - dx * cout;
+    const bool real = np < 2 * cout;
+    __shared__ float red[32];
+    float ss = 0.f;
+    if (real) for (int i = threadIdx.x; i < len; i += blockDim.x) { const float a = v[(size_t)co * len + i]; ss += a * a; }
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    const float scale = real ? g[co] / sqrtf(red[0]) : 0.f;
+    if (threadIdx.x == 0) bias_out[np] = real ? bias[co] : 0.f;
+    for (int i = threadIdx.x; i < taps * kp; i += blockDim.x) {
+        const int tap = i / kp, k = i - tap * kp;
+        int src_c, h;                                   // original input channel and input half
+        if (k < 2 * c0) { h = k / c0; src_c = k - h * c0; }
+        else { const int kk = k - 2 * c0; h = kk / c1; src_c = c0 + (kk - h * c1); }
+        float val = 0.f;
+        if (real) {
+            if (ks == 1) {
+                if (h == dx) val = v[(size_t)co * cin + src_c] * scale;
+            } else {
+                const int ky = tap / 3, s = tap - ky * 3 - 1;          // pair shift -1, 0, +1
+                const int kx = 2 * s + h - dx + 1;
+                if (kx >= 0 && kx < 3) val = v[((size_t)co * cin + src_c) * 9 + ky * 3 + kx] * scale;
+            }
+        }
+        w[((size_t)np * taps + tap) * kp + k] = from_f<T>(val);
     }
 }
 
@@ -826,6 +893,17 @@ extern "C" int fusg_fold_weightnorm(const float *v, const float *g, void *w_out,
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FUSG_DTYPE_BF16) k_fold_weightnorm<__nv_bfloat16><<<cout_pad, 256, 0, st>>>(v, g, (__nv_bfloat16 *)w_out, cout, cin, ksize, cout_pad, cin_pad);
     else k_fold_weightnorm<float><<<cout_pad, 256, 0, st>>>(v, g, (float *)w_out, cout, cin, ksize, cout_pad, cin_pad);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_fold_weightnorm_paired(const float *v, const float *g, const float *bias, void *w_out, float *bias_out, int cout,
+                                           int cin0, int cin1, int ksize, int cout_pad, int dtype, void *stream) {
+    if (!v || !g || !bias || !w_out || !bias_out || cout <= 0 || cin0 <= 0 || cin1 < 0 || cout_pad < 2 * cout) return FUSG_ERR_ARG;
+    if (ksize != 1 && ksize != 3) return FUSG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FUSG_DTYPE_BF16) k_fold_weightnorm_paired<__nv_bfloat16><<<cout_pad, 256, 0, st>>>(v, g, bias, (__nv_bfloat16 *)w_out, bias_out, cout, cin0, cin1, ksize, cout_pad);
+    else k_fold_weightnorm_paired<float><<<cout_pad, 256, 0, st>>>(v, g, bias, (float *)w_out, bias_out, cout, cin0, cin1, ksize, cout_pad);
     fusg_count_launch(1);
     return fusg_check_launch();
 }

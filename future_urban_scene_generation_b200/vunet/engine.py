@@ -15,7 +15,7 @@ from .. import _lib
 
 DT_BF16, DT_F32 = 0, 1
 IMPL_AUTO, IMPL_TC, IMPL_DIRECT = 0, 1, 2
-PLAIN, D2S, S2D, D2S_BLOCK = 0, 1, 2, 3
+PLAIN, D2S, S2D, D2S_BLOCK, UNPAIR = 0, 1, 2, 3, 4
 MAX_OUTS = 6
 
 
@@ -68,6 +68,8 @@ class VunetEngine:
         self.impl = {"auto": IMPL_AUTO, "tcgen05": IMPL_TC, "direct": IMPL_DIRECT}[impl]
         self._wkey = None
         self._w = {}
+        self._wp = {}                  # pixel-pair packed weights of the narrow stride-1 layers
+        self.pair_narrow = True        # run 32-channel stride-1 layers on pixel pairs (fusg_fold_weightnorm_paired)
         self.launches = 0
         self.profile = None            # list -> per-launch (path, impl, flops, start, end) CUDA-event records
         self.noise_provider = None     # callable(B,C,H,W) -> NHWC fp32 device tensor; None = CPU torch.randn (reference semantics)
@@ -111,6 +113,7 @@ class VunetEngine:
                                  "(call .to('cuda'))")
         L = _lib.lib()
         self._w = {}
+        self._wp = {}
         with torch.cuda.device(dev):
             for path, conv in self.m.convs.items():
                 cout, cin, k = conv.cout, conv.cin, conv.k
@@ -125,6 +128,17 @@ class VunetEngine:
                                                   self.cdtype, self._stream()), "fusg_fold_weightnorm")
                 self.launches += 1
                 self._w[path] = (w, bias, cout, cout_pad, cin_pad, k)
+                if self.dtype == "bf16" and cout in (32, 3) and cin in (32, 64):
+                    # narrow layer: also fold a pixel-pair packed copy (inputs are one or two 32-channel tensors)
+                    c0, c1 = 32, cin - 32
+                    cp2 = _pad16(2 * cout)
+                    wp = torch.empty((cp2, k * k, 2 * cin), dtype=self.tdtype, device=dev)
+                    bp = torch.empty((cp2,), dtype=torch.float32, device=dev)
+                    braw = conv.bias.detach().float().contiguous()
+                    _lib.check(L.fusg_fold_weightnorm_paired(_lib.ptr(v), _lib.ptr(g), _lib.ptr(braw), _lib.ptr(wp), _lib.ptr(bp), cout, c0, c1, k,
+                                                             cp2, self.cdtype, self._stream()), "fusg_fold_weightnorm_paired")
+                    self.launches += 1
+                    self._wp[path] = (wp, bp, 2 * cout, cp2, 2 * cin, k)
         self._wkey = key
 
     # ------------------------------------------------------------------ one conv launch
@@ -134,12 +148,18 @@ class VunetEngine:
         w, bias, cout, cout_pad, cin_pad, k = self._w[path]
         d = ConvDesc()
         a0, which0 = srcs[0]
+        # pixel-pair packing: [B,H,W,32] viewed as [B,H,W/2,64] (same bytes) for narrow stride-1 layers
+        pair = (self.pair_narrow and path in self._wp and stride == 1 and noise is None and a0.W >= 64 and a0.W % 2 == 0
+                and all(a.C == 32 and a.pitch == 32 and a.off == 0 for a, _ in srcs) and all(o.mode == PLAIN for o in outs))
+        if pair:
+            w, bias, cout, cout_pad, cin_pad, k = self._wp[path]
+        pm = 2 if pair else 1
         t0 = getattr(a0, which0)
         assert t0 is not None, f"{path}: input 0 has no '{which0}' copy"
         esz = t0.element_size()
         d.in0 = t0.data_ptr() + a0.off * esz
-        d.c0, d.pitch0 = a0.C, a0.pitch
-        ctot = a0.C
+        d.c0, d.pitch0 = a0.C * pm, a0.pitch * pm
+        ctot = a0.C * pm
         keep = [t0]
         if len(srcs) > 1:
             a1, which1 = srcs[1]
@@ -147,16 +167,16 @@ class VunetEngine:
             assert t1 is not None, f"{path}: input 1 has no '{which1}' copy"
             assert (a1.H, a1.W) == (a0.H, a0.W)
             d.in1 = t1.data_ptr() + a1.off * esz
-            d.c1, d.pitch1 = a1.C, a1.pitch
-            ctot += a1.C
+            d.c1, d.pitch1 = a1.C * pm, a1.pitch * pm
+            ctot += a1.C * pm
             keep.append(t1)
         assert ctot == cin_pad, f"{path}: channels {ctot} != weight cin {cin_pad}"
-        d.B, d.H, d.W = B, a0.H, a0.W
+        d.B, d.H, d.W = B, a0.H, a0.W // pm
         d.ksize, d.stride = k, stride
         d.weight, d.bias = w.data_ptr(), bias.data_ptr()
         d.cout, d.cout_pad = cout, cout_pad
         if residual is not None:
-            assert residual.raw is not None and residual.pitch == residual.C and residual.off == 0 and residual.C == cout
+            assert residual.raw is not None and residual.pitch == residual.C and residual.off == 0 and residual.C * pm == cout
             d.residual = residual.raw.data_ptr()
         if noise is not None:
             d.noise = noise.data_ptr()
@@ -165,6 +185,8 @@ class VunetEngine:
             d.outs[i].ptr = o.tensor.data_ptr()
             d.outs[i].source, d.outs[i].elu, d.outs[i].layout = o.source, o.elu, o.layout
             d.outs[i].mode, d.outs[i].blk = o.mode, o.blk
+            if pair and o.layout == 1:
+                d.outs[i].mode = UNPAIR
         d.dtype = self.cdtype
         d.impl = self.impl if self.dtype == "bf16" else IMPL_DIRECT
         prof = self.profile

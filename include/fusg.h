@@ -116,6 +116,8 @@ int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8_t *out, in
                                   /*   out[b, y/2, x/2, ((y%2)*2 + x%2)*cout + n]                 */
 #define FUSG_OUT_D2S_BLOCK 3      /* one block of a DepthToSpace of a channel concat              */
                                   /*   (vunet/models.py:85-86): out[b, 2y+blk/2, 2x+blk%2, n]     */
+#define FUSG_OUT_UNPAIR 4         /* pixel-pair packed layer (fusg_fold_weightnorm_paired):       */
+                                  /*   out[b, y, 2x + n/(cout/2), n % (cout/2)]; NCHW fp32 slots  */
 
 #define FUSG_CONV_MAX_OUTS 6
 
@@ -164,6 +166,15 @@ int fusg_conv2d_select(const fusg_conv_desc *desc);
  * fp32 to [cout_pad][k*k][cin_pad] in `dtype` (zero padded).  Run once per load_state_dict. */
 int fusg_fold_weightnorm(const float *v, const float *g, void *w_out, int cout, int cin, int ksize,
                          int cout_pad, int cin_pad, int dtype, void *stream);
+
+/* Same fold, for running a narrow stride-1 layer on PIXEL PAIRS: an NHWC tensor [B,H,W,c] is
+ * bit-identical to [B,H,W/2,2c], so a k x k convolution c0(+c1) -> cout over W pixels equals a
+ * k x 3 (3x3) or 1x1 convolution 2c0(+2c1) -> 2cout over W/2 pixel pairs whose weight matrix holds
+ * the original taps at kx = 2s + h - dx + 1 (pair shift s, input half h, output half dx) and zeros
+ * elsewhere.  Twice the bytes per TMA row and half the rows per pixel for the 32-channel layers.
+ * w_out: [cout_pad][k*k][2*(cin0+cin1)], bias_out: [cout_pad] (bias duplicated per half). */
+int fusg_fold_weightnorm_paired(const float *v, const float *g, const float *bias, void *w_out, float *bias_out,
+                                int cout, int cin0, int cin1, int ksize, int cout_pad, int dtype, void *stream);
 
 /* NCHW fp32 [B,C,H,W] -> NHWC [B,H,W,cpad] in `dtype` (zero padded channels), optional ELU. */
 int fusg_nchw_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int cpad, int elu, int dtype, void *stream);
