@@ -182,8 +182,76 @@ def run_ours(args):
     devin = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
-    # pre-staged device noise for the device-resident loop (an input like any other); the e2e loop
-    # draws it on the CPU generator exactly like the reference (vunet/layers.py:166)
+    from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
+    # The public batched API: NovelViewPipeline (CUDA-graph replay of the ~125 launches of a step, two
+    # steps in flight).  N > 1 adds the NCCL all-gather of the completed crops (eager launches then).
+    pipe = NovelViewPipeline(model, depth=2, gather_fn=(lambda c: gather_crops(c, world * B)) if world > 1 else None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def run_steps(n, resident):
+        last = None
+        for _ in range(n):
+            t = pipe.submit(host, resident=resident)
+            if last is not None and not resident:
+                pipe.result(last)                      # the previous step's outputs are on the host
+            last = t
+        if resident:
+            pipe.wait(last)
+        else:
+            pipe.result(last)
+        return last
+
+    # warm-up: builds the slots (eager pass + graph capture), fills inputs and noise on the device
+    torch.manual_seed(1)
+    last_ticket = run_steps(max(3, args.warmup), resident=False)
+    d2h_bytes = pipe.d2h_bytes(last_ticket)
+    launches_per_step = pipe.launches_per_step()
+
+    # ---- device-resident loop: inputs and noise already in HBM, graph replays only ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(pipe.compute_stream)
+    run_steps(args.steps, resident=True)
+    e1.record(pipe.compute_stream)
+    torch.cuda.synchronize()
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end-to-end loop: every step copies its own pinned inputs H2D, draws the Sampler noise on the
+    # CPU generator (reference semantics), and lands its own results in host memory, inside the timed region
+    e2e_steps = max(4, min(args.steps, 20))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(pipe.copy_stream)
+    run_steps(e2e_steps, resident=False)
+    e1.record(pipe.out_stream)
+    torch.cuda.synchronize()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = reduce_max(max(e0.elapsed_time(e1), e2e_wall))
+    barrier()
+    e2e_value = world * B / (e2e_ms / e2e_steps * 1e-3)
+
+    # ---- per-launch roofline pass (CUDA events around every conv launch, on the launching stream)
+    devin = {k: v.to(dev) for k, v in host.items()}
     noise_bank = {}
 
     def staged_noise(b, c, h, w):
@@ -193,74 +261,6 @@ def run_ours(args):
             noise_bank[key] = torch.randn((b, h, w, c), device=dev)
         return noise_bank[key]
     staged_noise.i = 0
-
-    def step(inp):
-        res = warp_batch(inp["src"], inp["src_kp"], inp["dst_kp"], inp["K"], inp["E_src"], inp["E_dst"], inp["kp3d"], device=dev)
-        x_tilde, _, _ = model(inp["y"], inp["x"])
-        crops = to_image_batch(x_tilde)
-        allc = gather_crops(crops, world * B)          # NCCL all-gather of completed crops (N > 1), the only collective
-        return res, (allc[first:last] if world > 1 else allc)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, iters):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        barrier()
-        return t.item(), wall * 1e3
-
-    # ---- device-resident loop -------------------------------------------------------------------
-    eng.noise_provider = staged_noise
-
-    def dev_step():
-        staged_noise.i = 0
-        step(devin)
-    for _ in range(max(3, args.warmup)):
-        dev_step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    n0 = _lib.kernel_launches()
-    ms_total, _ = timed(dev_step, args.steps)
-    launches = _lib.kernel_launches() - n0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / args.steps
-    value = world * B / (ms_per_step * 1e-3)
-
-    # ---- end-to-end loop: pinned host inputs -> device, CPU noise, results back to the host -----
-    eng.noise_provider = None
-    out_host = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
-    warped_host = torch.empty((B, 5, 256, 256, 3), dtype=torch.uint8).pin_memory()
-    d2h_bytes = out_host.numel() + warped_host.numel()
-
-    def e2e_step():
-        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        res, crops = step(inp)
-        out_host.copy_(crops, non_blocking=True)
-        warped_host.copy_(res.warped, non_blocking=True)
-        torch.cuda.synchronize()
-    for _ in range(2):
-        e2e_step()
-    e2e_steps = max(2, min(args.steps, 10))
-    e2e_ms, e2e_wall = timed(e2e_step, e2e_steps)
-    e2e_value = world * B / (max(e2e_ms, e2e_wall) / e2e_steps * 1e-3)
-
-    # ---- per-launch roofline pass (CUDA events around every conv launch, on the launching stream)
     eng.noise_provider = staged_noise
     roof = None
     warp_roof = None
@@ -315,10 +315,12 @@ def run_ours(args):
             "config": {"workload": f"{B} synthetic 256x256 vehicle crops per GPU per step: fused planar warp (5 CAD planes) + VUNet bf16 forward "
                                    f"(BASELINE config 2), random-init weights" + (", NCCL all-gather of completed uint8 crops" if world > 1 else ""),
                        "crops_per_gpu": B, "global_crops_per_step": world * B, "parallelism": f"crop-sharded dp{world}",
-                       "l2": "per-step activations (>5 GB) exceed the 126 MB L2; no explicit flush"},
+                       "l2": "per-step activations (>5 GB) exceed the 126 MB L2; no explicit flush",
+                       "launch": "one CUDA-graph replay per step (gpu_launches counts the kernels inside the graphs)" if world == 1 else "eager launches + NCCL all-gather"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": max(e2e_ms, e2e_wall) / e2e_steps, "steps": e2e_steps,
-                    "note": "pinned host inputs -> H2D, Sampler noise drawn on the CPU generator (reference semantics), completed crops + warped planes D2H"},
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "note": "NovelViewPipeline.submit/result: pinned host inputs -> H2D, Sampler noise drawn on the CPU generator (reference "
+                            "semantics), CUDA-graph replay, completed crops + warped planes + flags D2H; 2 steps in flight, all inside the timed region"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

@@ -1,0 +1,164 @@
+"""Batched, software-pipelined front end of the hot path: host buffers in, host buffers out.
+
+`NovelViewPipeline.submit(batch)` enqueues, for one batch of crops,
+    H2D of the pinned inputs (copy stream)  ->  fused planar warp + VUNet forward + to_image
+    (compute stream)  ->  D2H of the completed uint8 crops and warped planes (output stream)
+and returns immediately; `result(ticket)` blocks until that batch's outputs are in host memory.
+With `depth` batches in flight the copies of batch n+1 overlap the kernels of batch n, which is how
+a caller that streams (vehicle, step) pairs -- trajectory_inference.py:55,267 -- would drive the path.
+
+The ~125 kernel launches of one step are captured once per slot into a CUDA graph (static device
+buffers) and replayed, so the host issues one launch per step instead of ~125.  Sampler noise is
+still drawn on the CPU default generator in the reference's order and shapes (vunet/layers.py:166)
+-- `torch.manual_seed` reproduces the reference's outputs -- and copied into the graph's static
+noise buffers before each replay.
+"""
+import torch
+
+from . import _lib
+from .warp_learn.batch import warp_batch
+from .warp_learn.planes_utils import to_image_batch
+
+
+class _Slot:
+    """Static buffers + captured graph of one in-flight batch."""
+
+    def __init__(self):
+        self.graph = None
+        self.inp = None          # device input buffers (static)
+        self.noise = []          # device noise buffers in draw order, NHWC fp32
+        self.noise_shapes = []   # (B,C,H,W) per draw
+        self.dev_out = None      # device outputs (static)
+        self.out = None          # pinned host outputs
+        self.done = None
+        self.launches = 0
+
+
+class NovelViewPipeline:
+    WARP_KEYS = ("src", "src_kp", "dst_kp", "K", "E_src", "E_dst", "kp3d")
+
+    def __init__(self, model, depth: int = 2, gather_fn=None, use_graph: bool = True):
+        _lib.require_cuda()
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.depth = depth
+        self.gather_fn = gather_fn        # optional device-side collective on the completed crops (parallel.gather_crops)
+        self.use_graph = use_graph and gather_fn is None      # collectives stay outside the graph
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.compute_stream = torch.cuda.Stream(self.dev)
+        self.out_stream = torch.cuda.Stream(self.dev)
+        self.slots = [_Slot() for _ in range(depth)]
+        self.n = 0
+
+    # ------------------------------------------------------------------ one step of device work
+    def _compute(self, inp):
+        res = warp_batch(*(inp[k] for k in self.WARP_KEYS), device=self.dev)
+        x_tilde, _, _ = self.model(inp["y"], inp["x"])
+        crops = to_image_batch(x_tilde)
+        return {"crops": crops, "warped": res.warped, "plane_j": res.plane_j, "vis": res.vis}
+
+    def _prepare_slot(self, slot: _Slot, batch: dict):
+        """First use of a slot: allocate static buffers, run once eagerly (weight fold, function
+        attributes, allocator warm-up), then capture the step into a graph."""
+        eng = self.model.engine()
+        slot.inp = {k: torch.empty(tuple(v.shape), dtype=v.dtype, device=self.dev) for k, v in batch.items()}
+        for k, v in batch.items():
+            slot.inp[k].copy_(v)
+        shapes = []
+
+        def recording_provider(b, c, h, w):
+            shapes.append((b, c, h, w))
+            return torch.zeros((b, h, w, c), dtype=torch.float32, device=self.dev)
+        prev = eng.noise_provider
+        eng.noise_provider = recording_provider
+        with torch.cuda.stream(self.compute_stream):
+            self._compute(slot.inp)                                   # eager warm-up
+        self.compute_stream.synchronize()
+        slot.noise_shapes = list(shapes)
+        slot.noise = [torch.zeros((b, h, w, c), dtype=torch.float32, device=self.dev) for b, c, h, w in shapes]
+        it = iter(slot.noise)
+        eng.noise_provider = lambda b, c, h, w: next(it)
+        n0 = _lib.kernel_launches()
+        if self.use_graph:
+            slot.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(slot.graph, stream=self.compute_stream):
+                slot.dev_out = self._compute(slot.inp)
+        slot.launches = _lib.kernel_launches() - n0
+        eng.noise_provider = prev
+
+    def _draw_noise(self, slot: _Slot):
+        """CPU default generator, reference order/shapes (NCHW), shipped as NHWC into the static buffers."""
+        for buf, (b, c, h, w) in zip(slot.noise, slot.noise_shapes):
+            eps = torch.randn(b, c, h, w)
+            stage = torch.empty((b, h, w, c), dtype=torch.float32, pin_memory=True)
+            stage.copy_(eps.permute(0, 2, 3, 1))
+            buf.copy_(stage, non_blocking=True)
+
+    # ------------------------------------------------------------------ public API
+    def submit(self, batch: dict, resident: bool = False) -> int:
+        """batch: pinned host tensors `x` (B,6,256,256) f32, `y` (B,3,256,256) f32 and the warp inputs
+        `src` (B,256,256,3) u8, `src_kp`/`dst_kp` (B,12,2) i32, `K` (B,3,3), `E_src`/`E_dst` (B,3,4), `kp3d` (B,12,3) f64.
+        resident=True skips the host copies (inputs / noise already in the slot; outputs stay on the device)."""
+        ticket = self.n
+        slot = self.slots[ticket % self.depth]
+        if slot.done is not None:
+            slot.done.synchronize()                                   # the slot's previous outputs were consumed
+        if slot.inp is None or any(tuple(slot.inp[k].shape) != tuple(v.shape) for k, v in batch.items()):
+            self._prepare_slot(slot, batch)
+        eng = self.model.engine()
+        if not resident:
+            with torch.cuda.stream(self.copy_stream):
+                for k, v in batch.items():
+                    slot.inp[k].copy_(v, non_blocking=True)
+                self._draw_noise(slot)
+                copied = torch.cuda.Event()
+                copied.record(self.copy_stream)
+            self.compute_stream.wait_event(copied)
+        with torch.cuda.stream(self.compute_stream):
+            if slot.graph is not None:
+                slot.graph.replay()
+            else:
+                it = iter(slot.noise)
+                prev = eng.noise_provider
+                eng.noise_provider = lambda b, c, h, w: next(it)
+                slot.dev_out = self._compute(slot.inp)
+                eng.noise_provider = prev
+            dev_out = dict(slot.dev_out)
+            if self.gather_fn is not None:
+                dev_out["crops"] = self.gather_fn(dev_out["crops"])
+            computed = torch.cuda.Event()
+            computed.record(self.compute_stream)
+        if resident:
+            slot.done = computed
+            self.n += 1
+            return ticket
+        if slot.out is None or any(tuple(slot.out[k].shape) != tuple(v.shape) for k, v in dev_out.items()):
+            slot.out = {k: torch.empty(tuple(v.shape), dtype=v.dtype).pin_memory() for k, v in dev_out.items()}
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(computed)
+            for k, v in dev_out.items():
+                slot.out[k].copy_(v, non_blocking=True)
+                v.record_stream(self.out_stream)
+            slot.done = torch.cuda.Event()
+            slot.done.record(self.out_stream)
+        self.n += 1
+        return ticket
+
+    def result(self, ticket: int) -> dict:
+        """Host (pinned) outputs of a submitted batch: `crops` (B,256,256,3) u8 completed views,
+        `warped` (B,5,256,256,3) u8 planes, `plane_j`, `vis`.  Valid until `depth` more batches are submitted."""
+        slot = self.slots[ticket % self.depth]
+        slot.done.synchronize()
+        return slot.out
+
+    def wait(self, ticket: int):
+        self.slots[ticket % self.depth].done.synchronize()
+
+    def device_outputs(self, ticket: int) -> dict:
+        return self.slots[ticket % self.depth].dev_out
+
+    def launches_per_step(self) -> int:
+        return self.slots[0].launches
+
+    def d2h_bytes(self, ticket: int) -> int:
+        return sum(v.numel() * v.element_size() for v in self.slots[ticket % self.depth].out.values())

@@ -275,7 +275,10 @@ class VunetEngine:
             return self.noise_provider(B, Cn, H, W)
         torch = self.torch
         eps = torch.randn(B, Cn, H, W)
-        return eps.permute(0, 2, 3, 1).contiguous().to(self.device(), non_blocking=True)
+        # NHWC copy in pinned memory (caching host allocator: reuse is ordered after the async copy)
+        stage = torch.empty((B, H, W, Cn), dtype=torch.float32, pin_memory=True)
+        stage.copy_(eps.permute(0, 2, 3, 1))
+        return stage.to(self.device(), non_blocking=True)
 
     # ------------------------------------------------------------------ blocks
     def residual(self, path, x, skip=None, B=None, raw=True, elu=True, out_mode=PLAIN):
