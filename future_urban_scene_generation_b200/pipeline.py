@@ -28,10 +28,13 @@ class _Slot:
         self.inp = None          # device input buffers (static)
         self.noise = []          # device noise buffers in draw order, NHWC fp32
         self.noise_shapes = []   # (B,C,H,W) per draw
+        self.noise_stage = []    # pinned NHWC staging buffers (one per draw)
         self.dev_out = None      # device outputs (static)
         self.out = None          # pinned host outputs
         self.done = None
         self.launches = 0
+        self.stream = None       # this slot's compute stream: the small-grid tail layers of one batch overlap the
+                                 # full-grid layers of the next batch in flight
 
 
 class NovelViewPipeline:
@@ -45,9 +48,10 @@ class NovelViewPipeline:
         self.gather_fn = gather_fn        # optional device-side collective on the completed crops (parallel.gather_crops)
         self.use_graph = use_graph and gather_fn is None      # collectives stay outside the graph
         self.copy_stream = torch.cuda.Stream(self.dev)
-        self.compute_stream = torch.cuda.Stream(self.dev)
         self.out_stream = torch.cuda.Stream(self.dev)
         self.slots = [_Slot() for _ in range(depth)]
+        for sl in self.slots:
+            sl.stream = torch.cuda.Stream(self.dev)
         self.n = 0
 
     # ------------------------------------------------------------------ one step of device work
@@ -71,26 +75,27 @@ class NovelViewPipeline:
             return torch.zeros((b, h, w, c), dtype=torch.float32, device=self.dev)
         prev = eng.noise_provider
         eng.noise_provider = recording_provider
-        with torch.cuda.stream(self.compute_stream):
+        with torch.cuda.stream(slot.stream):
             self._compute(slot.inp)                                   # eager warm-up
-        self.compute_stream.synchronize()
+        slot.stream.synchronize()
         slot.noise_shapes = list(shapes)
         slot.noise = [torch.zeros((b, h, w, c), dtype=torch.float32, device=self.dev) for b, c, h, w in shapes]
+        slot.noise_stage = [torch.empty((b, h, w, c), dtype=torch.float32).pin_memory() for b, c, h, w in shapes]
         it = iter(slot.noise)
         eng.noise_provider = lambda b, c, h, w: next(it)
         n0 = _lib.kernel_launches()
         if self.use_graph:
             slot.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(slot.graph, stream=self.compute_stream):
+            with torch.cuda.graph(slot.graph, stream=slot.stream):
                 slot.dev_out = self._compute(slot.inp)
         slot.launches = _lib.kernel_launches() - n0
         eng.noise_provider = prev
 
     def _draw_noise(self, slot: _Slot):
         """CPU default generator, reference order/shapes (NCHW), shipped as NHWC into the static buffers."""
-        for buf, (b, c, h, w) in zip(slot.noise, slot.noise_shapes):
+        # the slot's previous batch has completed (submit() waited on slot.done), so its staging buffers are free
+        for buf, stage, (b, c, h, w) in zip(slot.noise, slot.noise_stage, slot.noise_shapes):
             eps = torch.randn(b, c, h, w)
-            stage = torch.empty((b, h, w, c), dtype=torch.float32, pin_memory=True)
             stage.copy_(eps.permute(0, 2, 3, 1))
             buf.copy_(stage, non_blocking=True)
 
@@ -113,8 +118,8 @@ class NovelViewPipeline:
                 self._draw_noise(slot)
                 copied = torch.cuda.Event()
                 copied.record(self.copy_stream)
-            self.compute_stream.wait_event(copied)
-        with torch.cuda.stream(self.compute_stream):
+            slot.stream.wait_event(copied)
+        with torch.cuda.stream(slot.stream):
             if slot.graph is not None:
                 slot.graph.replay()
             else:
@@ -127,7 +132,7 @@ class NovelViewPipeline:
             if self.gather_fn is not None:
                 dev_out["crops"] = self.gather_fn(dev_out["crops"])
             computed = torch.cuda.Event()
-            computed.record(self.compute_stream)
+            computed.record(slot.stream)
         if resident:
             slot.done = computed
             self.n += 1
