@@ -380,7 +380,8 @@ struct alignas(64) ConvTcParams {
     CUtensorMap tmA0, tmA1, tmW;
     fusg_conv_desc d;
     int Ho, Wo;
-    int Wt, Ht, Bt;                 // tile box (output pixels)
+    int Wt, Ht, Bt;                 // tile box (output pixels): Wt*Ht*Bt = 128*msub
+    int msub;                       // 128-row MMA sub-tiles per CTA tile (1 or 2): two sub-tiles share every B k-block
     int tiles_x, tiles_y, tiles_b;  // M-tile grid
     int n_tiles, block_n;           // N tiling
     int kc;                         // channels per k-block (64: 128B swizzle, 32: 64B swizzle)
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.msub * p.block_n);
                 for (int grp = 0; grp < groups; ++grp) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -502,9 +503,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     if (elect_one()) {
                         for (int g = 0; g < p.group; ++g) {
                             const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
-                                umma_bf16(d_tmem, a_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, (grp | g | ks) != 0 ? 1u : 0u);
+                            for (int sub = 0; sub < p.msub; ++sub) {
+                                // sub-tile `sub`: rows 128*sub.. of the A k-block, accumulator columns sub*block_n..
+                                const uint64_t a_sub = a_desc + (uint64_t)((sub * TC_BLOCK_M * p.kc * 2) >> 4);
+                                for (int ks = 0; ks < ksteps; ++ks) {
+                                    // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
+                                    umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), a_sub + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc,
+                                              (grp | g | ks) != 0 ? 1u : 0u);
+                                }
                             }
                             a_addr += (uint32_t)p.a_bytes;
                             b_addr += (uint32_t)p.b_bytes;
@@ -531,13 +537,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
-            const int wt = row % p.Wt, ht = (row / p.Wt) % p.Ht, bt = row / (p.Wt * p.Ht);
-            const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
-            const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
-            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c_begin);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            if (ncols > 0) {
+            for (int sub = 0; sub < p.msub && ncols > 0; ++sub) {
+                const int trow = row + sub * TC_BLOCK_M;               // row of the CTA tile
+                const int wt = trow % p.Wt, ht = (trow / p.Wt) % p.Ht, bt = trow / (p.Wt * p.Ht);
+                const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
+                const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+                const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.msub + sub) * p.block_n + c_begin);
                 uint32_t r[16];
                 tmem_ld16(t_base, r);
                 for (int c = 0; c < ncols; c += 16) {
@@ -743,19 +750,32 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     p.d = d;
     p.Ho = Ho; p.Wo = Wo;
-    p.Wt = Wo < 128 ? Wo : 128;
-    p.Ht = (128 / p.Wt) < Ho ? (128 / p.Wt) : Ho;
-    p.Bt = 128 / (p.Wt * p.Ht);
-    p.tiles_x = Wo / p.Wt; p.tiles_y = Ho / p.Ht; p.tiles_b = (d.B + p.Bt - 1) / p.Bt;
     p.block_n = d.cout_pad < 128 ? d.cout_pad : 128;
     p.n_tiles = d.cout_pad / p.block_n;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    // 256-row CTA tiles (two 128-row MMA sub-tiles sharing each weight k-block) once there is enough work for
+    // at least ~4 tiles per SM; halves the weight traffic per output pixel
+    static const int msub_max = getenv("FUSG_MSUB1") ? 1 : 2;
+    const long long rows = (long long)d.B * Ho * Wo;
+    p.msub = (msub_max == 2 && rows / 256 * p.n_tiles >= 4LL * num_sms && rows % 256 == 0) ? 2 : 1;
+    const int trows = TC_BLOCK_M * p.msub;
+    p.Wt = Wo < 128 ? Wo : 128;
+    p.Ht = (trows / p.Wt) < Ho ? (trows / p.Wt) : Ho;
+    p.Bt = trows / (p.Wt * p.Ht);
+    p.tiles_x = Wo / p.Wt; p.tiles_y = Ho / p.Ht; p.tiles_b = (d.B + p.Bt - 1) / p.Bt;
     const bool k64 = (d.c0 % 64 == 0) && (!d.in1 || d.c1 % 64 == 0);
     p.kc = k64 ? 64 : 32;
     p.chunks0 = d.c0 / p.kc;
     p.chunks1 = d.in1 ? d.c1 / p.kc : 0;
     const int taps = d.ksize * d.ksize;
     p.num_kblocks = taps * (p.chunks0 + p.chunks1);
-    p.a_bytes = TC_BLOCK_M * p.kc * 2;
+    p.a_bytes = TC_BLOCK_M * p.msub * p.kc * 2;
     p.b_bytes = p.block_n * p.kc * 2;
     // B k-blocks must start 1024-aligned too (swizzle atom): round the size up
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
@@ -777,7 +797,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    int cols = 2 * p.block_n;
+    int cols = 2 * p.msub * p.block_n;
     p.tmem_cols = cols < 32 ? 32 : cols;
 
     // lean epilogue: no noise, only NHWC bf16 outputs (<= one raw, <= one ELU) with one addressing mode
@@ -833,13 +853,6 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
         attr_set = true;
-    }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;

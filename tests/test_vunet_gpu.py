@@ -141,6 +141,9 @@ CONV_CASES = [
     ("sampler_plain", 3, (128,), 128, 3, 1, 4, False, True, 0),
     ("final_3ch", 1, (32,), 3, 3, 1, 64, False, False, 0),
     ("big_tile_256", 1, (128,), 128, 3, 1, 256, True, False, 0),
+    ("msub2_wide", 4, (128,), 128, 3, 1, 256, True, False, 0),        # enough tiles for 256-row CTA tiles
+    ("msub2_down", 8, (128,), 128, 3, 2, 256, False, False, 0),
+    ("msub2_cat32", 4, (32, 32), 32, 3, 1, 256, True, False, 0),
 ]
 
 
