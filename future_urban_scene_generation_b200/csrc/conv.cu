@@ -396,6 +396,65 @@ struct alignas(64) ConvTcParams {
     FastEpi fe;
 };
 
+
+// MMA-issuer role of k_conv_tc.  Everything the loop needs is hoisted into registers and the
+// (sub-tile, k-step) MMAs of a k-block are fully unrolled: the single issuing thread must stay well
+// under the tensor-pipe time of a k-block (KSTEPS*MSUB*64 cycles at N=128) or it becomes the bottleneck.
+template <int KSTEPS, int MSUB>
+__device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uint8_t *sB, uint64_t *full_bar, uint64_t *empty_bar,
+                                         uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *w_bar, uint32_t tmem_base, int total_tiles) {
+    const uint32_t block_n = (uint32_t)p.block_n;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    const uint32_t kc = KSTEPS * 16;
+    // descriptor high bits: LBO=1 | SBO = 8 rows of one swizzle span | version 1 | swizzle mode
+    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((kc * 2u * 8u) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KSTEPS == 4 ? 2u : 4u) << 61);
+    const uint32_t sub16 = (TC_BLOCK_M * kc * 2u) >> 4;                 // next 128-row sub-tile, in 16-byte units
+    const int group = p.group, stages = p.stages, groups = p.num_kblocks / p.group;
+    const uint32_t a_kb16 = (uint32_t)p.a_bytes >> 4, b_kb16 = (uint32_t)p.b_bytes >> 4;
+    const uint32_t a_stage16 = a_kb16 * group, b_stage16 = b_kb16 * group;
+    const bool resident = p.w_resident != 0;
+    const uint32_t sA16 = (s_addr(sA) & 0x3FFFF) >> 4, sB16 = (s_addr(sB) & 0x3FFFF) >> 4;
+    const uint32_t acc_cols = (uint32_t)MSUB * block_n;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc = 0, acc_phase = 0;
+    if (resident) mbar_wait(w_bar, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        for (int grp = 0; grp < groups; ++grp) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                uint32_t a16 = sA16 + (uint32_t)stage * a_stage16;
+                uint32_t b16 = sB16 + (resident ? (uint32_t)grp * b_stage16 : (uint32_t)stage * b_stage16);
+                for (int g = 0; g < group; ++g) {
+                    const uint64_t a_desc = desc_hi | (uint64_t)a16, b_desc = desc_hi | (uint64_t)b16;
+                    const uint32_t first = (grp | g) != 0 ? 1u : 0u;
+#pragma unroll
+                    for (int sub = 0; sub < MSUB; ++sub) {
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            // +2 (x16 bytes) per 16-element K step inside the swizzle span
+                            umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc + (uint64_t)(sub * sub16 + ks * 2), b_desc + (uint64_t)(ks * 2), idesc,
+                                      ks == 0 ? first : 1u);
+                        }
+                    }
+                    a16 += a_kb16;
+                    b16 += b_kb16;
+                }
+                umma_commit(&empty_bar[stage]);                // frees the smem stage when these MMAs retire
+                if (grp == groups - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (swizzle atoms)
@@ -479,50 +538,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
     } else if (warp == 1) {
         // =================== MMA issuer (whole warp runs the loop; one elected lane issues) ===================
-        {
-            // instruction descriptor: D=f32, A=B=bf16, K-major both, N, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
-            const uint32_t layout_type = p.kc == 64 ? 2u : 4u;     // SWIZZLE_128B : SWIZZLE_64B
-            const uint32_t sbo = (uint32_t)p.kc * 2u * 8u;          // 8 rows of one swizzle span
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            const int groups = p.num_kblocks / p.group;
-            const int ksteps = p.kc / 16;
-            if (p.w_resident) mbar_wait(w_bar, 0);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.msub * p.block_n);
-                for (int grp = 0; grp < groups; ++grp) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    uint32_t a_addr = s_addr(sA + (size_t)stage * p.group * p.a_bytes);
-                    uint32_t b_addr = p.w_resident ? s_addr(sB + (size_t)grp * p.group * p.b_bytes) : s_addr(sB + (size_t)stage * p.group * p.b_bytes);
-                    if (elect_one()) {
-                        for (int g = 0; g < p.group; ++g) {
-                            const uint64_t a_desc = make_smem_desc(a_addr, sbo, layout_type), b_desc = make_smem_desc(b_addr, sbo, layout_type);
-                            for (int sub = 0; sub < p.msub; ++sub) {
-                                // sub-tile `sub`: rows 128*sub.. of the A k-block, accumulator columns sub*block_n..
-                                const uint64_t a_sub = a_desc + (uint64_t)((sub * TC_BLOCK_M * p.kc * 2) >> 4);
-                                for (int ks = 0; ks < ksteps; ++ks) {
-                                    // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the >>4 start field
-                                    umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), a_sub + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc,
-                                              (grp | g | ks) != 0 ? 1u : 0u);
-                                }
-                            }
-                            a_addr += (uint32_t)p.a_bytes;
-                            b_addr += (uint32_t)p.b_bytes;
-                        }
-                        umma_commit(&empty_bar[stage]);        // frees the smem stage when these MMAs retire
-                        if (grp == groups - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
-                    }
-                    __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            }
+        if (p.kc == 64) {
+            if (p.msub == 2) mma_role<4, 2>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+            else mma_role<4, 1>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+        } else {
+            if (p.msub == 2) mma_role<2, 2>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+            else mma_role<2, 1>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
         }
     } else {
         // =================== epilogue warps (2..9) ===================
@@ -537,6 +558,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+            if (p.fast_epi && p.fe.res && ncols > 0) {
+                // the residual rows this thread will add: pull them into L2 while the MMAs of this tile run
+                for (int sub = 0; sub < p.msub; ++sub) {
+                    const int trow = row + sub * TC_BLOCK_M;
+                    const int wt = trow % p.Wt, ht = (trow / p.Wt) % p.Ht, bt = trow / (p.Wt * p.Ht);
+                    const int b = tb * p.Bt + bt;
+                    if (b < d.B) {
+                        const size_t opix = ((size_t)b * p.Ho + ty * p.Ht + ht) * p.Wo + tx * p.Wt + wt;
+                        const __nv_bfloat16 *rp = p.fe.res + opix * d.cout + nt * p.block_n + c_begin;
+                        for (int c = 0; c < ncols; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
+                    }
+                }
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             for (int sub = 0; sub < p.msub && ncols > 0; ++sub) {
@@ -763,7 +797,8 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     // at least ~4 tiles per SM; halves the weight traffic per output pixel
     static const int msub_max = getenv("FUSG_MSUB1") ? 1 : 2;
     const long long rows = (long long)d.B * Ho * Wo;
-    p.msub = (msub_max == 2 && rows / 256 * p.n_tiles >= 4LL * num_sms && rows % 256 == 0) ? 2 : 1;
+    // (only for 3x3 layers: a 1x1 layer has one or two k-blocks per tile and is bound by its output writes)
+    p.msub = (msub_max == 2 && d.ksize == 3 && rows / 256 * p.n_tiles >= 4LL * num_sms && rows % 256 == 0) ? 2 : 1;
     const int trows = TC_BLOCK_M * p.msub;
     p.Wt = Wo < 128 ? Wo : 128;
     p.Ht = (trows / p.Wt) < Ho ? (trows / p.Wt) : Ho;
