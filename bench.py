@@ -285,8 +285,13 @@ def run_ours(args):
         tc = agg.get(1, [0.0, 1e-9, 0])
         achieved = tc[0] / tc[1] / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic_summary.json")
+        if os.path.exists(tpath) and B == 64:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
         roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu; B=64)", "traffic_source": traffic_src, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_per_step": tc[2] // 2, "avg_launch_ms": 1e3 * tc[1] / max(1, tc[2]),
                 "algorithmic_flops_per_step": tc[0] / 2, "share_of_vunet_time": tc[1] / max(1e-9, sum(a[1] for a in agg.values()))}
         # fused warp kernel alone (BASELINE config 3 shape, HBM bound)
@@ -319,7 +324,7 @@ def run_ours(args):
                                    f"(BASELINE config 2), random-init weights" + (", NCCL all-gather of completed uint8 crops" if world > 1 else ""),
                        "crops_per_gpu": B, "global_crops_per_step": world * B, "parallelism": f"crop-sharded dp{world}",
                        "l2": "per-step activations (>5 GB) exceed the 126 MB L2; no explicit flush",
-                       "launch": "one CUDA-graph replay per step (gpu_launches counts the kernels inside the graphs)" if world == 1 else "eager launches + NCCL all-gather"},
+                       "launch": "one CUDA-graph replay per step (gpu_launches counts the kernels inside the graphs)" + (" + eager NCCL all-gather" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "note": "NovelViewPipeline.submit/result: pinned host inputs -> H2D, Sampler noise drawn on the CPU generator (reference "

@@ -46,7 +46,7 @@ class NovelViewPipeline:
         self.dev = next(model.parameters()).device
         self.depth = depth
         self.gather_fn = gather_fn        # optional device-side collective on the completed crops (parallel.gather_crops)
-        self.use_graph = use_graph and gather_fn is None      # collectives stay outside the graph
+        self.use_graph = use_graph        # the collective (if any) is issued eagerly after the graph replay
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.out_stream = torch.cuda.Stream(self.dev)
         self.slots = [_Slot() for _ in range(depth)]
