@@ -199,7 +199,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    def run_steps(n, resident):
+    def run_steps(n, resident, pipe=pipe):
         last = None
         for _ in range(n):
             t = pipe.submit(host, resident=resident)
@@ -240,13 +240,18 @@ def run_ours(args):
 
     # ---- end-to-end loop: every step copies its own pinned inputs H2D, draws the Sampler noise on the
     # CPU generator (reference semantics), and lands its own results in host memory, inside the timed region
-    e2e_steps = max(4, min(args.steps, 20))
+    # (one compute stream shared by the two slots: with host copies in the loop, graphs that overlap only
+    # partially slow each other down -- measured 11.8 vs 14.2 ms/step, scripts/e2e_probe.py)
+    pipe_e2e = NovelViewPipeline(model, depth=2, shared_stream=True,
+                                 gather_fn=(lambda c: gather_crops(c, world * B)) if world > 1 else None)
+    run_steps(4, resident=False, pipe=pipe_e2e)
+    e2e_steps = max(4, min(args.steps, 30))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record(pipe.copy_stream)
-    run_steps(e2e_steps, resident=False)
-    e1.record(pipe.out_stream)
+    e0.record(pipe_e2e.copy_stream)
+    run_steps(e2e_steps, resident=False, pipe=pipe_e2e)
+    e1.record(pipe_e2e.out_stream)
     torch.cuda.synchronize()
     e2e_wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = reduce_max(max(e0.elapsed_time(e1), e2e_wall))

@@ -32,6 +32,7 @@ class _Slot:
         self.dev_out = None      # device outputs (static)
         self.out = None          # pinned host outputs
         self.done = None
+        self.copied = None       # event: this slot's last H2D (inputs + noise) has been consumed from the pinned buffers
         self.launches = 0
         self.stream = None       # this slot's compute stream: the small-grid tail layers of one batch overlap the
                                  # full-grid layers of the next batch in flight
@@ -40,7 +41,7 @@ class _Slot:
 class NovelViewPipeline:
     WARP_KEYS = ("src", "src_kp", "dst_kp", "K", "E_src", "E_dst", "kp3d")
 
-    def __init__(self, model, depth: int = 2, gather_fn=None, use_graph: bool = True):
+    def __init__(self, model, depth: int = 2, gather_fn=None, use_graph: bool = True, shared_stream: bool = False):
         _lib.require_cuda()
         self.model = model
         self.dev = next(model.parameters()).device
@@ -50,8 +51,9 @@ class NovelViewPipeline:
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.out_stream = torch.cuda.Stream(self.dev)
         self.slots = [_Slot() for _ in range(depth)]
+        one = torch.cuda.Stream(self.dev)
         for sl in self.slots:
-            sl.stream = torch.cuda.Stream(self.dev)
+            sl.stream = one if shared_stream else torch.cuda.Stream(self.dev)
         self.n = 0
 
     # ------------------------------------------------------------------ one step of device work
@@ -92,11 +94,15 @@ class NovelViewPipeline:
         eng.noise_provider = prev
 
     def _draw_noise(self, slot: _Slot):
-        """CPU default generator, reference order/shapes (NCHW), shipped as NHWC into the static buffers."""
-        # the slot's previous batch has completed (submit() waited on slot.done), so its staging buffers are free
-        for buf, stage, (b, c, h, w) in zip(slot.noise, slot.noise_stage, slot.noise_shapes):
+        """CPU default generator, reference order/shapes (NCHW), laid out NHWC in the slot's pinned staging buffers."""
+        if slot.copied is not None:
+            slot.copied.synchronize()          # the previous H2D out of these staging buffers has long completed
+        for stage, (b, c, h, w) in zip(slot.noise_stage, slot.noise_shapes):
             eps = torch.randn(b, c, h, w)
             stage.copy_(eps.permute(0, 2, 3, 1))
+
+    def _upload_noise(self, slot: _Slot):
+        for buf, stage in zip(slot.noise, slot.noise_stage):
             buf.copy_(stage, non_blocking=True)
 
     # ------------------------------------------------------------------ public API
@@ -106,18 +112,24 @@ class NovelViewPipeline:
         resident=True skips the host copies (inputs / noise already in the slot; outputs stay on the device)."""
         ticket = self.n
         slot = self.slots[ticket % self.depth]
+        fresh = slot.inp is None or any(tuple(slot.inp[k].shape) != tuple(v.shape) for k, v in batch.items())
+        if not resident and not fresh:
+            self._draw_noise(slot)                                    # host RNG work overlaps the batches still in flight
         if slot.done is not None:
             slot.done.synchronize()                                   # the slot's previous outputs were consumed
-        if slot.inp is None or any(tuple(slot.inp[k].shape) != tuple(v.shape) for k, v in batch.items()):
+        if fresh:
             self._prepare_slot(slot, batch)
+            if not resident:
+                self._draw_noise(slot)
         eng = self.model.engine()
         if not resident:
             with torch.cuda.stream(self.copy_stream):
                 for k, v in batch.items():
                     slot.inp[k].copy_(v, non_blocking=True)
-                self._draw_noise(slot)
+                self._upload_noise(slot)
                 copied = torch.cuda.Event()
                 copied.record(self.copy_stream)
+            slot.copied = copied
             slot.stream.wait_event(copied)
         with torch.cuda.stream(slot.stream):
             if slot.graph is not None:
