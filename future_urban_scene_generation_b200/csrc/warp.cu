@@ -33,96 +33,21 @@ namespace fusg {
 struct VisShared {
     int vx[N_KP], vy[N_KP];
     double dist[N_VIS];
-    int area[2 * N_VIS];
-    int oob;
 };
 
-// one pose: fills sm.area / sm.oob; all threads of the CTA participate
-__device__ void visibility_pose(VisShared &sm, const double *K, const double *E, const double *kp3d, int H, int W) {
-    const int tid = threadIdx.x;
-    if (tid < N_KP) {
-        double u, v;
-        project_point(K, E, kp3d + 3 * tid, &u, &v);
-        // int(): truncation toward zero; values far outside int range are clamped (they are
-        // rejected as out-of-frame below anyway)
-        u = fmin(fmax(u, -1.0e9), 1.0e9);
-        v = fmin(fmax(v, -1.0e9), 1.0e9);
-        sm.vx[tid] = (int)u;
-        sm.vy[tid] = (int)v;
-    } else if (tid >= 32 && tid < 32 + N_VIS) {
-        sm.dist[tid - 32] = plane_distance(E, kp3d, tid - 32);
-    } else if (tid >= 64 && tid < 64 + 2 * N_VIS) {
-        sm.area[tid - 64] = 0;
-    } else if (tid == 96) {
-        sm.oob = 0;
-    }
-    __syncthreads();
-    if (tid < N_KP) {
-        if (sm.vx[tid] < 0 || sm.vx[tid] >= W || sm.vy[tid] < 0 || sm.vy[tid] >= H) sm.oob = 1;
-    }
-    __syncthreads();
-    if (sm.oob) return;
+constexpr int VIS_WARPS = 4;     // poses per CTA (one warp each; no block-level barriers)
 
-    // occluder sets: planes strictly nearer to the camera
-    unsigned nearer[N_VIS];
-    for (int p = 0; p < N_VIS; ++p) {
-        unsigned mk = 0;
-        for (int q = 0; q < N_VIS; ++q)
-            if (sm.dist[q] < sm.dist[p]) mk |= 1u << q;
-        nearer[p] = mk;
-    }
-    int px[N_VIS][6], py[N_VIS][6];
-    for (int p = 0; p < N_VIS; ++p)
-        for (int k = 0; k < c_plane_n[p]; ++k) {
-            px[p][k] = sm.vx[c_plane_kp[p][k]];
-            py[p][k] = sm.vy[c_plane_kp[p][k]];
-        }
-    int cnt_abs[N_VIS], cnt_occ[N_VIS];
-    for (int p = 0; p < N_VIS; ++p) cnt_abs[p] = cnt_occ[p] = 0;
-    // every polygon lies inside the bounding box of the 12 projected keypoints: only those rows / words can hold pixels
-    int bx0 = sm.vx[0], bx1 = sm.vx[0], by0 = sm.vy[0], by1 = sm.vy[0];
-    for (int k = 1; k < N_KP; ++k) {
-        bx0 = min(bx0, sm.vx[k]); bx1 = max(bx1, sm.vx[k]);
-        by0 = min(by0, sm.vy[k]); by1 = max(by1, sm.vy[k]);
-    }
-    const int w0 = bx0 >> 5, w1 = bx1 >> 5;
-    for (int y = by0 + tid; y <= by1; y += blockDim.x) {
-        int lo[N_VIS][MAX_RANGES], hi[N_VIS][MAX_RANGES], rc[N_VIS];
-        for (int p = 0; p < N_VIS; ++p) rc[p] = poly_row_ranges(px[p], py[p], c_plane_n[p], y, lo[p], hi[p]);
-        for (int w = w0; w <= w1; ++w) {
-            unsigned bits[N_VIS];
-            for (int p = 0; p < N_VIS; ++p) bits[p] = ranges_word(lo[p], hi[p], rc[p], w);
-            for (int p = 0; p < N_VIS; ++p) {
-                unsigned occl = 0;
-                for (int q = 0; q < N_VIS; ++q)
-                    if ((nearer[p] >> q) & 1u) occl |= bits[q];
-                cnt_abs[p] += __popc(bits[p]);
-                cnt_occ[p] += __popc(bits[p] & ~occl);
-            }
-        }
-    }
-    for (int p = 0; p < N_VIS; ++p) {
-        int a = cnt_abs[p], o = cnt_occ[p];
-        for (int off = 16; off > 0; off >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, off);
-            o += __shfl_xor_sync(0xffffffffu, o, off);
-        }
-        if ((tid & 31) == 0) {
-            atomicAdd(&sm.area[2 * p], a);
-            atomicAdd(&sm.area[2 * p + 1], o);
-        }
-    }
-    __syncthreads();
-}
-
-// grid.x = number of poses.  Pose g reads K[g / poses_per_K], E[g], kp3d[g / poses_per_K].
-// E is addressed as E0 (even g) / E1 (odd g) when E1 != nullptr (the fused src/dst layout).
-__global__ void __launch_bounds__(256) k_visibility(const double *__restrict__ K, const double *__restrict__ E0,
-                                                    const double *__restrict__ E1, const double *__restrict__ kp3d,
-                                                    uint8_t *__restrict__ vis, int32_t *__restrict__ pts,
-                                                    int32_t *__restrict__ areas, int H, int W) {
-    __shared__ VisShared sm;
-    const int g = blockIdx.x;
+// grid.x = ceil(poses / VIS_WARPS).  Pose g reads K[b], kp3d[b], and E0/E1[b] (fused src/dst layout, b = g/2)
+// when E1 != nullptr, else K[g], E0[g], kp3d[g].
+__global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__restrict__ K, const double *__restrict__ E0,
+                                                               const double *__restrict__ E1, const double *__restrict__ kp3d,
+                                                               uint8_t *__restrict__ vis, int32_t *__restrict__ pts,
+                                                               int32_t *__restrict__ areas, int n_poses, int H, int W) {
+    __shared__ VisShared sm_all[VIS_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * VIS_WARPS + warp;
+    if (g >= n_poses) return;
+    VisShared &sm = sm_all[warp];
     const double *Kp, *Ep, *Xp;
     if (E1) {
         const int b = g >> 1;
@@ -131,16 +56,83 @@ __global__ void __launch_bounds__(256) k_visibility(const double *__restrict__ K
     } else {
         Kp = K + 9 * g; Xp = kp3d + 36 * g; Ep = E0 + 12 * g;
     }
-    visibility_pose(sm, Kp, Ep, Xp, H, W);
-    const int tid = threadIdx.x;
-    if (tid < N_VIS) {
-        uint8_t v = 0;
-        if (!sm.oob) v = (double)sm.area[2 * tid + 1] > 0.9 * (double)sm.area[2 * tid] ? 1 : 0;
-        else v = 0xff;                                    // out-of-frame marker
-        vis[N_VIS * g + tid] = v;
+    // 12 projections (lanes 0..11) and 7 plane distances (lanes 12..18)
+    if (lane < N_KP) {
+        double u, v;
+        project_point(Kp, Ep, Xp + 3 * lane, &u, &v);
+        // int(): truncation toward zero; far-out values are clamped (rejected as out-of-frame below anyway)
+        u = fmin(fmax(u, -1.0e9), 1.0e9);
+        v = fmin(fmax(v, -1.0e9), 1.0e9);
+        sm.vx[lane] = (int)u;
+        sm.vy[lane] = (int)v;
+    } else if (lane < N_KP + N_VIS) {
+        sm.dist[lane - N_KP] = plane_distance(Ep, Xp, lane - N_KP);
     }
-    if (pts && tid < N_KP) { pts[(N_KP * g + tid) * 2] = sm.vx[tid]; pts[(N_KP * g + tid) * 2 + 1] = sm.vy[tid]; }
-    if (areas && tid < 2 * N_VIS) areas[2 * N_VIS * g + tid] = sm.oob ? -1 : sm.area[tid];
+    __syncwarp();
+    bool oob = false;
+    if (lane < N_KP) oob = sm.vx[lane] < 0 || sm.vx[lane] >= W || sm.vy[lane] < 0 || sm.vy[lane] >= H;
+    oob = __any_sync(0xffffffffu, oob);
+    int cnt_abs[N_VIS], cnt_occ[N_VIS];
+#pragma unroll
+    for (int p = 0; p < N_VIS; ++p) cnt_abs[p] = cnt_occ[p] = 0;
+    if (!oob) {
+        // occluder sets: planes strictly nearer to the camera
+        unsigned nearer[N_VIS];
+#pragma unroll
+        for (int p = 0; p < N_VIS; ++p) {
+            unsigned mk = 0;
+#pragma unroll
+            for (int q = 0; q < N_VIS; ++q)
+                if (sm.dist[q] < sm.dist[p]) mk |= 1u << q;
+            nearer[p] = mk;
+        }
+        // every polygon lies inside the bounding box of the 12 projected keypoints
+        int bx0 = sm.vx[0], bx1 = sm.vx[0], by0 = sm.vy[0], by1 = sm.vy[0];
+        for (int k = 1; k < N_KP; ++k) {
+            bx0 = min(bx0, sm.vx[k]); bx1 = max(bx1, sm.vx[k]);
+            by0 = min(by0, sm.vy[k]); by1 = max(by1, sm.vy[k]);
+        }
+        const int w0 = bx0 >> 5, w1 = bx1 >> 5;
+        for (int y = by0 + lane; y <= by1; y += 32) {
+            int lo[N_VIS][MAX_RANGES], hi[N_VIS][MAX_RANGES], rc[N_VIS];
+#pragma unroll 1
+            for (int p = 0; p < N_VIS; ++p) {
+                int px[6], py[6];
+                const int n = c_plane_n[p];
+                for (int k = 0; k < n; ++k) { px[k] = sm.vx[c_plane_kp[p][k]]; py[k] = sm.vy[c_plane_kp[p][k]]; }
+                rc[p] = poly_row_ranges(px, py, n, y, lo[p], hi[p]);
+            }
+            for (int w = w0; w <= w1; ++w) {
+                unsigned bits[N_VIS];
+#pragma unroll
+                for (int p = 0; p < N_VIS; ++p) bits[p] = ranges_word(lo[p], hi[p], rc[p], w);
+#pragma unroll
+                for (int p = 0; p < N_VIS; ++p) {
+                    unsigned occl = 0;
+#pragma unroll
+                    for (int q = 0; q < N_VIS; ++q)
+                        if ((nearer[p] >> q) & 1u) occl |= bits[q];
+                    cnt_abs[p] += __popc(bits[p]);
+                    cnt_occ[p] += __popc(bits[p] & ~occl);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < N_VIS; ++p) {
+            for (int off = 16; off > 0; off >>= 1) {
+                cnt_abs[p] += __shfl_xor_sync(0xffffffffu, cnt_abs[p], off);
+                cnt_occ[p] += __shfl_xor_sync(0xffffffffu, cnt_occ[p], off);
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < N_VIS; ++p) {
+            vis[N_VIS * g + p] = oob ? 0xff : ((double)cnt_occ[p] > 0.9 * (double)cnt_abs[p] ? 1 : 0);   // 0xff: out-of-frame marker
+            if (areas) { areas[2 * N_VIS * g + 2 * p] = oob ? -1 : cnt_abs[p]; areas[2 * N_VIS * g + 2 * p + 1] = oob ? -1 : cnt_occ[p]; }
+        }
+    }
+    if (pts && lane < N_KP) { pts[(N_KP * g + lane) * 2] = sm.vx[lane]; pts[(N_KP * g + lane) * 2 + 1] = sm.vy[lane]; }
 }
 
 // ============================================================================================
@@ -207,44 +199,70 @@ __global__ void __launch_bounds__(HG_WARPS * 32) k_homography(const int32_t *__r
 }
 
 
-// thread-per-(crop, plane) variant: same results, better throughput once tens of thousands of
-// solves are in flight (each solve is a long dependent fp64 chain; here 32x more of them overlap)
-__global__ void __launch_bounds__(128) k_homography_thread(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
-                                                           const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j,
-                                                           double *__restrict__ H12, double *__restrict__ Minv, int B, int H, int W) {
+// Large batches: thread-per-solve (each solve is a long dependent fp64 chain; 32x more of them overlap
+// than with a warp per solve), fed from COMPACTED task lists so that every lane of a warp has a real solve
+// of the same kind: k_plane_gate applies the gating / remap of planes_utils.py:57-68 and appends the
+// surviving (crop, plane) tasks to a 6-point list (left/right, LM-refined) or a 4-point list; skipped
+// planes get their outputs written there.  Outputs are indexed by task id, so the (non-deterministic)
+// list order does not affect results.
+__global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                    const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j, double *__restrict__ H12,
+                                                    double *__restrict__ Minv, int *__restrict__ counters, int *__restrict__ list6,
+                                                    int *__restrict__ list4, int B, int H, int W) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * N_TEX) return;
     const int b = t / N_TEX, i = t % N_TEX;
     const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
-    int j = -1;
     bool bad = sv[0] == 0xff || dv[0] == 0xff;
     const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
     for (int k = 0; k < N_KP && !bad; ++k) {
         if (sk[2 * k] < 0 || sk[2 * k] >= W || sk[2 * k + 1] < 0 || sk[2 * k + 1] >= H) bad = true;
         if (dk[2 * k] < 0 || dk[2 * k] >= W || dk[2 * k + 1] < 0 || dk[2 * k + 1] >= H) bad = true;
     }
-    double Hm[9], Mi[9];
-    for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
-    if (bad) {
-        j = -2;
-    } else {
-        j = plane_target(i, sv, dv);
-        if (j >= 0) {
-            const int n = c_plane_n[i];
-            int s[12], d[12];
-            for (int k = 0; k < n; ++k) {
-                s[2 * k] = sk[2 * c_plane_kp[i][k]]; s[2 * k + 1] = sk[2 * c_plane_kp[i][k] + 1];
-                d[2 * k] = dk[2 * c_plane_kp[j][k]]; d[2 * k + 1] = dk[2 * c_plane_kp[j][k] + 1];
-            }
-            if (!find_homography_thread(s, d, n, Hm)) {
-                j = -1;
-                for (int k = 0; k < 9; ++k) Hm[k] = 0;
-            } else {
-                invert3(Hm, Mi);
-            }
-        }
-    }
+    const int j = bad ? -2 : plane_target(i, sv, dv);
     plane_j[t] = (int8_t)j;
+    if (j >= 0) {
+        if (i < 2) list6[atomicAdd(&counters[0], 1)] = t;
+        else list4[atomicAdd(&counters[1], 1)] = t;
+    } else {
+        for (int k = 0; k < 9; ++k) Minv[9 * t + k] = 0;
+        if (H12) for (int k = 0; k < 9; ++k) H12[9 * t + k] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_homography_list(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                         int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
+                                                         const int *__restrict__ counters, const int *__restrict__ list6,
+                                                         const int *__restrict__ list4) {
+    // blocks [0, ceil(n6/128)) take the 6-point list (longest solves first), the following blocks the 4-point list
+    const int n6 = counters[0], n4 = counters[1];
+    const int blocks6 = (n6 + 127) >> 7;
+    int t;
+    if ((int)blockIdx.x < blocks6) {
+        const int idx = blockIdx.x * 128 + threadIdx.x;
+        if (idx >= n6) return;
+        t = list6[idx];
+    } else {
+        const int idx = (blockIdx.x - blocks6) * 128 + threadIdx.x;
+        if (idx >= n4) return;
+        t = list4[idx];
+    }
+    const int b = t / N_TEX, i = t % N_TEX, j = plane_j[t];
+    const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
+    const int n = c_plane_n[i];
+    int s[12], d[12];
+    for (int k = 0; k < n; ++k) {
+        s[2 * k] = sk[2 * c_plane_kp[i][k]]; s[2 * k + 1] = sk[2 * c_plane_kp[i][k] + 1];
+        d[2 * k] = dk[2 * c_plane_kp[j][k]]; d[2 * k + 1] = dk[2 * c_plane_kp[j][k] + 1];
+    }
+    double Hm[9], Mi[9];
+    // H21 is only ever used through its "is None" test, the same (symmetric) degeneracy test as H12's
+    if (!find_homography_thread(s, d, n, Hm)) {
+        plane_j[t] = -1;
+        for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
+    } else {
+        invert3(Hm, Mi);
+    }
     for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
     if (H12) for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
 }
@@ -586,16 +604,17 @@ static size_t warp_smem_bytes(int H, int W) {
     return (size_t)src_pad + (size_t)MAX_HW * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + sizeof(WarpSmemHeader) + 128;
 }
 
+// workspace: Minv [B,5,9] f64 | counters [4] i32 | list6 [2B] i32 | list4 [3B] i32
 extern "C" size_t fusg_warp_workspace_bytes(int B) {
     if (B <= 0) return 0;
-    return (size_t)B * N_TEX * 9 * sizeof(double);
+    return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 5 * (size_t)B) * sizeof(int);
 }
 
 extern "C" int fusg_visibility(const double *K, const double *E, const double *kp3d, uint8_t *vis, int32_t *pts,
                                int32_t *areas, int B, int H, int W, void *stream) {
     if (!K || !E || !kp3d || !vis || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    k_visibility<<<B, 128, 0, st>>>(K, E, nullptr, kp3d, vis, pts, areas, H, W);
+    k_visibility<<<(B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E, nullptr, kp3d, vis, pts, areas, B, H, W);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
@@ -644,10 +663,17 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
             return fusg_check_launch();
         attr_set = true;
     }
-    k_visibility<<<2 * B, 128, 0, st>>>(K, E_src, E_dst, kp3d, vis, nullptr, nullptr, H, W);
+    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, vis, nullptr, nullptr, 2 * B, H, W);
     // small batches: latency matters -> one warp per solve; large batches: throughput -> one thread per solve
     if (B * N_TEX <= 8192) k_homography<<<(B * N_TEX + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
-    else k_homography_thread<<<(B * N_TEX + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
+    else {
+        int *counters = reinterpret_cast<int *>(Minv + (size_t)B * N_TEX * 9);
+        int *list6 = counters + 4, *list4 = list6 + 2 * (size_t)B;
+        if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
+        k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
+        k_homography_list<<<(2 * B + 127) / 128 + (3 * B + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4);
+        fusg_count_launch(1);
+    }
     k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);
     fusg_count_launch(3);
     return fusg_check_launch();

@@ -156,3 +156,22 @@ def test_large_batch_properties(cuda):
     res2 = warp_batch(batch["src"][sub], batch["src_kp"][sub], batch["dst_kp"][sub], batch["K"][sub], batch["E_src"][sub],
                       batch["E_dst"][sub], batch["kp3d"][sub])
     assert cuda.equal(res2.warped, res.warped[sub])
+
+
+def test_large_batch_solver_path_matches_small_batch(cuda):
+    """Above 8192 (crop, plane) tasks the homographies come from the compacted thread-per-solve kernels
+    instead of the warp-cooperative one; both must give the same bits (and the oracle's, by transitivity)."""
+    from future_urban_scene_generation_b200.warp_learn import warp_batch
+    torch = cuda
+    U, R = 96, 24                                   # 96 unique crops tiled to 2304 (> 8192 / 5)
+    batch = synth.make_warp_batch(300, U)
+    small = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"])
+    big_in = {k: np.concatenate([v] * R, 0) for k, v in batch.items()}
+    big = warp_batch(big_in["src"], big_in["src_kp"], big_in["dst_kp"], big_in["K"], big_in["E_src"], big_in["E_dst"], big_in["kp3d"])
+    torch.cuda.synchronize()
+    for r in (0, 7, R - 1):
+        sl = slice(r * U, (r + 1) * U)
+        assert torch.equal(big.plane_j[sl], small.plane_j)
+        assert torch.equal(big.vis[sl], small.vis)
+        assert torch.equal(big.H12[sl].view(torch.int64), small.H12.view(torch.int64))
+        assert torch.equal(big.warped[sl], small.warped)
