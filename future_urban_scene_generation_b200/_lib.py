@@ -28,6 +28,7 @@ def _load():
         "fusg_last_error": ([], C.c_char_p),
         "fusg_kernel_launches": ([], i),
         "fusg_warp_workspace_bytes": ([i], sz),
+        "fusg_warp_workspace_bytes_hw": ([i, i, i], sz),
         "fusg_warp_fused": ([vp] * 11 + [vp, sz, i, i, i, vp], i),
         "fusg_visibility": ([vp] * 6 + [i, i, i, vp], i),
         "fusg_get_planes": ([vp] * 3 + [i, i, i, vp], i),

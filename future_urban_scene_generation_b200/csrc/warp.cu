@@ -591,6 +591,76 @@ __global__ void __launch_bounds__(256) k_warp_perspective(const uint8_t *__restr
     o[0] = v.x; o[1] = v.y; o[2] = v.z;
 }
 
+
+// ============================================================================================
+// Frames larger than the shared-memory path (the reference runs the stage on whole 1280x720 frames,
+// GUI/app_interface.py:181): same arithmetic, source and polygon bit masks read from global memory / L2.
+// ============================================================================================
+__global__ void __launch_bounds__(128) k_plane_masks(const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
+                                                     uint32_t *__restrict__ masks, int H, int words) {
+    // grid (H, 5, B): bit mask of row y of SOURCE plane i (only for planes that are warped)
+    const int y = blockIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (plane_j[b * N_TEX + i] < 0) return;
+    __shared__ int lo[MAX_RANGES], hi[MAX_RANGES], rc;
+    if (threadIdx.x == 0) {
+        int px[6], py[6], l[MAX_RANGES], h[MAX_RANGES];
+        const int n = c_plane_n[i];
+        for (int k = 0; k < n; ++k) { px[k] = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2]; py[k] = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1]; }
+        const int c = poly_row_ranges(px, py, n, y, l, h);
+        for (int k = 0; k < c; ++k) { lo[k] = l[k]; hi[k] = h[k]; }
+        rc = c;
+    }
+    __syncthreads();
+    uint32_t *row = masks + (((size_t)b * N_TEX + i) * H + y) * words;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) row[w] = ranges_word(lo, hi, rc, w);
+}
+
+__global__ void __launch_bounds__(256) k_warp_frame(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
+                                                    const int8_t *__restrict__ plane_j, const double *__restrict__ Minv,
+                                                    const uint32_t *__restrict__ masks, uint8_t *__restrict__ warped, int H, int W, int words) {
+    // grid (H, 5, B): one output row of output plane j
+    const int y = blockIdx.x, j = blockIdx.y, b = blockIdx.z;
+    __shared__ double M[9];
+    __shared__ int s_i, s_lo, s_hi;
+    if (threadIdx.x == 0) {
+        int i = -1;
+        for (int k = 0; k < N_TEX; ++k) if (plane_j[b * N_TEX + k] == j) i = k;      // last writer wins
+        s_i = i;
+        if (i >= 0) {
+            for (int k = 0; k < 9; ++k) M[k] = Minv[((size_t)b * N_TEX + i) * 9 + k];
+            int bbox[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+            for (int k = 0; k < c_plane_n[i]; ++k) {
+                const int vx = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2], vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
+                bbox[0] = min(bbox[0], vx); bbox[1] = max(bbox[1], vx); bbox[2] = min(bbox[2], vy); bbox[3] = max(bbox[3], vy);
+            }
+            int xlo, xhi;
+            row_active_span(M, y, W, bbox, xlo, xhi);
+            s_lo = xlo; s_hi = xhi;
+        }
+    }
+    __syncthreads();
+    uint8_t *orow = warped + ((((size_t)b * N_TEX + j) * H + y) * W) * 3;
+    const int i = s_i;
+    if (i < 0 || s_lo > s_hi) {
+        for (int k = threadIdx.x; k < W * 3; k += blockDim.x) orow[k] = 0;
+        return;
+    }
+    const uint8_t *simg = src + (size_t)b * H * W * 3;
+    const uint32_t *mk = masks + ((size_t)b * N_TEX + i) * H * words;
+    const int bw = warp_block_w(H, W);
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        uchar3 v = make_uchar3(0, 0, 0);
+        if (x >= s_lo && x <= s_hi) {
+            const int bx = (x / bw) * bw;
+            const RowBase rb = row_base(M, bx, y);
+            int X, Y;
+            src_coord(M, rb, x - bx, X, Y);
+            v = bilinear_tap4<true>(simg, mk, words, H, W, X, Y);
+        }
+        orow[3 * x] = v.x; orow[3 * x + 1] = v.y; orow[3 * x + 2] = v.z;
+    }
+}
+
 }  // namespace fusg
 
 // ================================================================================================
@@ -604,10 +674,16 @@ static size_t warp_smem_bytes(int H, int W) {
     return (size_t)src_pad + (size_t)MAX_HW * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + sizeof(WarpSmemHeader) + 128;
 }
 
-// workspace: Minv [B,5,9] f64 | counters [4] i32 | list6 [2B] i32 | list4 [3B] i32
-extern "C" size_t fusg_warp_workspace_bytes(int B) {
-    if (B <= 0) return 0;
-    return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 5 * (size_t)B) * sizeof(int);
+// workspace: Minv [B,5,9] f64 | counters [4] i32 | list6 [2B] i32 | list4 [3B] i32 | (frames > 256: plane bit masks [B,5,H,ceil(W/32)] u32)
+static size_t warp_ws_base(int B) { return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 5 * (size_t)B) * sizeof(int); }
+
+extern "C" size_t fusg_warp_workspace_bytes(int B) { return B <= 0 ? 0 : warp_ws_base(B); }
+
+extern "C" size_t fusg_warp_workspace_bytes_hw(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    size_t n = (warp_ws_base(B) + 15) & ~(size_t)15;
+    if (H > MAX_HW || W > MAX_HW) n += (size_t)B * N_TEX * H * ((W + 31) / 32) * sizeof(uint32_t);
+    return n;
 }
 
 extern "C" int fusg_visibility(const double *K, const double *E, const double *kp3d, uint8_t *vis, int32_t *pts,
@@ -652,12 +728,13 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
                                void *stream) {
     if (!src || !src_kp || !dst_kp || !K || !E_src || !E_dst || !kp3d || !warped || !vis || !plane_j || !workspace) return FUSG_ERR_ARG;
     if (B <= 0) return FUSG_ERR_ARG;
-    if (H < 8 || W < 8 || H > MAX_HW || W > MAX_HW) return FUSG_ERR_UNSUPPORTED;
-    if (workspace_bytes < fusg_warp_workspace_bytes(B)) return FUSG_ERR_WORKSPACE;
+    if (H < 8 || W < 8 || H > 65535 || B > 65535) return FUSG_ERR_UNSUPPORTED;
+    const bool frame_path = H > MAX_HW || W > MAX_HW;
+    if (workspace_bytes < fusg_warp_workspace_bytes_hw(B, H, W)) return FUSG_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     double *Minv = reinterpret_cast<double *>(workspace);
     static bool attr_set = false;
-    const size_t smem = warp_smem_bytes(H, W);
+    const size_t smem = H <= MAX_HW && W <= MAX_HW ? warp_smem_bytes(H, W) : 0;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW, MAX_HW)) != cudaSuccess)
             return fusg_check_launch();
@@ -674,7 +751,15 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
         k_homography_list<<<(2 * B + 127) / 128 + (3 * B + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4);
         fusg_count_launch(1);
     }
-    k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);
-    fusg_count_launch(3);
+    if (!frame_path) {
+        k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);
+        fusg_count_launch(3);
+    } else {
+        const int words = (W + 31) / 32;
+        uint32_t *masks = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(workspace) + ((warp_ws_base(B) + 15) & ~(size_t)15));
+        k_plane_masks<<<dim3(H, N_TEX, B), 128, 0, st>>>(src_kp, plane_j, masks, H, words);
+        k_warp_frame<<<dim3(H, N_TEX, B), 256, 0, st>>>(src, src_kp, plane_j, Minv, masks, warped, H, W, words);
+        fusg_count_launch(4);
+    }
     return fusg_check_launch();
 }

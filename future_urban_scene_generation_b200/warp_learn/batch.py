@@ -60,7 +60,7 @@ def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None
             plane_j=torch.empty((B, 5), dtype=torch.int8, device=device),
             H12=torch.empty((B, 5, 3, 3), dtype=torch.float64, device=device))
     L = _lib.lib()
-    ws_bytes = L.fusg_warp_workspace_bytes(B)
+    ws_bytes = L.fusg_warp_workspace_bytes_hw(B, H, W)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         rc = L.fusg_warp_fused(_lib.ptr(src), _lib.ptr(skp), _lib.ptr(dkp), _lib.ptr(Kt), _lib.ptr(Es), _lib.ptr(Ed),

@@ -36,8 +36,9 @@ int fusg_kernel_launches(void);        /* number of kernels this library launche
 /* Warp stage                                                                              */
 /* ====================================================================================== */
 
-/* Bytes of device workspace fusg_warp_fused needs for a batch of B crops. */
+/* Bytes of device workspace fusg_warp_fused needs for a batch of B crops (H, W <= 256), and for any frame size. */
 size_t fusg_warp_workspace_bytes(int B);
+size_t fusg_warp_workspace_bytes_hw(int B, int H, int W);
 
 /*
  * Fused planar warp for a batch of B vehicle crops.  Stands behind
@@ -61,9 +62,10 @@ size_t fusg_warp_workspace_bytes(int B);
  *   H12      [B,5,9]   f64  out (may be NULL): homography of source plane i (zeros if skipped)
  *   workspace, workspace_bytes: device scratch, >= fusg_warp_workspace_bytes(B)
  *
- * Supported: 8 <= H,W <= 256 (the crop is staged in shared memory); every vertex must lie inside
- * the frame, else that crop's outputs are zero and plane_j = -2 (the reference's clipped-polygon
- * regime is not covered).
+ * H, W >= 8.  Up to 256 x 256 the crop is staged in shared memory (the HBM-bound fast path); larger
+ * frames (the reference works on 1280 x 720) gather from global memory with the same arithmetic and need
+ * fusg_warp_workspace_bytes_hw(B,H,W) of workspace.  Every vertex must lie inside the frame, else that
+ * crop's outputs are zero and plane_j = -2 (the reference's clipped-polygon regime is not covered).
  */
 int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp,
                     const double *K, const double *E_src, const double *E_dst, const double *kp3d,

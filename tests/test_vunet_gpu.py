@@ -138,6 +138,8 @@ CONV_CASES = [
     ("res_s2d", 5, (128,), 128, 3, 1, 4, True, False, 2),
     ("ar_res_1024", 5, (512, 512), 512, 3, 1, 2, True, False, 0),
     ("sampler_blk", 5, (512,), 128, 3, 1, 2, False, True, 3),
+    ("ar_res_1024_b64", 64, (512, 512), 512, 3, 1, 2, True, False, 0),   # AR-block shapes at the bench batch size
+    ("sampler_blk_b64", 64, (512,), 128, 3, 1, 4, False, True, 3),
     ("sampler_plain", 3, (128,), 128, 3, 1, 4, False, True, 0),
     ("final_3ch", 1, (32,), 3, 3, 1, 64, False, False, 0),
     ("big_tile_256", 1, (128,), 128, 3, 1, 256, True, False, 0),

@@ -15,11 +15,11 @@ def _oracle_batch(batch, h, w):
     return [np.stack([o[k] for o in outs]) for k in range(4)]
 
 
-@pytest.mark.parametrize("hw", [(256, 256), (128, 160), (100, 77)])
+@pytest.mark.parametrize("hw", [(256, 256), (128, 160), (100, 77), (300, 400), (720, 1280)])
 def test_fused_matches_oracle(cuda, hw):
     from future_urban_scene_generation_b200.warp_learn import warp_batch
     h, w = hw
-    B = 40 if hw == (256, 256) else 12
+    B = 40 if hw == (256, 256) else (12 if h <= 256 else 3)
     batch = synth.make_warp_batch(0, B, h, w)
     res = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"])
     cuda.cuda.synchronize()
