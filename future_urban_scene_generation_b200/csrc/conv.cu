@@ -314,6 +314,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+__device__ __forceinline__ uint4 elu_piece(uint4 v) {
+    uint4 o;
+    o.x = pack_bf16x2(elu1(bf16lo_to_f(v.x)), elu1(bf16hi_to_f(v.x)));
+    o.y = pack_bf16x2(elu1(bf16lo_to_f(v.y)), elu1(bf16hi_to_f(v.y)));
+    o.z = pack_bf16x2(elu1(bf16lo_to_f(v.z)), elu1(bf16hi_to_f(v.z)));
+    o.w = pack_bf16x2(elu1(bf16lo_to_f(v.w)), elu1(bf16hi_to_f(v.w)));
+    return o;
+}
+
 // element offset (in channels) of output channel n of plain-output pixel (b,y,x) under `mode`
 __device__ __forceinline__ size_t fast_out_offset(const FastEpi &fe, int cout, int Ho, int Wo, int b, int y, int x, int n) {
     switch (fe.mode) {
@@ -392,7 +401,7 @@ struct alignas(64) ConvTcParams {
     int group;                      // k-blocks per pipeline stage (one barrier round trip)
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
     int tmem_cols;
-    int fast_epi;                   // 1: lean epilogue applies
+    int fast_epi;                   // 1: lean epilogue, 2: lean + warp-staged epilogue (every global access covers whole 128-byte lines)
     FastEpi fe;
 };
 
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     uint64_t *w_bar = tempty_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 6);        // cout_pad floats, 16-byte aligned (float4 reads)
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_bias + p.d.cout_pad);   // fast_epi == 2: 8 epilogue warps x 4 KB
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fusg_conv_desc &d = p.d;
@@ -558,6 +568,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+            if (p.fast_epi == 2) {
+                // ---- warp-staged epilogue.  A warp owns 32 consecutive pixels of one image row (Wt >= 32) x ncols
+                // channels per sub-tile; residual in and results out go through a 4 KB swizzled staging block so that
+                // each global instruction of the warp moves whole 128-byte lines (the direct path touches 32 lines
+                // per instruction and saturates the L1TEX data pipe: 74 % lsu wavefronts in r1_ncu_conv_res128raw_B64.csv)
+                const int ppr = ncols >> 3;                        // 16-byte pieces per row (2, 4 or 8)
+                const int rp128 = 8 / ppr;
+                uint4 *stg = reinterpret_cast<uint4 *>(s_stage + (size_t)(warp - 2) * 4096);
+                const int n_base = nt * p.block_n + c_begin;
+                const FastEpi &fe = p.fe;
+                const int sw = (lane / rp128) & (ppr - 1);
+                bool waited = false;
+                for (int sub = 0; sub < p.msub; ++sub) {
+                    const int trow = row + sub * TC_BLOCK_M;
+                    const int wt = trow % p.Wt, ht = (trow / p.Wt) % p.Ht, bt = trow / (p.Wt * p.Ht);
+                    const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
+                    const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+                    const bool valid = b < d.B;                    // uniform across the warp
+                    if (fe.res && valid) {                         // pull this thread's residual row towards L2 while the MMAs run
+                        const __nv_bfloat16 *rp = fe.res + opix * d.cout + n_base;
+                        for (int c = 0; c < ncols; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
+                    }
+                    if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); waited = true; }
+                    const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.msub + sub) * p.block_n + c_begin);
+                    uint32_t r[16];
+                    tmem_ld16(t_base, r);
+                    for (int c = 0; c < ncols; c += 16) {
+                        tmem_ld_wait();
+                        float v[16];
+                        const float4 *b4 = reinterpret_cast<const float4 *>(s_bias + n_base + c);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bb = b4[i];
+                            v[4 * i] = __uint_as_float(r[4 * i]) + bb.x;
+                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                        }
+                        if (c + 16 < ncols) tmem_ld16(t_base + (uint32_t)(c + 16), r);  // prefetch the next chunk
+                        const int j0 = c >> 3;
+                        uint4 *s0 = stg + lane * ppr + (j0 ^ sw), *s1 = stg + lane * ppr + ((j0 + 1) ^ sw);
+                        if (fe.res && valid) {
+                            const uint4 *rq = reinterpret_cast<const uint4 *>(fe.res + opix * d.cout + n_base + c);
+                            const uint4 q0 = __ldg(rq), q1 = __ldg(rq + 1);
+                            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo_to_f(w[i]); v[2 * i + 1] += bf16hi_to_f(w[i]); }
+                        }
+                        *s0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                        *s1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                    }
+                    __syncwarp();
+                    if (sub == p.msub - 1) {                       // all TMEM reads of this tile are done: release the buffer early
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    if (valid) {                                   // transposed read-back: 8 lanes cover one pixel's 128 bytes
+                        for (int qq = lane; qq < 32 * ppr; qq += 32) {
+                            const int rw = qq / ppr, j = qq - rw * ppr;
+                            const uint4 val = stg[rw * ppr + (j ^ ((rw / rp128) & (ppr - 1)))];
+                            const size_t off = fast_out_offset(fe, d.cout, p.Ho, p.Wo, b, oy, ox - lane + rw, n_base + 8 * j);
+                            if (fe.raw) *reinterpret_cast<uint4 *>(fe.raw + off) = val;
+                            if (fe.elu) *reinterpret_cast<uint4 *>(fe.elu + off) = elu_piece(val);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             if (p.fast_epi && p.fe.res && ncols > 0) {
                 // the residual rows this thread will add: pull them into L2 while the MMAs of this tile run
                 for (int sub = 0; sub < p.msub; ++sub) {
@@ -814,7 +894,10 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.b_bytes = p.block_n * p.kc * 2;
     // B k-blocks must start 1024-aligned too (swizzle atom): round the size up
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
-    const int smem_budget = 200 * 1024;
+    // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
+    static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
+    const bool want_staged = staged_on && d.ksize == 3 && p.Wt >= 32 && p.block_n >= 32 && d.noise == nullptr && d.cout % 16 == 0;
+    const int smem_budget = (want_staged ? 168 : 200) * 1024;
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
     const int avail = smem_budget - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
@@ -857,7 +940,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             else { int sh = 0; while ((1 << sh) < cq) ++sh; fe.cq_shift = sh; }
         }
         fe.mode = mode < 0 ? 0 : mode;
-        p.fast_epi = ok ? 1 : 0;
+        p.fast_epi = ok ? (want_staged ? 2 : 1) : 0;
         p.fe = fe;
     }
     PFN_encodeTiled enc = get_encode();
@@ -883,7 +966,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             return FUSG_ERR_UNSUPPORTED;
     }
     const size_t smem = (size_t)p.stages * p.group * p.a_bytes + (p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes) +
-                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/;
+                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 8 * 4096 : 0) /*epilogue staging*/;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
