@@ -304,6 +304,7 @@ struct FastEpi {
     __nv_bfloat16 *raw, *elu;
     const __nv_bfloat16 *res;
     int mode, blk, cq_shift;
+    int stride_a, stride_b;   // elements between output pixels x -> x+2 and x -> x+1 (x even) of one image row under `mode`
 };
 
 __device__ __forceinline__ float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
@@ -312,6 +313,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ uint4 elu_piece(uint4 v) {
@@ -390,6 +400,8 @@ struct alignas(64) ConvTcParams {
     fusg_conv_desc d;
     int Ho, Wo;
     int Wt, Ht, Bt;                 // tile box (output pixels): Wt*Ht*Bt = 128*msub
+    int wt_shift, ht_shift;         // log2(Wt), log2(Ht): Ho, Wo and the tile box are powers of two on this path
+    int txs, tys;                   // log2(tiles_x), log2(tiles_y)
     int msub;                       // 128-row MMA sub-tiles per CTA tile (1 or 2): two sub-tiles share every B k-block
     int tiles_x, tiles_y, tiles_b;  // M-tile grid
     int n_tiles, block_n;           // N tiling
@@ -519,8 +531,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-                const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+                const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
                 const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt;
                 const int ixb = ox0 * d.stride - pad, iyb = oy0 * d.stride - pad, n0 = nt * p.block_n;
                 int ky = 0, kx = 0, cidx = 0, kcol = 0;            // running k-block coordinates (no div/mod in the loop)
@@ -566,30 +578,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+            const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
             if (p.fast_epi == 2) {
                 // ---- warp-staged epilogue.  A warp owns 32 consecutive pixels of one image row (Wt >= 32) x ncols
                 // channels per sub-tile; residual in and results out go through a 4 KB swizzled staging block so that
                 // each global instruction of the warp moves whole 128-byte lines (the direct path touches 32 lines
                 // per instruction and saturates the L1TEX data pipe: 74 % lsu wavefronts in r1_ncu_conv_res128raw_B64.csv)
-                const int ppr = ncols >> 3;                        // 16-byte pieces per row (2, 4 or 8)
-                const int rp128 = 8 / ppr;
-                uint4 *stg = reinterpret_cast<uint4 *>(s_stage + (size_t)(warp - 2) * 4096);
+                const int ppr_shift = 31 - __clz(ncols >> 3);      // 16-byte pieces per row: 2, 4 or 8
+                const int ppr = 1 << ppr_shift;
+                const int rp_shift = 3 - ppr_shift;                // log2(rows per 128 bytes)
+                const uint32_t stg = s_addr(s_stage) + (uint32_t)(warp - 2) * 4096u;
                 const int n_base = nt * p.block_n + c_begin;
                 const FastEpi &fe = p.fe;
-                const int sw = (lane / rp128) & (ppr - 1);
+                const int sw = (lane >> rp_shift) & (ppr - 1);
+                // read-back role of this lane: piece jr of rows rw0, rw0 + rw_step, ...
+                const int jr = lane & (ppr - 1), rw0 = lane >> ppr_shift, rw_step = 32 >> ppr_shift;
                 bool waited = false;
                 for (int sub = 0; sub < p.msub; ++sub) {
                     const int trow = row + sub * TC_BLOCK_M;
-                    const int wt = trow % p.Wt, ht = (trow / p.Wt) % p.Ht, bt = trow / (p.Wt * p.Ht);
+                    const int wt = trow & (p.Wt - 1), ht = (trow >> p.wt_shift) & (p.Ht - 1), bt = trow >> (p.wt_shift + p.ht_shift);
                     const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
                     const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
                     const bool valid = b < d.B;                    // uniform across the warp
+                    const __nv_bfloat16 *rp = fe.res + opix * d.cout + n_base;
                     if (fe.res && valid) {                         // pull this thread's residual row towards L2 while the MMAs run
-                        const __nv_bfloat16 *rp = fe.res + opix * d.cout + n_base;
                         for (int c = 0; c < ncols; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
                     }
+                    // output offset of this lane's read-back piece in the warp's first pixel (x0 = ox - lane, a multiple of 32)
+                    const size_t off0 = fast_out_offset(fe, d.cout, p.Ho, p.Wo, b, oy, ox - lane, n_base + 8 * jr);
                     if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); waited = true; }
                     const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.msub + sub) * p.block_n + c_begin);
                     uint32_t r[16];
@@ -608,16 +625,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         }
                         if (c + 16 < ncols) tmem_ld16(t_base + (uint32_t)(c + 16), r);  // prefetch the next chunk
                         const int j0 = c >> 3;
-                        uint4 *s0 = stg + lane * ppr + (j0 ^ sw), *s1 = stg + lane * ppr + ((j0 + 1) ^ sw);
+                        const uint32_t s0 = stg + (uint32_t)(((lane << ppr_shift) + (j0 ^ sw)) << 4);
+                        const uint32_t s1 = stg + (uint32_t)(((lane << ppr_shift) + ((j0 + 1) ^ sw)) << 4);
                         if (fe.res && valid) {
-                            const uint4 *rq = reinterpret_cast<const uint4 *>(fe.res + opix * d.cout + n_base + c);
+                            const uint4 *rq = reinterpret_cast<const uint4 *>(rp + c);
                             const uint4 q0 = __ldg(rq), q1 = __ldg(rq + 1);
                             const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
                             for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo_to_f(w[i]); v[2 * i + 1] += bf16hi_to_f(w[i]); }
                         }
-                        *s0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                        *s1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                        sts128(s0, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+                        sts128(s1, make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
                     }
                     __syncwarp();
                     if (sub == p.msub - 1) {                       // all TMEM reads of this tile are done: release the buffer early
@@ -625,10 +643,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
                     if (valid) {                                   // transposed read-back: 8 lanes cover one pixel's 128 bytes
-                        for (int qq = lane; qq < 32 * ppr; qq += 32) {
-                            const int rw = qq / ppr, j = qq - rw * ppr;
-                            const uint4 val = stg[rw * ppr + (j ^ ((rw / rp128) & (ppr - 1)))];
-                            const size_t off = fast_out_offset(fe, d.cout, p.Ho, p.Wo, b, oy, ox - lane + rw, n_base + 8 * j);
+                        for (int rw = rw0; rw < 32; rw += rw_step) {
+                            const uint4 val = lds128(stg + (uint32_t)(((rw << ppr_shift) + (jr ^ ((rw >> rp_shift) & (ppr - 1)))) << 4));
+                            const size_t off = off0 + (size_t)((rw >> 1) * fe.stride_a + (rw & 1) * fe.stride_b);
                             if (fe.raw) *reinterpret_cast<uint4 *>(fe.raw + off) = val;
                             if (fe.elu) *reinterpret_cast<uint4 *>(fe.elu + off) = elu_piece(val);
                         }
@@ -642,7 +659,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 // the residual rows this thread will add: pull them into L2 while the MMAs of this tile run
                 for (int sub = 0; sub < p.msub; ++sub) {
                     const int trow = row + sub * TC_BLOCK_M;
-                    const int wt = trow % p.Wt, ht = (trow / p.Wt) % p.Ht, bt = trow / (p.Wt * p.Ht);
+                    const int wt = trow & (p.Wt - 1), ht = (trow >> p.wt_shift) & (p.Ht - 1), bt = trow >> (p.wt_shift + p.ht_shift);
                     const int b = tb * p.Bt + bt;
                     if (b < d.B) {
                         const size_t opix = ((size_t)b * p.Ho + ty * p.Ht + ht) * p.Wo + tx * p.Wt + wt;
@@ -655,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             tc_fence_after();
             for (int sub = 0; sub < p.msub && ncols > 0; ++sub) {
                 const int trow = row + sub * TC_BLOCK_M;               // row of the CTA tile
-                const int wt = trow % p.Wt, ht = (trow / p.Wt) % p.Ht, bt = trow / (p.Wt * p.Ht);
+                const int wt = trow & (p.Wt - 1), ht = (trow >> p.wt_shift) & (p.Ht - 1), bt = trow >> (p.wt_shift + p.ht_shift);
                 const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
                 const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
                 const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.msub + sub) * p.block_n + c_begin);
@@ -884,6 +901,8 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.Ht = (trows / p.Wt) < Ho ? (trows / p.Wt) : Ho;
     p.Bt = trows / (p.Wt * p.Ht);
     p.tiles_x = Wo / p.Wt; p.tiles_y = Ho / p.Ht; p.tiles_b = (d.B + p.Bt - 1) / p.Bt;
+    auto ilog2 = [](int v) { int sh = 0; while ((1 << sh) < v) ++sh; return sh; };
+    p.wt_shift = ilog2(p.Wt); p.ht_shift = ilog2(p.Ht); p.txs = ilog2(p.tiles_x); p.tys = ilog2(p.tiles_y);
     const bool k64 = (d.c0 % 64 == 0) && (!d.in1 || d.c1 % 64 == 0);
     p.kc = k64 ? 64 : 32;
     p.chunks0 = d.c0 / p.kc;
@@ -896,7 +915,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
     // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
     static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
-    const bool want_staged = staged_on && d.ksize == 3 && p.Wt >= 32 && p.block_n >= 32 && d.noise == nullptr && d.cout % 16 == 0;
+    const bool want_staged = staged_on && d.ksize == 3 && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
     const int smem_budget = (want_staged ? 168 : 200) * 1024;
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
@@ -940,6 +959,12 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             else { int sh = 0; while ((1 << sh) < cq) ++sh; fe.cq_shift = sh; }
         }
         fe.mode = mode < 0 ? 0 : mode;
+        switch (fe.mode) {
+            default: fe.stride_a = 2 * d.cout; fe.stride_b = d.cout; break;
+            case FUSG_OUT_D2S: fe.stride_a = d.cout; fe.stride_b = d.cout / 2; break;          // 4*cq, 2*cq with cq = cout/4
+            case FUSG_OUT_S2D: fe.stride_a = 4 * d.cout; fe.stride_b = d.cout; break;
+            case FUSG_OUT_D2S_BLOCK: fe.stride_a = 4 * d.cout; fe.stride_b = 2 * d.cout; break;
+        }
         p.fast_epi = ok ? (want_staged ? 2 : 1) : 0;
         p.fe = fe;
     }
