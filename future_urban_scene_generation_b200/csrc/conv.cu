@@ -390,8 +390,12 @@ __device__ __forceinline__ void fast_chunk16(const FastEpi &fe, const float *s_b
 // ------------------------------------------------------------------------------------------------
 // k_conv_tc
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_EPI_WARPS = 8;
+#ifndef FUSG_TC_EPI_WARPS
+#define FUSG_TC_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = FUSG_TC_EPI_WARPS;          // 8 or 16: warps 2.. ; warp 0 TMA, warp 1 MMA
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_STAGE_BYTES = 32768 / TC_EPI_WARPS;     // per-warp staging block of the staged epilogue
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_MAX_STAGES = 16;
 
@@ -571,16 +575,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // =================== epilogue warps (2..9) ===================
         // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share a lane quadrant and split the columns
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;                      // 0 .. TC_EPI_WARPS/4 - 1
         const int row = q * 32 + lane;                         // tile row == TMEM lane
-        const int ncols = p.block_n >= 32 ? p.block_n / 2 : (half == 0 ? p.block_n : 0);
-        const int c_begin = p.block_n >= 32 ? half * ncols : 0;
+        int nparts = TC_EPI_WARPS / 4;
+        while (nparts > 1 && p.block_n % (16 * nparts)) nparts >>= 1;
+        const int ncols = part < nparts ? p.block_n / nparts : 0;
+        const int c_begin = part * ncols;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
-            if (p.fast_epi == 2) {
+            if (p.fast_epi == 2 && ncols > 0) {
                 // ---- warp-staged epilogue.  A warp owns 32 consecutive pixels of one image row (Wt >= 32) x ncols
                 // channels per sub-tile; residual in and results out go through a 4 KB swizzled staging block so that
                 // each global instruction of the warp moves whole 128-byte lines (the direct path touches 32 lines
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 const int ppr_shift = 31 - __clz(ncols >> 3);      // 16-byte pieces per row: 2, 4 or 8
                 const int ppr = 1 << ppr_shift;
                 const int rp_shift = 3 - ppr_shift;                // log2(rows per 128 bytes)
-                const uint32_t stg = s_addr(s_stage) + (uint32_t)(warp - 2) * 4096u;
+                const uint32_t stg = s_addr(s_stage) + (uint32_t)(warp - 2) * (uint32_t)TC_STAGE_BYTES;
                 const int n_base = nt * p.block_n + c_begin;
                 const FastEpi &fe = p.fe;
                 const int sw = (lane >> rp_shift) & (ppr - 1);
@@ -915,7 +921,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
     // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
     static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
-    const bool want_staged = staged_on && d.ksize == 3 && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
+    const bool want_staged = staged_on && (d.ksize == 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
     const int smem_budget = (want_staged ? 168 : 200) * 1024;
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
@@ -991,7 +997,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             return FUSG_ERR_UNSUPPORTED;
     }
     const size_t smem = (size_t)p.stages * p.group * p.a_bytes + (p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes) +
-                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 8 * 4096 : 0) /*epilogue staging*/;
+                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();

@@ -50,6 +50,7 @@ class NovelViewPipeline:
         self.use_graph = use_graph        # the collective (if any) is issued eagerly after the graph replay
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.out_stream = torch.cuda.Stream(self.dev)
+        self.side_stream = torch.cuda.Stream(self.dev)
         self.slots = [_Slot() for _ in range(depth)]
         one = torch.cuda.Stream(self.dev)
         for sl in self.slots:
@@ -58,9 +59,18 @@ class NovelViewPipeline:
 
     # ------------------------------------------------------------------ one step of device work
     def _compute(self, inp):
-        res = warp_batch(*(inp[k] for k in self.WARP_KEYS), device=self.dev)
+        # the planar warp is a chain of small latency-bound kernels (visibility -> homographies -> gather) that does
+        # not feed the VUNet of the same batch: fork it onto a side stream so it fills the SMs the narrow VUNet
+        # layers leave idle, and join before the outputs are read (inside a graph this becomes a parallel branch)
+        cur = torch.cuda.current_stream(self.dev)
+        self.side_stream.wait_stream(cur)
+        with torch.cuda.stream(self.side_stream):
+            res = warp_batch(*(inp[k] for k in self.WARP_KEYS), device=self.dev)
         x_tilde, _, _ = self.model(inp["y"], inp["x"])
         crops = to_image_batch(x_tilde)
+        cur.wait_stream(self.side_stream)
+        for t in (res.warped, res.plane_j, res.vis):
+            t.record_stream(cur)
         return {"crops": crops, "warped": res.warped, "plane_j": res.plane_j, "vis": res.vis}
 
     def _prepare_slot(self, slot: _Slot, batch: dict):
