@@ -203,6 +203,12 @@ class Vunet_fix_res(nn.Module):
             del skips[:]                       # the reference pops the caller's list empty (models.py:416-457)
             return x_tilde, [e.to_nchw(a) for a in mu], [e.to_nchw(a) for a in z]
 
+    def _side_stream(self):
+        dev = torch.cuda.current_device()
+        if getattr(self, "_side", None) is None or self._side[0] != dev:
+            self._side = (dev, torch.cuda.Stream(dev))
+        return self._side[1]
+
     def forward(self, y_tilde, x=None, mean_mode='mean_appearance'):
         if self.vunet_256:
             assert y_tilde.shape[-1] == 256
@@ -215,9 +221,22 @@ class Vunet_fix_res(nn.Module):
             e.raw_skips = False                # fused path: skips are consumed pre-activated only
             try:
                 if mean_mode == 'mean_appearance':
-                    out_e, skips_e = e.enc_up(x)
-                    mu_app, z_app = e.enc_down(out_e, skips_e)
-                    out_d, skips_d = e.dec_up(y_tilde)
+                    # the shape encoder (dec_up) does not depend on the appearance branch (enc_up -> enc_down):
+                    # run it on a forked stream so its layers fill the SMs the narrow appearance layers leave idle
+                    # (fork_branches = False keeps everything on the current stream, e.g. for per-launch timing)
+                    if getattr(self, "fork_branches", True):
+                        cur = torch.cuda.current_stream()
+                        side = self._side_stream()
+                        side.wait_stream(cur)
+                        with torch.cuda.stream(side):
+                            out_d, skips_d = e.dec_up(y_tilde)
+                        out_e, skips_e = e.enc_up(x)
+                        mu_app, z_app = e.enc_down(out_e, skips_e)
+                        cur.wait_stream(side)
+                    else:
+                        out_e, skips_e = e.enc_up(x)
+                        mu_app, z_app = e.enc_down(out_e, skips_e)
+                        out_d, skips_d = e.dec_up(y_tilde)
                     x_tilde, mu_shape, _ = e.dec_down(out_d, skips_d, [z.aux["s2d_elu"] for z in z_app])
                     return x_tilde, [e.to_nchw(a) for a in mu_app], [e.to_nchw(a) for a in mu_shape]
                 out_d, skips_d = e.dec_up(y_tilde)

@@ -24,3 +24,45 @@ for depth, shared in ((2, False), (2, True), (3, False), (3, True), (1, True)):
     T0=time.perf_counter(); run(pipe, 30); dt=(time.perf_counter()-T0)*1e3/30
     print(f"depth={depth} shared_stream={shared}: {dt:.2f} ms/step e2e")
     del pipe; torch.cuda.empty_cache()
+
+# --- component costs of one e2e step -------------------------------------------------------------
+dev = torch.device("cuda")
+dst = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+s = torch.cuda.Stream()
+def t_copy():
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s):
+        e0.record(s)
+        for k, v in host.items(): dst[k].copy_(v, non_blocking=True)
+        e1.record(s)
+    s.synchronize()
+    return e0.elapsed_time(e1)
+t_copy()
+nb = sum(v.numel() * v.element_size() for v in host.values())
+ms = min(t_copy() for _ in range(5))
+print(f"H2D {nb/1e6:.1f} MB: {ms:.2f} ms ({nb/ms/1e6:.1f} GB/s)")
+pipe = NovelViewPipeline(m, depth=2, shared_stream=True)
+run(pipe, 4)
+out = pipe.result(pipe.n - 1)
+devout = {k: v.to(dev) for k, v in out.items()}
+def t_d2h():
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s):
+        e0.record(s)
+        for k, v in devout.items(): out[k].copy_(v, non_blocking=True)
+        e1.record(s)
+    s.synchronize()
+    return e0.elapsed_time(e1)
+t_d2h()
+nb2 = sum(v.numel() * v.element_size() for v in out.values())
+ms2 = min(t_d2h() for _ in range(5))
+print(f"D2H {nb2/1e6:.1f} MB: {ms2:.2f} ms ({nb2/ms2/1e6:.1f} GB/s)")
+sl = pipe.slots[0]
+T0 = time.perf_counter()
+for _ in range(10): pipe._draw_noise(sl)
+print(f"noise draw (host): {(time.perf_counter()-T0)*100:.3f} ms/step, {sum(x.numel() for x in sl.noise_stage)*4/1e6:.2f} MB")
+T0 = time.perf_counter()
+for _ in range(10):
+    t = pipe.submit(host); pipe.result(t)
+torch.cuda.synchronize()
+print(f"unpipelined submit+result latency: {(time.perf_counter()-T0)*100:.2f} ms")

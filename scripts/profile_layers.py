@@ -13,6 +13,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 torch.manual_seed(0)
 m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).cuda().eval()
 e = m.engine()
+m.fork_branches = False   # per-launch timing on one stream
 x, y = synth.make_vunet_inputs(0, B)
 x, y = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
 bank = {}
