@@ -283,6 +283,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// thread-block cluster helpers (split-K layers)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -416,6 +437,8 @@ struct alignas(64) ConvTcParams {
     int a_bytes, b_bytes;           // per k-block
     int group;                      // k-blocks per pipeline stage (one barrier round trip)
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
+    int ksplit;                     // > 1: thread-block cluster of `ksplit` CTAs per tile, each reducing 1/ksplit of K (few-tile layers)
+    int kb_local;                   // k-blocks per CTA = num_kblocks / ksplit
     int tmem_cols;
     int fast_epi;                   // 1: lean epilogue, 2: lean + warp-staged epilogue (every global access covers whole 128-byte lines)
     FastEpi fe;
@@ -434,7 +457,7 @@ __device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uin
     // descriptor high bits: LBO=1 | SBO = 8 rows of one swizzle span | version 1 | swizzle mode
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((kc * 2u * 8u) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KSTEPS == 4 ? 2u : 4u) << 61);
     const uint32_t sub16 = (TC_BLOCK_M * kc * 2u) >> 4;                 // next 128-row sub-tile, in 16-byte units
-    const int group = p.group, stages = p.stages, groups = p.num_kblocks / p.group;
+    const int group = p.group, stages = p.stages, groups = p.kb_local / p.group;
     const uint32_t a_kb16 = (uint32_t)p.a_bytes >> 4, b_kb16 = (uint32_t)p.b_bytes >> 4;
     const uint32_t a_stage16 = a_kb16 * group, b_stage16 = b_kb16 * group;
     const bool resident = p.w_resident != 0;
@@ -444,7 +467,7 @@ __device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uin
     uint32_t phase = 0;
     uint32_t acc = 0, acc_phase = 0;
     if (resident) mbar_wait(w_bar, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x / p.ksplit; tile < total_tiles; tile += gridDim.x / p.ksplit) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
@@ -493,7 +516,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     uint64_t *w_bar = tempty_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 6);        // cout_pad floats, 16-byte aligned (float4 reads)
-    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_bias + p.d.cout_pad);   // fast_epi == 2: 8 epilogue warps x 4 KB
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_bias + p.d.cout_pad);   // fast_epi == 2: 32 KB of per-warp staging blocks
+    float *s_recv = reinterpret_cast<float *>(s_stage);                      // ksplit > 1: block_n x 128 fp32 receive buffer (no staging then)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fusg_conv_desc &d = p.d;
@@ -513,16 +537,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // split-K: every CTA of the cluster must be running before a peer writes into its shared memory; arrive now,
+    // wait just before the first remote store
+    if (p.ksplit > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     const int total_tiles = m_tiles * p.n_tiles;
     const int pad = d.ksize >> 1;
     const int cpt = p.chunks0 + p.chunks1;        // k-blocks per tap
+    int split_tile = -1;                          // split-K: the tile whose partial accumulator this epilogue warp parked
 
     if (warp == 0) {
         // =================== TMA producer (whole warp runs the loop; one elected lane issues) ===================
         {
-            const int groups = p.num_kblocks / p.group;
+            const int groups = p.kb_local / p.group;
+            const int kb0 = p.ksplit > 1 ? (int)cluster_ctarank() * p.kb_local : 0;     // first k-block of this CTA
             const uint32_t stage_tx = (uint32_t)(p.group * (p.a_bytes + (p.w_resident ? 0 : p.b_bytes)));
             if (p.w_resident) {
                 // the weight matrix of this N tile is loaded once per CTA
@@ -534,12 +563,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x / p.ksplit; tile < total_tiles; tile += gridDim.x / p.ksplit) {
                 const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
                 const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt;
                 const int ixb = ox0 * d.stride - pad, iyb = oy0 * d.stride - pad, n0 = nt * p.block_n;
-                int ky = 0, kx = 0, cidx = 0, kcol = 0;            // running k-block coordinates (no div/mod in the loop)
+                // running k-block coordinates (no div/mod in the loop)
+                const int tap0 = kb0 / cpt;
+                int ky = tap0 / d.ksize, kx = tap0 - ky * d.ksize, cidx = kb0 - tap0 * cpt, kcol = kb0 * p.kc;
                 for (int grp = 0; grp < groups; ++grp) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     const bool leader = elect_one();
@@ -583,9 +614,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const int c_begin = part * ncols;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x / p.ksplit; tile < total_tiles; tile += gridDim.x / p.ksplit) {
             const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
+            if (p.ksplit > 1) {
+                // ---- split-K: push this CTA's partial accumulator, 16-column chunk by chunk, into the receive buffer of
+                // the cluster CTA that owns the chunk (remote stores are fire-and-forget; the cluster barrier after the
+                // role code publishes them).  One tile per cluster.
+                mbar_wait(&tfull_bar[0], 0);
+                tc_fence_after();
+                const int S = p.ksplit, cpc = (p.block_n >> 4) / S;    // chunks per owner
+                const uint32_t me = cluster_ctarank();
+                const uint32_t recv = s_addr(s_recv);                 // [S sources][128 rows][cpc*16 floats]
+                const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin;
+                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+                for (int c = 0; c < ncols; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_base + (uint32_t)c, r);
+                    tmem_ld_wait();
+                    const int ch = (c_begin + c) >> 4, owner = ch / cpc, jc = ch - owner * cpc;
+                    const uint32_t dst = dsmem_addr(recv + (uint32_t)((((int)me * TC_BLOCK_M + row) * cpc + jc) * 64), (uint32_t)owner);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "r"(r[4 * i]), "r"(r[4 * i + 1]),
+                                     "r"(r[4 * i + 2]), "r"(r[4 * i + 3]) : "memory");
+                }
+                tc_fence_before();
+                split_tile = tile;
+                break;
+            }
             if (p.fast_epi == 2 && ncols > 0) {
                 // ---- warp-staged epilogue.  A warp owns 32 consecutive pixels of one image row (Wt >= 32) x ncols
                 // channels per sub-tile; residual in and results out go through a 4 KB swizzled staging block so that
@@ -706,6 +763,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    if (p.ksplit > 1) {
+        // split-K reduction: CTA r of the cluster owns the 16-column chunks [r*cpc, (r+1)*cpc) of the tile; every CTA
+        // has pushed its partials of those chunks into this CTA's receive buffer.  Sum them in rank order
+        // (deterministic) and run the normal epilogue.
+        __syncwarp();
+        if (warp < 2) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // pairs with the arrive of the prologue
+        cluster_sync_all();
+        if (warp >= 2 && split_tile >= 0) {
+            const int q = warp & 3, part = (warp - 2) >> 2, row = q * 32 + lane;
+            const int S = p.ksplit, cpc = (p.block_n >> 4) / S;
+            const int crank = (int)cluster_ctarank();
+            const int mt = p.n_tiles == 1 ? split_tile : split_tile / p.n_tiles, nt = split_tile - mt * p.n_tiles;
+            const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
+            const int wt = row & (p.Wt - 1), ht = (row >> p.wt_shift) & (p.Ht - 1), bt = row >> (p.wt_shift + p.ht_shift);
+            const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
+            const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+            const float4 *recv = reinterpret_cast<const float4 *>(s_recv);
+            for (int j = part; j < cpc; j += TC_EPI_WARPS / 4) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                for (int src = 0; src < S; ++src) {
+                    const float4 *pr = recv + ((size_t)(src * TC_BLOCK_M + row) * cpc + j) * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 t = pr[i];
+                        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                    }
+                }
+                if (b < d.B) {
+                    const int n = nt * p.block_n + (crank * cpc + j) * 16;
+                    if (p.fast_epi) {
+                        uint32_t rr[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(v[i]);
+                        fast_chunk16(p.fe, s_bias, d.cout, p.Ho, p.Wo, opix, b, oy, ox, n, rr);
+                    } else {
+                        epilogue16<__nv_bfloat16>(d, s_bias, p.Ho, p.Wo, b, oy, ox, n, v);
+                    }
+                }
+            }
         }
     }
     tc_fence_before();
@@ -919,19 +1019,38 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.b_bytes = p.block_n * p.kc * 2;
     // B k-blocks must start 1024-aligned too (swizzle atom): round the size up
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
+    // few-tile layers (the coarse scales and the auto-regressive tail): a cluster of `ksplit` CTAs per tile, each
+    // streaming 1/ksplit of the K range, then a DSMEM reduce-scatter -- a single SM pulls ~50-80 GB/s through TMA,
+    // so a 128 x 4608 weight slab per CTA costs ~45 us however few tiles there are
+    static const int ksplit_max = getenv("FUSG_KSPLIT_MAX") ? atoi(getenv("FUSG_KSPLIT_MAX")) : 8;
+    static const int ksplit_min_kb = getenv("FUSG_KSPLIT_MIN_KB") ? atoi(getenv("FUSG_KSPLIT_MIN_KB")) : 36;
+    p.ksplit = 1;
+    {
+        const int tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+        if (p.msub == 1 && p.block_n % 16 == 0) {
+            for (int sk = 8; sk >= 2; sk >>= 1) {
+                if (sk > ksplit_max || tiles * sk > 128) continue;
+                if (p.num_kblocks % sk || p.num_kblocks < ksplit_min_kb) continue;
+                if ((p.block_n / 16) % sk) continue;
+                p.ksplit = sk;
+                break;
+            }
+        }
+    }
+    p.kb_local = p.num_kblocks / p.ksplit;
     // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
     static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
-    const bool want_staged = staged_on && (d.ksize == 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
-    const int smem_budget = (want_staged ? 168 : 200) * 1024;
+    const bool want_staged = p.ksplit == 1 && staged_on && (d.ksize == 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
+    const int smem_budget = (want_staged ? 168 : 200) * 1024 - (p.ksplit > 1 ? p.block_n * TC_BLOCK_M * 4 : 0);
     // weights resident when the whole (single) N tile fits next to a useful pipeline
-    p.w_resident = (p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
+    p.w_resident = (p.ksplit == 1 && p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
     const int avail = smem_budget - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
     const int kb_bytes = p.a_bytes + (p.w_resident ? 0 : p.b_bytes);
     // group = k-blocks per barrier round trip: the largest divisor of num_kblocks that keeps the
     // stage <= 64 KB and leaves >= 3 stages
     int group = 1;
-    for (int g = 1; g <= p.num_kblocks; ++g) {
-        if (p.num_kblocks % g) continue;
+    for (int g = 1; g <= p.kb_local; ++g) {
+        if (p.kb_local % g) continue;
         if (g * kb_bytes > 64 * 1024) break;
         if (avail / (g * kb_bytes) >= 3) group = g;
     }
@@ -997,13 +1116,32 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             return FUSG_ERR_UNSUPPORTED;
     }
     const size_t smem = (size_t)p.stages * p.group * p.a_bytes + (p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes) +
-                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/;
+                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
         attr_set = true;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+    if (p.ksplit > 1) {
+        // one cluster per tile
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(total_tiles * p.ksplit), 1, 1);
+        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.ksplit;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, k_conv_tc, p) != cudaSuccess) return fusg_check_launch();
+        fusg_count_launch(1);
+        return fusg_check_launch();
+    }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     k_conv_tc<<<grid, TC_THREADS, smem, st>>>(p);
     fusg_count_launch(1);
