@@ -437,6 +437,7 @@ struct alignas(64) ConvTcParams {
     int a_bytes, b_bytes;           // per k-block
     int group;                      // k-blocks per pipeline stage (one barrier round trip)
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
+    int pdl;                        // launched with programmatic stream serialization (griddepcontrol in the kernel)
     int ksplit;                     // > 1: thread-block cluster of `ksplit` CTAs per tile, each reducing 1/ksplit of K (few-tile layers)
     int kb_local;                   // k-blocks per CTA = num_kblocks / ksplit
     int tmem_cols;
@@ -537,6 +538,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above (barriers, TMEM, tensor-map prefetch, bias) touched nothing the
+    // previous kernel of the stream produces; wait for it here, then let the next kernel start its own prologue
+    if (p.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     // split-K: every CTA of the cluster must be running before a peer writes into its shared memory; arrive now,
     // wait just before the first remote store
     if (p.ksplit > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -1123,27 +1130,32 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         attr_set = true;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+    static const int pdl_on = getenv("FUSG_NO_PDL") ? 0 : 1;
+    p.pdl = pdl_on;
+    const int grid = p.ksplit > 1 ? total_tiles * p.ksplit /* one cluster per tile */ : (total_tiles < num_sms ? total_tiles : num_sms);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     if (p.ksplit > 1) {
-        // one cluster per tile
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)(total_tiles * p.ksplit), 1, 1);
-        cfg.blockDim = dim3(TC_THREADS, 1, 1);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)p.ksplit;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, k_conv_tc, p) != cudaSuccess) return fusg_check_launch();
-        fusg_count_launch(1);
-        return fusg_check_launch();
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)p.ksplit;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     }
-    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    k_conv_tc<<<grid, TC_THREADS, smem, st>>>(p);
+    if (p.pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)na;
+    if (cudaLaunchKernelEx(&cfg, k_conv_tc, p) != cudaSuccess) return fusg_check_launch();
     fusg_count_launch(1);
     return fusg_check_launch();
 }
