@@ -13,6 +13,8 @@ still drawn on the CPU default generator in the reference's order and shapes (vu
 -- `torch.manual_seed` reproduces the reference's outputs -- and copied into the graph's static
 noise buffers before each replay.
 """
+import threading
+
 import torch
 
 from . import _lib
@@ -36,18 +38,21 @@ class _Slot:
         self.launches = 0
         self.stream = None       # this slot's compute stream: the small-grid tail layers of one batch overlap the
                                  # full-grid layers of the next batch in flight
+        self.prefetch = None     # (thread, state_before, result holder) of a background noise draw into noise_stage
 
 
 class NovelViewPipeline:
     WARP_KEYS = ("src", "src_kp", "dst_kp", "K", "E_src", "E_dst", "kp3d")
 
-    def __init__(self, model, depth: int = 2, gather_fn=None, use_graph: bool = True, shared_stream: bool = False):
+    def __init__(self, model, depth: int = 2, gather_fn=None, use_graph: bool = True, shared_stream: bool = False,
+                 prefetch_noise: bool = True):
         _lib.require_cuda()
         self.model = model
         self.dev = next(model.parameters()).device
         self.depth = depth
         self.gather_fn = gather_fn        # optional device-side collective on the completed crops (parallel.gather_crops)
         self.use_graph = use_graph        # the collective (if any) is issued eagerly after the graph replay
+        self.prefetch_noise = prefetch_noise
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.out_stream = torch.cuda.Stream(self.dev)
         self.side_stream = torch.cuda.Stream(self.dev)
@@ -103,13 +108,45 @@ class NovelViewPipeline:
         slot.launches = _lib.kernel_launches() - n0
         eng.noise_provider = prev
 
-    def _draw_noise(self, slot: _Slot):
-        """CPU default generator, reference order/shapes (NCHW), laid out NHWC in the slot's pinned staging buffers."""
+    def _draw_noise(self, slot: _Slot, generator=None):
+        """CPU generator (default: the global one), reference order/shapes (NCHW), laid out NHWC in the slot's pinned
+        staging buffers."""
         if slot.copied is not None:
             slot.copied.synchronize()          # the previous H2D out of these staging buffers has long completed
         for stage, (b, c, h, w) in zip(slot.noise_stage, slot.noise_shapes):
-            eps = torch.randn(b, c, h, w)
+            eps = torch.randn(b, c, h, w, generator=generator)
             stage.copy_(eps.permute(0, 2, 3, 1))
+
+    # The Sampler noise of a step costs ~3.6 ms of host time at 64 crops (1.3 M normals on the CPU generator, which is
+    # what the reference draws from: vunet/layers.py:166).  To keep it off the submit path, the noise of the NEXT use
+    # of a slot is drawn on a worker thread from a CLONE of the global generator; `submit` adopts it only if the
+    # global generator is still in the state the clone started from (nobody seeded it or drew from it in between) and
+    # then advances the global generator to the clone's end state -- bit-identical to drawing in `submit`.
+    def _start_prefetch(self, slot: _Slot):
+        if not self.prefetch_noise or not slot.noise_stage:
+            return
+        state0 = torch.get_rng_state()
+        holder = {}
+
+        def work():
+            g = torch.Generator()
+            g.set_state(state0)
+            self._draw_noise(slot, generator=g)
+            holder["state1"] = g.get_state()
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        slot.prefetch = (th, state0, holder)
+
+    def _take_noise(self, slot: _Slot):
+        """Fill the slot's staging buffers with this step's noise (adopt the prefetched draw when it is valid)."""
+        pf, slot.prefetch = slot.prefetch, None
+        if pf is not None:
+            th, state0, holder = pf
+            th.join()
+            if "state1" in holder and torch.equal(torch.get_rng_state(), state0):
+                torch.set_rng_state(holder["state1"])
+                return
+        self._draw_noise(slot)
 
     def _upload_noise(self, slot: _Slot):
         for buf, stage in zip(slot.noise, slot.noise_stage):
@@ -124,13 +161,16 @@ class NovelViewPipeline:
         slot = self.slots[ticket % self.depth]
         fresh = slot.inp is None or any(tuple(slot.inp[k].shape) != tuple(v.shape) for k, v in batch.items())
         if not resident and not fresh:
-            self._draw_noise(slot)                                    # host RNG work overlaps the batches still in flight
+            self._take_noise(slot)                                    # host RNG work overlaps the batches still in flight
         if slot.done is not None:
             slot.done.synchronize()                                   # the slot's previous outputs were consumed
         if fresh:
+            if slot.prefetch is not None:                             # a draw into the old staging buffers is in flight
+                slot.prefetch[0].join()
+                slot.prefetch = None
             self._prepare_slot(slot, batch)
             if not resident:
-                self._draw_noise(slot)
+                self._take_noise(slot)
         eng = self.model.engine()
         if not resident:
             with torch.cuda.stream(self.copy_stream):
@@ -169,6 +209,9 @@ class NovelViewPipeline:
             slot.done = torch.cuda.Event()
             slot.done.record(self.out_stream)
         self.n += 1
+        nxt = self.slots[self.n % self.depth]
+        if not resident and nxt.inp is not None and nxt.prefetch is None:
+            self._start_prefetch(nxt)                                 # the next step's noise, off the submit path
         return ticket
 
     def result(self, ticket: int) -> dict:

@@ -62,3 +62,38 @@ def test_pipeline_matches_eager_and_oracle(cuda):
     w0 = WO.warp_fused(host["src"][0].numpy(), host["src_kp"][0].numpy(), host["dst_kp"][0].numpy(), host["K"][0].numpy(),
                        host["E_src"][0].numpy(), host["E_dst"][0].numpy(), host["kp3d"][0].numpy())[0]
     assert np.array_equal(outs[0]["warped"][0].numpy(), w0)
+
+
+def test_noise_prefetch_keeps_generator_semantics(cuda):
+    """The background noise draw is adopted only when it is bit-identical to drawing inside submit(): same outputs as
+    prefetch_noise=False for one seed, also when the caller reseeds or draws from the global generator between steps."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    B = 2
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).cuda().eval()
+    wb = synth.make_warp_batch(3, B)
+    xs, ys = synth.make_vunet_inputs(3, B)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
+    host["x"], host["y"] = torch.from_numpy(xs).pin_memory(), torch.from_numpy(ys).pin_memory()
+
+    def run(prefetch):
+        pipe = NovelViewPipeline(m, depth=2, prefetch_noise=prefetch)
+        torch.manual_seed(5)
+        outs = []
+        for step in range(6):
+            if step == 3:
+                torch.manual_seed(77)              # reseed between steps: a pending prefetch must be discarded
+            if step == 4:
+                torch.rand(3)                      # foreign draw from the global generator
+            t = pipe.submit(host)
+            outs.append(pipe.result(t)["crops"].clone())
+        return outs, torch.get_rng_state()
+
+    a, sa = run(True)
+    b, sb = run(False)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert torch.equal(sa, sb)                     # the global generator ends in the same state
+    assert not torch.equal(a[0], a[1])             # different noise every step
