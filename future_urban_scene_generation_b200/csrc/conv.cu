@@ -418,6 +418,8 @@ constexpr int TC_EPI_WARPS = FUSG_TC_EPI_WARPS;          // 8 or 16: warps 2.. ;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_STAGE_BYTES = 32768 / TC_EPI_WARPS;     // per-warp staging block of the staged epilogue
 constexpr int TC_BLOCK_M = 128;
+constexpr int TC_HALO_ROWS = TC_BLOCK_M + 2;                       // pixels of one halo A buffer
+constexpr int TC_HALO_BYTES = ((TC_HALO_ROWS * 128 + 1023) / 1024) * 1024;   // 128-byte rows (kc = 64), 1024-aligned
 constexpr int TC_MAX_STAGES = 16;
 
 struct alignas(64) ConvTcParams {
@@ -437,6 +439,8 @@ struct alignas(64) ConvTcParams {
     int a_bytes, b_bytes;           // per k-block
     int group;                      // k-blocks per pipeline stage (one barrier round trip)
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
+    int halo;                       // 1: sliding-window A tiles -- one TMA load of an image-row segment + 2 halo pixels serves the
+                                    //    three horizontal taps (3x3, stride 1, Wt = 128, one image row per 128-row sub-tile)
     int pdl;                        // launched with programmatic stream serialization (griddepcontrol in the kernel)
     int ksplit;                     // > 1: thread-block cluster of `ksplit` CTAs per tile, each reducing 1/ksplit of K (few-tile layers)
     int kb_local;                   // k-blocks per CTA = num_kblocks / ksplit
@@ -504,14 +508,71 @@ __device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uin
     }
 }
 
+// MMA issuer of the sliding-window (halo) mode: a pipeline stage holds, for one (tap row ky, 64-channel chunk), the
+// two image-row segments of the CTA tile with one extra pixel on each side, and the three weight k-blocks kx = 0..2.
+// The A descriptor of tap kx simply starts kx rows (kx * 128 bytes) into the buffer: the 128-byte swizzle is a
+// function of the absolute shared-memory address, so a start address that is 128- but not 1024-byte aligned
+// addresses the same swizzled rows (checked on the device by scripts/umma_shift_probe.cu).
+__device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA, uint8_t *sB, uint64_t *full_bar, uint64_t *empty_bar,
+                                              uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *w_bar, uint32_t tmem_base, int total_tiles) {
+    const uint32_t block_n = (uint32_t)p.block_n;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2u << 61);
+    const int stages = p.stages, cpt = p.chunks0 + p.chunks1, nst = 3 * cpt;
+    const uint32_t b_kb16 = (uint32_t)p.b_bytes >> 4;
+    const uint32_t a_stage16 = (2u * TC_HALO_BYTES) >> 4, b_stage16 = 3u * b_kb16;
+    const bool resident = p.w_resident != 0;
+    const uint32_t sA16 = (s_addr(sA) & 0x3FFFF) >> 4, sB16 = (s_addr(sB) & 0x3FFFF) >> 4;
+    const uint32_t acc_cols = 2u * block_n;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc = 0, acc_phase = 0;
+    if (resident) mbar_wait(w_bar, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        for (int st = 0; st < nst; ++st) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a16 = sA16 + (uint32_t)stage * a_stage16;
+                // weight k-block index of (ky, kx, chunk) is (ky*3 + kx)*cpt + chunk; st = ky*cpt + chunk
+                const int ky = st / cpt, c = st - ky * cpt;
+                const uint32_t b16 = resident ? sB16 + (uint32_t)(ky * 3 * cpt + c) * b_kb16 : sB16 + (uint32_t)stage * b_stage16;
+                const uint32_t b_step = resident ? (uint32_t)cpt * b_kb16 : b_kb16;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t a_desc = desc_hi | (uint64_t)(a16 + (uint32_t)sub * (TC_HALO_BYTES >> 4) + (uint32_t)kx * 8u + (uint32_t)ks * 2u);
+                            const uint64_t b_desc = desc_hi | (uint64_t)(b16 + (uint32_t)kx * b_step + (uint32_t)ks * 2u);
+                            umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st | kx | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (st == nst - 1) umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (swizzle atoms)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // [stages][group] A k-blocks | B k-blocks ([stages][group] streamed, or [num_kblocks] resident) | barriers | bias
     uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)p.stages * p.group * p.a_bytes;
-    const size_t b_region = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes;
+    uint8_t *sB = smem + (p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes);
+    const size_t b_region = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes
+                                         : (p.halo ? (size_t)p.stages * 3 * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + b_region);
     uint64_t *full_bar = bars, *empty_bar = bars + TC_MAX_STAGES, *tfull_bar = bars + 2 * TC_MAX_STAGES, *tempty_bar = tfull_bar + 2;
     uint64_t *w_bar = tempty_bar + 2;
@@ -570,6 +631,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
             int stage = 0;
             uint32_t phase = 0;
+            if (p.halo) {
+                const uint32_t tx_bytes = 2u * (uint32_t)(TC_HALO_ROWS * 128) + (p.w_resident ? 0u : 3u * (uint32_t)p.b_bytes);
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                    const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
+                    const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt, n0 = nt * p.block_n;
+                    for (int ky = 0; ky < 3; ++ky) {
+                        for (int c = 0; c < cpt; ++c) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                                uint8_t *a_dst = sA + (size_t)stage * 2 * TC_HALO_BYTES;
+                                for (int sub = 0; sub < 2; ++sub) {      // sub-tile = image row oy0 + sub, pixels ox0-1 .. ox0+128
+                                    if (c < p.chunks0) tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA0, &full_bar[stage], c * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
+                                    else tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA1, &full_bar[stage], (c - p.chunks0) * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
+                                }
+                                if (!p.w_resident) {
+                                    uint8_t *b_dst = sB + (size_t)stage * 3 * p.b_bytes;
+                                    for (int kx = 0; kx < 3; ++kx)
+                                        tma_load_2d(b_dst + (size_t)kx * p.b_bytes, &p.tmW, &full_bar[stage], ((ky * 3 + kx) * cpt + c) * 64, n0);
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            } else
             for (int tile = blockIdx.x / p.ksplit; tile < total_tiles; tile += gridDim.x / p.ksplit) {
                 const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
@@ -602,7 +691,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
     } else if (warp == 1) {
         // =================== MMA issuer (whole warp runs the loop; one elected lane issues) ===================
-        if (p.kc == 64) {
+        if (p.halo) mma_role_halo(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+        else if (p.kc == 64) {
             if (p.msub == 2) mma_role<4, 2>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
             else mma_role<4, 1>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
         } else {
@@ -1066,6 +1156,18 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) stages = 2;
     p.stages = stages;
+    // sliding-window (halo) A tiles for the wide-frame 3x3 layers: one row-segment load serves the three horizontal taps
+    static const int halo_on = getenv("FUSG_NO_HALO") ? 0 : 1;
+    static const int halo_nmax = getenv("FUSG_HALO_NMAX") ? atoi(getenv("FUSG_HALO_NMAX")) : 64;
+    p.halo = 0;
+    if (halo_on && p.ksplit == 1 && d.ksize == 3 && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
+        p.block_n <= halo_nmax) {
+        const int budget = (want_staged ? 192 : 222) * 1024 - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
+        const int stage_bytes = 2 * TC_HALO_BYTES + (p.w_resident ? 0 : 3 * p.b_bytes);
+        int st = budget / stage_bytes;
+        if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+        if (st >= 2) { p.halo = 1; p.stages = st; p.group = 1; }
+    }
     int cols = 2 * p.msub * p.block_n;
     p.tmem_cols = cols < 32 ? 32 : cols;
 
@@ -1106,6 +1208,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)d.W * pitch * 2, (cuuint64_t)d.H * d.W * pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.Wt * d.stride), (cuuint32_t)(p.Ht * d.stride), (cuuint32_t)p.Bt};
+        if (p.halo) { box[1] = TC_HALO_ROWS; box[2] = 1; box[3] = 1; }
         cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
         return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1122,7 +1225,9 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FUSG_ERR_UNSUPPORTED;
     }
-    const size_t smem = (size_t)p.stages * p.group * p.a_bytes + (p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes) +
+    const size_t pipe_a = p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes;
+    const size_t pipe_b = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (p.halo ? (size_t)p.stages * 3 * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
+    const size_t smem = pipe_a + pipe_b +
                         1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
     static bool attr_set = false;
     if (!attr_set) {

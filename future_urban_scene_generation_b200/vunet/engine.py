@@ -10,6 +10,7 @@ dtype 'bf16' is the product path (tcgen05 kernels); dtype 'fp32' is the verifica
 (north_star: <=1e-4), which runs the same program on the CUDA-core direct kernel.
 """
 import ctypes as C
+import os
 
 from .. import _lib
 
@@ -69,7 +70,7 @@ class VunetEngine:
         self._wkey = None
         self._w = {}
         self._wp = {}                  # pixel-pair packed weights of the narrow stride-1 layers
-        self.pair_narrow = True        # run 32-channel stride-1 layers on pixel pairs (fusg_fold_weightnorm_paired)
+        self.pair_narrow = os.environ.get("FUSG_NO_PAIR") is None   # run 32-channel stride-1 layers on pixel pairs (fusg_fold_weightnorm_paired)
         self.launches = 0
         self.profile = None            # list -> per-launch (path, impl, flops, start, end) CUDA-event records
         self.noise_provider = None     # callable(B,C,H,W) -> NHWC fp32 device tensor; None = CPU torch.randn (reference semantics)

@@ -146,6 +146,9 @@ CONV_CASES = [
     ("msub2_wide", 4, (128,), 128, 3, 1, 256, True, False, 0),        # enough tiles for 256-row CTA tiles
     ("msub2_down", 8, (128,), 128, 3, 2, 256, False, False, 0),
     ("msub2_cat32", 4, (32, 32), 32, 3, 1, 256, True, False, 0),
+    ("halo_cat64", 4, (64, 64), 64, 3, 1, 256, True, False, 0),       # sliding-window A tiles, streamed weights
+    ("halo_res64", 4, (64,), 64, 3, 1, 256, True, False, 0),          # sliding-window A tiles, resident weights
+    ("halo_w128", 16, (64,), 64, 3, 1, 128, True, False, 0),          # one tile column (image row == sub-tile)
 ]
 
 
@@ -238,6 +241,27 @@ def test_forward_matches_oracle(cuda, nets, dtype, impl, tol):
         errs[f"mu_shape{i}"] = _maxabs(g_mus[i], r_mus[i])
     print(dtype, impl, errs)
     assert max(errs.values()) <= tol, errs
+
+
+def test_forward_matches_oracle_batch8(cuda, nets):
+    """Batch 8 is the smallest batch at which the wide layers take the large-batch kernel variants of the bench
+    (256-row CTA tiles, sliding-window A tiles, warp-staged epilogue); batch 2 above never reaches them."""
+    torch = cuda
+    m, sd, VO = nets
+    m.set_compute("bf16", "auto")
+    x, y = _inputs(torch, 40, 8)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        r_x, r_mua, r_mus = VO.forward(sd, y, x)
+    torch.manual_seed(3)
+    g_x, g_mua, g_mus = m(y.cuda(), x.cuda())
+    torch.cuda.synchronize()
+    errs = {"x_tilde": _maxabs(g_x, r_x)}
+    for i in range(2):
+        errs[f"mu_app{i}"] = _maxabs(g_mua[i], r_mua[i])
+        errs[f"mu_shape{i}"] = _maxabs(g_mus[i], r_mus[i])
+    print("batch8", errs)
+    assert max(errs.values()) <= TOL_BF16, errs
 
 
 def test_golden_fingerprint(cuda, nets):
