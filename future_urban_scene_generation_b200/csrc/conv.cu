@@ -1158,7 +1158,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.stages = stages;
     // sliding-window (halo) A tiles for the wide-frame 3x3 layers: one row-segment load serves the three horizontal taps
     static const int halo_on = getenv("FUSG_NO_HALO") ? 0 : 1;
-    static const int halo_nmax = getenv("FUSG_HALO_NMAX") ? atoi(getenv("FUSG_HALO_NMAX")) : 64;
+    static const int halo_nmax = getenv("FUSG_HALO_NMAX") ? atoi(getenv("FUSG_HALO_NMAX")) : 128;
     p.halo = 0;
     if (halo_on && p.ksplit == 1 && d.ksize == 3 && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
         p.block_n <= halo_nmax) {
