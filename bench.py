@@ -163,6 +163,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version/info lines must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     B = args.crops_per_rank
     peaks = _peaks()
