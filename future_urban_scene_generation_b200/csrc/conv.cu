@@ -91,7 +91,9 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
                 for (int i = 0; i < 16; ++i) v[i] += (float)r[i];
             }
         } else {
-            for (int i = 0; i < nvalid; ++i) v[i] += (float)r[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nvalid) v[i] += (float)r[i];
         }
     }
     float z[16];
@@ -116,15 +118,20 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
         if (o.layout == 1 && o.mode == FUSG_OUT_UNPAIR) {    // pixel-pair packed layer -> NCHW fp32
             float *p = reinterpret_cast<float *>(o.ptr);
             const int cq = d.cout >> 1;
-            for (int i = 0; i < nvalid; ++i) {
-                const int nn = n + i, dx = nn / cq, c = nn - dx * cq;
-                p[(((size_t)b * cq + c) * Ho + y) * (2 * Wo) + 2 * x + dx] = o.elu ? elu1(val[i]) : val[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {             // constant trip count keeps val[] in registers
+                if (i < nvalid) {
+                    const int nn = n + i, dx = nn >= cq ? 1 : 0, c = nn - dx * cq;   // nn < 2*cq
+                    p[(((size_t)b * cq + c) * Ho + y) * (2 * Wo) + 2 * x + dx] = o.elu ? elu1(val[i]) : val[i];
+                }
             }
         } else if (o.layout == 1) {                          // NCHW fp32, unrounded
             float *p = reinterpret_cast<float *>(o.ptr);
             const size_t plane = (size_t)a.Ht * a.Wt;
             const size_t base = ((size_t)b * a.Ct + a.ch) * plane + (size_t)a.py * a.Wt + a.px;
-            for (int i = 0; i < nvalid; ++i) p[base + (size_t)i * plane] = o.elu ? elu1(val[i]) : val[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nvalid) p[base + (size_t)i * plane] = o.elu ? elu1(val[i]) : val[i];
         } else if constexpr (sizeof(T) == 2) {
             __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(o.ptr) + a.pix * a.Ct + a.ch;
             uint32_t w[8];
@@ -141,11 +148,15 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
                 reinterpret_cast<uint4 *>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                 reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
             } else {
-                for (int i = 0; i < nvalid; ++i) p[i] = reinterpret_cast<const __nv_bfloat16 *>(w)[i];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) p[i] = __ushort_as_bfloat16((unsigned short)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu)));
             }
         } else {
             float *p = reinterpret_cast<float *>(o.ptr) + a.pix * a.Ct + a.ch;
-            for (int i = 0; i < nvalid; ++i) p[i] = o.elu ? elu1(val[i]) : val[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nvalid) p[i] = o.elu ? elu1(val[i]) : val[i];
         }
     }
 }
