@@ -10,6 +10,11 @@ rows = list(csv.DictReader(lines[start:]))
 skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rows = rows[skip:]
 agg = collections.defaultdict(lambda: [0, 0.0])
+spin = [r for r in rows if "spin_kernel" in r["Kernel Name"]]
+rows = [r for r in rows if "spin_kernel" not in r["Kernel Name"]]
+if spin:
+    # torch.cuda._sleep: bench.py parks the stream behind it before its per-launch roofline pass (outside the timed steps)
+    print(f"(excluded: {len(spin)} torch.cuda._sleep spin launches, {sum(float(r['Metric Value']) for r in spin) / 1e6:.1f} ms -- bench.py's per-launch timing pass)")
 for r in rows:
     name = r["Kernel Name"].split("(")[0]
     agg[name][0] += 1
