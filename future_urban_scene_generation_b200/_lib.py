@@ -43,6 +43,9 @@ def _load():
         "fusg_nhwc_to_nchw": ([vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_to_image": ([vp, vp, i, i, i, vp], i),
         "fusg_elu": ([vp, vp, sz, i, vp], i),
+        "fusg_resize_u8": ([vp] * 6 + [i, i, vp], i),
+        "fusg_paste_workspace_bytes": ([i, i, i], sz),
+        "fusg_paste_back": ([vp] * 7 + [sz, i, i, i, i, i, i, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

@@ -1,0 +1,138 @@
+"""Paste-back of completed vehicle crops into video frames on the GPU.
+
+Mirrors what `trajectory_inference.py` does after each network forward (:184-198 ICN, :236-250 VUNet, :393-407 and
+:428-442 in the trajectory loop):
+
+    crop_inv = cv2.resize(net_image, crop_size_orig[::-1])
+    crop_inv = crop_inv[pad_xy_before[1]:crop_inv.shape[0] - pad_xy_after[1],
+                        pad_xy_before[0]:crop_inv.shape[1] - pad_xy_after[0]]
+    out_frame = np.zeros_like(frame)
+    out_frame[crop_xy_min[1]: ..., crop_xy_min[0]: ...] = crop_inv
+    img_output[dst_sketch_mask] = out_frame[dst_sketch_mask]
+
+`paste_back` is the one-vehicle drop-in (numpy in / numpy out, same arguments as the reference's local variables),
+`paste_back_batch` the form a maintainer adopts: every (vehicle, step) of a clip in one call, crops taken straight
+from `to_image_batch` on the device, bit-identical to the sequential reference loop (last vehicle wins where masks
+overlap).  `resize` is cv2.resize(img, dsize) for uint8 HWC images.  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+INFO_FIELDS = 9      # frame, h_orig, w_orig, pad_x0, pad_y0, pad_x1, pad_y1, x_min, y_min
+
+
+def _dev(torch, a, dtype=None):
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def resize_batch(images, dsizes):
+    """images: list of uint8 (h, w, 3) arrays / tensors; dsizes: list of (width, height) like cv2.
+    Returns a list of uint8 CUDA tensors (height, width, 3) == cv2.resize(image, dsize) (INTER_LINEAR)."""
+    torch = _lib.require_cuda()
+    assert len(images) == len(dsizes) and len(images) > 0
+    srcs = [_dev(torch, im, torch.uint8) for im in images]
+    for s in srcs:
+        if s.dim() != 3 or s.shape[2] != 3 or s.shape[0] < 1 or s.shape[1] < 1:
+            raise ValueError("resize_batch: images must be (h, w, 3) uint8")
+    src_off, dst_off, so, do = [], [], 0, 0
+    for s, (dw, dh) in zip(srcs, dsizes):
+        if dw < 1 or dh < 1:
+            raise ValueError("resize_batch: empty destination size")
+        src_off.append(so)
+        dst_off.append(do)
+        so += s.numel()
+        do += int(dh) * int(dw) * 3
+    src = torch.cat([s.reshape(-1) for s in srcs])
+    dst = torch.empty((do,), dtype=torch.uint8, device=src.device)
+    src_hw = torch.tensor([[s.shape[0], s.shape[1]] for s in srcs], dtype=torch.int32, device=src.device)
+    dst_hw = torch.tensor([[int(dh), int(dw)] for dw, dh in dsizes], dtype=torch.int32, device=src.device)
+    t_so = torch.tensor(src_off, dtype=torch.int64, device=src.device)
+    t_do = torch.tensor(dst_off, dtype=torch.int64, device=src.device)
+    mx = max(int(dh) * int(dw) for dw, dh in dsizes)
+    _lib.check(_lib.lib().fusg_resize_u8(_lib.ptr(src), _lib.ptr(t_so), _lib.ptr(src_hw), _lib.ptr(dst), _lib.ptr(t_do), _lib.ptr(dst_hw),
+                                         len(srcs), mx, _lib.stream_ptr(torch)), "fusg_resize_u8")
+    return [dst[o:o + int(dh) * int(dw) * 3].view(int(dh), int(dw), 3) for o, (dw, dh) in zip(dst_off, dsizes)]
+
+
+def resize(image, dsize):
+    """cv2.resize(image, dsize) for a uint8 (h, w, 3) numpy image; returns numpy."""
+    return resize_batch([image], [dsize])[0].cpu().numpy()
+
+
+def pack_crop_info(crop_infos, frame_index, frame_hw):
+    """crop_info dicts (warp_learn/models.py:337-342) + frame index per item -> (B, 9) int32 for fusg_paste_back.
+    Raises ValueError where the reference's slice assignment would raise (the un-padded crop must fit the frame)."""
+    Hf, Wf = frame_hw
+    out = np.zeros((len(crop_infos), INFO_FIELDS), np.int32)
+    for b, (ci, fr) in enumerate(zip(crop_infos, frame_index)):
+        h, w = (int(v) for v in ci["crop_size_orig"])
+        px0, py0 = (int(v) for v in ci["pad_xy_before"])
+        px1, py1 = (int(v) for v in ci["pad_xy_after"])
+        x_min, y_min = (int(v) for v in ci["crop_xy_min"])
+        ch, cw = h - py0 - py1, w - px0 - px1
+        if h < 1 or w < 1 or min(px0, py0, px1, py1) < 0 or ch < 1 or cw < 1:
+            raise ValueError(f"paste_back: item {b}: empty crop after un-padding")
+        if x_min < 0 or y_min < 0 or y_min + ch > Hf or x_min + cw > Wf:
+            raise ValueError(f"paste_back: item {b}: crop of shape {(ch, cw)} at {(x_min, y_min)} does not fit the {(Hf, Wf)} frame")
+        out[b] = (fr, h, w, px0, py0, px1, py1, x_min, y_min)
+    return out
+
+
+def paste_back_batch(frames, crops, masks, crop_infos, frame_index, mask_rects=None):
+    """frames: (F, Hf, Wf, 3) uint8 CUDA tensor, updated in place (or numpy -> a new CUDA tensor is returned);
+    crops: (B, S, S, 3) uint8 (the `to_image_batch` output); masks: list of B bool/uint8 arrays -- full-frame
+    `dst_sketch_mask`s, or sub-rectangles when `mask_rects` [(x, y, w, h)] is given; crop_infos: list of B dicts;
+    frame_index: list of B ints.  Items are applied in list order (later items win), like the reference loop."""
+    torch = _lib.require_cuda()
+    fr = _dev(torch, frames, torch.uint8)
+    if fr.dim() != 4 or fr.shape[3] != 3:
+        raise ValueError("paste_back_batch: frames must be (F, Hf, Wf, 3) uint8")
+    F, Hf, Wf = int(fr.shape[0]), int(fr.shape[1]), int(fr.shape[2])
+    cr = _dev(torch, crops, torch.uint8)
+    B, S = int(cr.shape[0]), int(cr.shape[1])
+    if cr.dim() != 4 or cr.shape[2] != S or cr.shape[3] != 3 or not (len(masks) == len(crop_infos) == len(frame_index) == B):
+        raise ValueError("paste_back_batch: crops must be (B, S, S, 3) with one mask / crop_info / frame index per crop")
+    if any(f < 0 or f >= F for f in frame_index):
+        raise ValueError("paste_back_batch: frame index out of range")
+    info = pack_crop_info(crop_infos, frame_index, (Hf, Wf))
+    rects = np.zeros((B, 4), np.int32)
+    offs, flat, o = [], [], 0
+    for b, m in enumerate(masks):
+        mt = _dev(torch, m)
+        mt = (mt != 0).to(torch.uint8) if mt.dtype != torch.uint8 else mt
+        if mask_rects is None:
+            if tuple(mt.shape) != (Hf, Wf):
+                raise ValueError(f"paste_back_batch: mask {b} is {tuple(mt.shape)}, frame is {(Hf, Wf)}")
+            rects[b] = (0, 0, Wf, Hf)
+        else:
+            x, y, w, h = (int(v) for v in mask_rects[b])
+            if tuple(mt.shape) != (h, w):
+                raise ValueError(f"paste_back_batch: mask {b} is {tuple(mt.shape)}, its rect says {(h, w)}")
+            rects[b] = (x, y, w, h)
+        offs.append(o)
+        flat.append(mt.reshape(-1))
+        o += mt.numel()
+    mflat = torch.cat(flat)
+    t_off = torch.tensor(offs, dtype=torch.int64, device=fr.device)
+    t_rect = torch.from_numpy(rects).to(fr.device)
+    t_info = torch.from_numpy(info).to(fr.device)
+    L = _lib.lib()
+    ws_bytes = L.fusg_paste_workspace_bytes(F, Hf, Wf)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=fr.device)
+    mx = int((rects[:, 2].astype(np.int64) * rects[:, 3]).max())
+    _lib.check(L.fusg_paste_back(_lib.ptr(fr), _lib.ptr(cr), _lib.ptr(mflat), _lib.ptr(t_off), _lib.ptr(t_rect), _lib.ptr(t_info),
+                                 _lib.ptr(ws), ws_bytes, B, F, Hf, Wf, S, mx, _lib.stream_ptr(torch)), "fusg_paste_back")
+    return fr
+
+
+def paste_back(img_output, net_image, crop_info, dst_sketch_mask):
+    """One vehicle, reference-style: numpy (H, W, 3) uint8 `img_output` is updated in place and returned."""
+    out = paste_back_batch(img_output[None], np.asarray(net_image)[None], [dst_sketch_mask], [crop_info], [0])
+    img_output[...] = out[0].cpu().numpy()
+    return img_output

@@ -128,3 +128,29 @@ def make_vunet_inputs(start: int, count: int, res: int = 256):
         xs.append(np.float32(x8) / 255 * 2.0 - 1.0)
         ys.append(np.float32(y8) / 255 * 2.0 - 1.0)
     return np.stack(xs).astype(np.float32), np.stack(ys).astype(np.float32)
+
+
+def make_paste_case(idx: int, frame_hw=(1080, 1920), crop_res: int = 256):
+    """One synthetic vehicle for the paste-back step (trajectory_inference.py:236-250): a bounding box (every fourth one
+    hangs over a frame border so the square crop needs padding), the full-frame vehicle mask `dst_sketch_mask`
+    (an ellipse inside the box, bool), and a `crop_res`^2 uint8 completed view.  Returns (bbox, mask, net_image);
+    the crop geometry (`crop_info`) is derived from the bbox by the caller (utils/crop_utils.py:4-52)."""
+    H, W = frame_hw
+    rng = np.random.default_rng(70_000 + idx)
+    bw = int(rng.integers(40, min(W, 480)))
+    bh = int(rng.integers(30, min(H, 360)))
+    if idx % 4 == 3:                                   # hug a border: the 1.1x square crop sticks out of the frame
+        edge = (idx // 4) % 4
+        x0 = 0 if edge == 0 else (W - 1 - bw if edge == 1 else int(rng.integers(0, W - bw)))
+        y0 = 0 if edge == 2 else (H - 1 - bh if edge == 3 else int(rng.integers(0, H - bh)))
+    else:
+        x0 = int(rng.integers(0, W - bw))
+        y0 = int(rng.integers(0, H - bh))
+    x1, y1 = x0 + bw, y0 + bh
+    yy, xx = np.mgrid[0:H, 0:W]
+    cx, cy = (x0 + x1) / 2.0, (y0 + y1) / 2.0
+    mask = ((xx - cx) / (bw / 2.0)) ** 2 + ((yy - cy) / (bh / 2.0)) ** 2 <= 1.0
+    ys, xs = np.nonzero(mask)
+    bbox = [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())]          # as warp_learn/models.py:330-332
+    net_image = rng.integers(0, 256, (crop_res, crop_res, 3), dtype=np.uint8)
+    return bbox, mask, net_image

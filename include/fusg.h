@@ -186,6 +186,24 @@ int fusg_nhwc_to_nchw(const void *in, float *out, int B, int C, int H, int W, in
  * HWC uint8, x = clip((x + 1) / 2 * 255, 0, 255) with the reference's truncating cast.
  *   in [B,3,H,W] f32 -> out [B,H,W,3] u8 */
 int fusg_to_image(const float *in, uint8_t *out, int B, int H, int W, void *stream);
+/* ---- paste-back of completed crops into frames --------------------------------------
+ * cv2.resize(src, dsize) with INTER_LINEAR on 8-bit, 3-channel HWC images, batched: item i reads src + src_off[i]
+ * ([src_hw[2i], src_hw[2i+1], 3]) and writes dst + dst_off[i] ([dst_hw[2i], dst_hw[2i+1], 3]); offsets in bytes,
+ * all arrays in device memory.  Replaces cv2.resize at trajectory_inference.py:191,243,400,435. */
+int fusg_resize_u8(const uint8_t *src, const long long *src_off, const int32_t *src_hw, uint8_t *dst, const long long *dst_off,
+                   const int32_t *dst_hw, int B, int max_dst_pixels, void *stream);
+size_t fusg_paste_workspace_bytes(int F, int Hf, int Wf);
+/* The five lines after each network forward (trajectory_inference.py:236-250): for item b = 0..B-1 in order,
+ *   crop_inv = resize(crops[b] (S,S,3), (w_orig, h_orig))[pad_y0 : h_orig - pad_y1, pad_x0 : w_orig - pad_x1]
+ *   frames[frame][mask_b] = (zeros with crop_inv placed at (x_min, y_min))[mask_b]
+ * info [B,9] int32 = frame, h_orig, w_orig, pad_x0, pad_y0, pad_x1, pad_y1, x_min, y_min (crop_info of
+ * warp_learn/models.py:337-342); the mask of item b is the uint8 array masks + mask_off[b] of shape
+ * (mask_rect[4b+3], mask_rect[4b+2]) placed at frame position (x, y) = (mask_rect[4b], mask_rect[4b+1]) -- a full-frame
+ * dst_sketch_mask is rect (0, 0, Wf, Hf).  Later items win where masks overlap, as in the sequential reference.
+ * frames [F,Hf,Wf,3] u8 is updated in place. */
+int fusg_paste_back(uint8_t *frames, const uint8_t *crops, const uint8_t *masks, const long long *mask_off, const int32_t *mask_rect,
+                    const int32_t *info, void *workspace, size_t workspace_bytes, int B, int F, int Hf, int Wf, int S,
+                    int max_mask_pixels, void *stream);
 /* NHWC elementwise ELU (activation dtype) over n elements. */
 int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
 

@@ -174,3 +174,28 @@ def test_space_depth_permutations_are_block_major():
             for c in range(3):
                 assert torch.equal(s[:, (dy * 2 + dx) * 3 + c], x[:, c, dy::2, dx::2])
     assert torch.equal(VO.depth_to_space(s), x)
+
+
+def test_frame_oracle_matches_cv2_goldens():
+    """oracle/frame_oracle.py (cv2.resize INTER_LINEAR restatement + paste-back lines) against the vectors that
+    scripts/make_golden_frame.py produced with cv2 and the reference's square_crop_from_bbox."""
+    import hashlib
+    import json
+    from oracle import frame_oracle as FO
+    from future_urban_scene_generation_b200 import synth
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frame_golden.json")))
+    sha = lambda a: hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for c in gold["resize"]:
+        sh, sw = c["src_hw"]
+        src = np.random.default_rng(c["seed"]).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert sha(FO.resize_linear_u8(src, (c["dst_hw"][1], c["dst_hw"][0]))) == c["sha1"], c
+    Hf, Wf = gold["frame_hw"]
+    img = np.random.default_rng(gold["frame_seed"]).integers(0, 256, (Hf, Wf, 3), dtype=np.uint8)
+    for ci, p in zip(gold["crop_info"], gold["paste"]):
+        bbox, mask, net = synth.make_paste_case(ci["idx"], (Hf, Wf))
+        info = FO.square_crop_info((Hf, Wf), bbox)
+        assert bbox == ci["bbox"]
+        for k in ("crop_xy_min", "pad_xy_before", "pad_xy_after", "crop_size_orig"):
+            assert list(info[k]) == ci[k], (ci["idx"], k)
+        FO.paste_back(img, net, info, mask)
+        assert sha(img) == p["sha1_after"], ci["idx"]

@@ -1,0 +1,106 @@
+"""Paste-back row: CUDA resize / paste-back against the numpy oracle and the cv2 goldens."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from future_urban_scene_generation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frame_golden.json")))
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_resize_matches_cv2_goldens(cuda):
+    from future_urban_scene_generation_b200.frame_ops import resize_batch
+    imgs, ds = [], []
+    for c in GOLD["resize"]:
+        sh, sw = c["src_hw"]
+        imgs.append(np.random.default_rng(c["seed"]).integers(0, 256, (sh, sw, 3), dtype=np.uint8))
+        ds.append((c["dst_hw"][1], c["dst_hw"][0]))
+    outs = resize_batch(imgs, ds)                       # one ragged batch
+    for c, o in zip(GOLD["resize"], outs):
+        assert list(o.shape[:2]) == c["dst_hw"]
+        assert sha(o.cpu().numpy()) == c["sha1"], c
+
+
+def test_resize_matches_oracle_random_sizes(cuda):
+    from future_urban_scene_generation_b200.frame_ops import resize_batch
+    from oracle import frame_oracle as FO
+    rng = np.random.default_rng(5)
+    imgs, ds = [], []
+    for t in range(60):
+        sh, sw = (int(v) for v in rng.integers(1, 300, 2))
+        dh, dw = (int(v) for v in rng.integers(1, 300, 2))
+        if t % 6 == 0:
+            sh, sw = 256, 256
+        if t % 10 == 0:
+            sh, sw = 2 * dh, 2 * dw                      # the exact-halving (box average) route
+        imgs.append(rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8))
+        ds.append((dw, dh))
+    outs = resize_batch(imgs, ds)
+    for im, d, o in zip(imgs, ds, outs):
+        assert np.array_equal(o.cpu().numpy(), FO.resize_linear_u8(im, d)), (im.shape, d)
+
+
+def _golden_sequence():
+    Hf, Wf = GOLD["frame_hw"]
+    frame = np.random.default_rng(GOLD["frame_seed"]).integers(0, 256, (Hf, Wf, 3), dtype=np.uint8)
+    items = []
+    for ci in GOLD["crop_info"]:
+        bbox, mask, net = synth.make_paste_case(ci["idx"], (Hf, Wf))
+        assert bbox == ci["bbox"]
+        items.append((mask, net, {k: ci[k] for k in ("crop_xy_min", "pad_xy_before", "pad_xy_after", "crop_size_orig")}))
+    return frame, items
+
+
+def test_paste_back_sequence_matches_cv2_goldens(cuda):
+    """Prefixes of the golden vehicle sequence pasted in ONE batched call each must land on the frame hash the
+    sequential cv2 reference loop had after that many vehicles (overlapping masks: last vehicle wins)."""
+    from future_urban_scene_generation_b200.frame_ops import paste_back_batch, paste_back
+    frame, items = _golden_sequence()
+    for n in (1, 5, 13, len(items)):
+        out = paste_back_batch(frame[None].copy(), np.stack([it[1] for it in items[:n]]), [it[0] for it in items[:n]],
+                               [it[2] for it in items[:n]], [0] * n)
+        assert sha(out[0].cpu().numpy()) == GOLD["paste"][n - 1]["sha1_after"], n
+    # one-vehicle drop-in, applied sequentially like the reference
+    img = frame.copy()
+    for k, (mask, net, info) in enumerate(items[:6]):
+        paste_back(img, net, info, mask)
+        assert sha(img) == GOLD["paste"][k]["sha1_after"]
+
+
+def test_paste_back_multi_frame_and_rects_match_oracle(cuda):
+    """Config-5-like: several frames, several vehicles per frame, masks given as bbox-sized sub-rectangles."""
+    from future_urban_scene_generation_b200.frame_ops import paste_back_batch
+    from oracle import frame_oracle as FO
+    Hf, Wf, F, V = 270, 480, 3, 7
+    rng = np.random.default_rng(2)
+    frames = rng.integers(0, 256, (F, Hf, Wf, 3), dtype=np.uint8)
+    ref = frames.copy()
+    crops, masks, rects, infos, fidx = [], [], [], [], []
+    for f in range(F):
+        for v in range(V):
+            bbox, mask, net = synth.make_paste_case(100 + f * V + v, (Hf, Wf))
+            info = FO.square_crop_info((Hf, Wf), bbox)
+            FO.paste_back(ref[f], net, info, mask)
+            x0, y0, x1, y1 = bbox
+            crops.append(net); infos.append(info); fidx.append(f)
+            masks.append(mask[y0:y1 + 1, x0:x1 + 1]); rects.append((x0, y0, x1 - x0 + 1, y1 - y0 + 1))
+    out = paste_back_batch(frames, np.stack(crops), masks, infos, fidx, mask_rects=rects)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_paste_back_rejects_what_the_reference_rejects(cuda):
+    from future_urban_scene_generation_b200.frame_ops import paste_back_batch
+    frame = np.zeros((1, 64, 64, 3), np.uint8)
+    crop = np.zeros((1, 256, 256, 3), np.uint8)
+    mask = np.ones((64, 64), bool)
+    bad = {"crop_xy_min": (40, 0), "pad_xy_before": (0, 0), "pad_xy_after": (0, 0), "crop_size_orig": (30, 30)}   # 40 + 30 > 64
+    with pytest.raises(ValueError):
+        paste_back_batch(frame, crop, [mask], [bad], [0])
