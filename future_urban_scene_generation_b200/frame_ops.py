@@ -84,6 +84,68 @@ def pack_crop_info(crop_infos, frame_index, frame_hw):
     return out
 
 
+class PastePlan:
+    """Device-side description of a batch of paste-back items (masks, rectangles, crop geometry), built once by
+    `prepare_paste` and reusable for any frames / crops tensors of the same layout."""
+
+    def __init__(self, masks, off, rect, info, max_mask_pixels, B, frame_hw):
+        self.masks, self.off, self.rect, self.info = masks, off, rect, info
+        self.max_mask_pixels, self.B, self.frame_hw = max_mask_pixels, B, frame_hw
+
+
+def prepare_paste(masks, crop_infos, frame_index, frame_hw, n_frames, mask_rects=None):
+    torch = _lib.require_cuda()
+    Hf, Wf = frame_hw
+    B = len(masks)
+    if not (len(crop_infos) == len(frame_index) == B) or B == 0:
+        raise ValueError("paste_back: one mask / crop_info / frame index per crop")
+    if any(f < 0 or f >= n_frames for f in frame_index):
+        raise ValueError("paste_back: frame index out of range")
+    info = pack_crop_info(crop_infos, frame_index, (Hf, Wf))
+    rects = np.zeros((B, 4), np.int32)
+    offs, flat, o = [], [], 0
+    for b, m in enumerate(masks):
+        mt = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m))
+        if mt.dtype == torch.bool:
+            mt = mt.view(torch.uint8)                      # numpy/torch bools are one byte, 0 or 1
+        elif mt.dtype != torch.uint8:
+            mt = (mt != 0).to(torch.uint8)
+        if mask_rects is None:
+            if tuple(mt.shape) != (Hf, Wf):
+                raise ValueError(f"paste_back: mask {b} is {tuple(mt.shape)}, frame is {(Hf, Wf)}")
+            rects[b] = (0, 0, Wf, Hf)
+        else:
+            x, y, w, h = (int(v) for v in mask_rects[b])
+            if tuple(mt.shape) != (h, w):
+                raise ValueError(f"paste_back: mask {b} is {tuple(mt.shape)}, its rect says {(h, w)}")
+            rects[b] = (x, y, w, h)
+        offs.append(o)
+        flat.append(mt.reshape(-1))
+        o += mt.numel()
+    mflat = torch.cat(flat).cuda()                         # one H2D for all host masks
+    dev = mflat.device
+    return PastePlan(mflat, torch.tensor(offs, dtype=torch.int64, device=dev), torch.from_numpy(rects).to(dev),
+                     torch.from_numpy(info).to(dev), int((rects[:, 2].astype(np.int64) * rects[:, 3]).max()), B, (Hf, Wf))
+
+
+def paste_back_packed(frames, crops, plan: PastePlan):
+    """frames (F, Hf, Wf, 3) uint8 CUDA tensor, updated in place; crops (B, S, S, 3) uint8 CUDA tensor."""
+    torch = _lib.require_cuda()
+    F, Hf, Wf = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+    B, S = int(crops.shape[0]), int(crops.shape[1])
+    if frames.dim() != 4 or frames.shape[3] != 3 or (Hf, Wf) != plan.frame_hw or frames.dtype != torch.uint8:
+        raise ValueError("paste_back: frames must be (F, Hf, Wf, 3) uint8 matching the plan")
+    if crops.dim() != 4 or crops.shape[2] != S or crops.shape[3] != 3 or B != plan.B or crops.dtype != torch.uint8:
+        raise ValueError("paste_back: crops must be (B, S, S, 3) uint8 with one crop per planned item")
+    L = _lib.lib()
+    ws_bytes = L.fusg_paste_workspace_bytes(F, Hf, Wf)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=frames.device)
+    _lib.check(L.fusg_paste_back(_lib.ptr(frames), _lib.ptr(crops), _lib.ptr(plan.masks), _lib.ptr(plan.off), _lib.ptr(plan.rect),
+                                 _lib.ptr(plan.info), _lib.ptr(ws), ws_bytes, B, F, Hf, Wf, S, plan.max_mask_pixels,
+                                 _lib.stream_ptr(torch)), "fusg_paste_back")
+    return frames
+
+
 def paste_back_batch(frames, crops, masks, crop_infos, frame_index, mask_rects=None):
     """frames: (F, Hf, Wf, 3) uint8 CUDA tensor, updated in place (or numpy -> a new CUDA tensor is returned);
     crops: (B, S, S, 3) uint8 (the `to_image_batch` output); masks: list of B bool/uint8 arrays -- full-frame
@@ -93,42 +155,9 @@ def paste_back_batch(frames, crops, masks, crop_infos, frame_index, mask_rects=N
     fr = _dev(torch, frames, torch.uint8)
     if fr.dim() != 4 or fr.shape[3] != 3:
         raise ValueError("paste_back_batch: frames must be (F, Hf, Wf, 3) uint8")
-    F, Hf, Wf = int(fr.shape[0]), int(fr.shape[1]), int(fr.shape[2])
     cr = _dev(torch, crops, torch.uint8)
-    B, S = int(cr.shape[0]), int(cr.shape[1])
-    if cr.dim() != 4 or cr.shape[2] != S or cr.shape[3] != 3 or not (len(masks) == len(crop_infos) == len(frame_index) == B):
-        raise ValueError("paste_back_batch: crops must be (B, S, S, 3) with one mask / crop_info / frame index per crop")
-    if any(f < 0 or f >= F for f in frame_index):
-        raise ValueError("paste_back_batch: frame index out of range")
-    info = pack_crop_info(crop_infos, frame_index, (Hf, Wf))
-    rects = np.zeros((B, 4), np.int32)
-    offs, flat, o = [], [], 0
-    for b, m in enumerate(masks):
-        mt = _dev(torch, m)
-        mt = (mt != 0).to(torch.uint8) if mt.dtype != torch.uint8 else mt
-        if mask_rects is None:
-            if tuple(mt.shape) != (Hf, Wf):
-                raise ValueError(f"paste_back_batch: mask {b} is {tuple(mt.shape)}, frame is {(Hf, Wf)}")
-            rects[b] = (0, 0, Wf, Hf)
-        else:
-            x, y, w, h = (int(v) for v in mask_rects[b])
-            if tuple(mt.shape) != (h, w):
-                raise ValueError(f"paste_back_batch: mask {b} is {tuple(mt.shape)}, its rect says {(h, w)}")
-            rects[b] = (x, y, w, h)
-        offs.append(o)
-        flat.append(mt.reshape(-1))
-        o += mt.numel()
-    mflat = torch.cat(flat)
-    t_off = torch.tensor(offs, dtype=torch.int64, device=fr.device)
-    t_rect = torch.from_numpy(rects).to(fr.device)
-    t_info = torch.from_numpy(info).to(fr.device)
-    L = _lib.lib()
-    ws_bytes = L.fusg_paste_workspace_bytes(F, Hf, Wf)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=fr.device)
-    mx = int((rects[:, 2].astype(np.int64) * rects[:, 3]).max())
-    _lib.check(L.fusg_paste_back(_lib.ptr(fr), _lib.ptr(cr), _lib.ptr(mflat), _lib.ptr(t_off), _lib.ptr(t_rect), _lib.ptr(t_info),
-                                 _lib.ptr(ws), ws_bytes, B, F, Hf, Wf, S, mx, _lib.stream_ptr(torch)), "fusg_paste_back")
-    return fr
+    plan = prepare_paste(masks, crop_infos, frame_index, (int(fr.shape[1]), int(fr.shape[2])), int(fr.shape[0]), mask_rects)
+    return paste_back_packed(fr, cr, plan)
 
 
 def paste_back(img_output, net_image, crop_info, dst_sketch_mask):
