@@ -116,9 +116,166 @@ __global__ void __launch_bounds__(256) k_paste_apply(uint8_t *__restrict__ frame
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// VUNet input packing (trajectory_inference.py:205-227): bbox of the vehicle mask -> square crop (utils/crop_utils.py:
+// 4-52) of the masked frame and of the two normal sketches -> cv2.resize to res x res -> background fill ->
+// to_tensor (utils/misc_utils.py:35-50) -> channel flip / concat.  Everything is pointwise in the output pixel once the
+// bbox is known, so it is one reduction kernel (k_mask_bbox) and one gather kernel (k_pack_inputs).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mask_bbox(const uint8_t *__restrict__ masks, const long long *__restrict__ off,
+                                                   const int *__restrict__ rect, int *__restrict__ bbox) {
+    const int b = blockIdx.y;
+    const int x0 = rect[4 * b], y0 = rect[4 * b + 1], w = rect[4 * b + 2], h = rect[4 * b + 3];
+    const uint8_t *m = masks + off[b];
+    int xmin = 0x7fffffff, ymin = 0x7fffffff, xmax = -1, ymax = -1;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)w * h; p += (long long)gridDim.x * blockDim.x) {
+        if (!m[p]) continue;
+        const int yy = (int)(p / w), xx = (int)(p - (long long)yy * w);
+        xmin = min(xmin, x0 + xx); xmax = max(xmax, x0 + xx);
+        ymin = min(ymin, y0 + yy); ymax = max(ymax, y0 + yy);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o)); ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && xmax >= 0) {
+        atomicMin(&bbox[4 * b], xmin); atomicMin(&bbox[4 * b + 1], ymin);
+        atomicMax(&bbox[4 * b + 2], xmax); atomicMax(&bbox[4 * b + 3], ymax);
+    }
+}
+
+__global__ void k_bbox_init(int *__restrict__ bbox, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { bbox[4 * b] = 0x7fffffff; bbox[4 * b + 1] = 0x7fffffff; bbox[4 * b + 2] = -1; bbox[4 * b + 3] = -1; }
+}
+
+struct CropGeom { int nx0, ny0, pxb, pyb, cw, ch; };
+
+// utils/crop_utils.py:14-50 for dataset='pascal' (Python float = double, int() truncates toward zero)
+__device__ __forceinline__ CropGeom crop_geometry(const int *bb, int image_h, int image_w) {
+    const int x_min = bb[0], y_min = bb[1], side_x = bb[2] - bb[0], side_y = bb[3] - bb[1];
+    const double major = (double)max(side_x, side_y) * 1.1;
+    const double cx = (double)x_min + (double)side_x / 2.0, cy = (double)y_min + (double)side_y / 2.0;
+    CropGeom g;
+    g.pxb = g.pyb = 0;
+    g.nx0 = (int)(cx - major / 2.0);
+    if (g.nx0 < 0) { g.pxb = -g.nx0; g.nx0 = 0; }
+    int nx1 = (int)(cx + major / 2.0) + g.pxb;
+    int pxa = 0;
+    if (nx1 > image_w) { pxa = nx1 - image_w; nx1 = image_w + pxa; }
+    g.ny0 = (int)(cy - major / 2.0);
+    if (g.ny0 < 0) { g.pyb = -g.ny0; g.ny0 = 0; }
+    int ny1 = (int)(cy + major / 2.0) + g.pyb;
+    int pya = 0;
+    if (ny1 > image_h) { pya = ny1 - image_h; ny1 = image_h + pya; }
+    g.cw = min(nx1, image_w + g.pxb + pxa) - g.nx0;
+    g.ch = min(ny1, image_h + g.pyb + pya) - g.ny0;
+    return g;
+}
+
+struct Px9 { uint8_t m[3], ns[3], nd[3]; };
+
+// pixel (cy, cx) of the three square crops: masked frame, source normals, destination normals (zero in the padding)
+__device__ __forceinline__ Px9 pack_fetch(const uint8_t *__restrict__ frame, const uint8_t *__restrict__ mask, const uint8_t *__restrict__ nsrc,
+                                          const uint8_t *__restrict__ ndst, const CropGeom &g, int rx0, int ry0, int rw, int rh, int Hf, int Wf,
+                                          int cy, int cx) {
+    Px9 p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.m[c] = p.ns[c] = p.nd[c] = 0;
+    const int fy = g.ny0 + cy - g.pyb, fx = g.nx0 + cx - g.pxb;
+    if (fy < 0 || fy >= Hf || fx < 0 || fx >= Wf) return p;
+    const int yy = fy - ry0, xx = fx - rx0;
+    if (yy < 0 || yy >= rh || xx < 0 || xx >= rw) return p;          // outside the item's rectangle everything is background
+    const size_t q = (size_t)yy * rw + xx;
+    const bool veh = mask[q] != 0;
+    const uint8_t *fp = frame + ((size_t)fy * Wf + fx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { p.m[c] = veh ? fp[c] : 0; p.ns[c] = nsrc[q * 3 + c]; p.nd[c] = ndst[q * 3 + c]; }
+    return p;
+}
+
+__device__ __forceinline__ float to_tensor1(int v) { return ((float)v / 255.f) * 2.f - 1.f; }
+
+__global__ void __launch_bounds__(256) k_pack_inputs(const uint8_t *__restrict__ frames, const int *__restrict__ frame_idx,
+                                                     const uint8_t *__restrict__ masks, const uint8_t *__restrict__ nsrc,
+                                                     const uint8_t *__restrict__ ndst, const long long *__restrict__ off,
+                                                     const int *__restrict__ rect, const int *__restrict__ bbox, float *__restrict__ x,
+                                                     float *__restrict__ y, int Hf, int Wf, int res) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= res * res) return;
+    const int oy = p / res, ox = p - oy * res;
+    const CropGeom g = crop_geometry(bbox + 4 * b, Hf, Wf);
+    const uint8_t *frame = frames + (size_t)frame_idx[b] * Hf * Wf * 3;
+    const uint8_t *mk = masks + off[b], *ns = nsrc + off[b] * 3, *nd = ndst + off[b] * 3;
+    const int rx0 = rect[4 * b], ry0 = rect[4 * b + 1], rw = rect[4 * b + 2], rh = rect[4 * b + 3];
+    int vm[3], vs[3], vd[3];
+    if (g.cw == 2 * res && g.ch == 2 * res) {                                  // exact halving -> 2x2 box average
+        const Px9 a = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, 2 * oy, 2 * ox);
+        const Px9 bq = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, 2 * oy, 2 * ox + 1);
+        const Px9 c = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, 2 * oy + 1, 2 * ox);
+        const Px9 d = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, 2 * oy + 1, 2 * ox + 1);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            vm[ch] = (a.m[ch] + bq.m[ch] + c.m[ch] + d.m[ch] + 2) >> 2;
+            vs[ch] = (a.ns[ch] + bq.ns[ch] + c.ns[ch] + d.ns[ch] + 2) >> 2;
+            vd[ch] = (a.nd[ch] + bq.nd[ch] + c.nd[ch] + d.nd[ch] + 2) >> 2;
+        }
+    } else {
+        const Tap tx = resize_tap(res, g.cw, ox, true), ty = resize_tap(res, g.ch, oy, false);
+        const Px9 p00 = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, ty.i0, tx.i0);
+        const Px9 p01 = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, ty.i0, tx.i1);
+        const Px9 p10 = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, ty.i1, tx.i0);
+        const Px9 p11 = pack_fetch(frame, mk, ns, nd, g, rx0, ry0, rw, rh, Hf, Wf, ty.i1, tx.i1);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            int s0 = p00.m[ch] * tx.a0 + p01.m[ch] * tx.a1, s1 = p10.m[ch] * tx.a0 + p11.m[ch] * tx.a1;
+            vm[ch] = min(max((((ty.a0 * (s0 >> 4)) >> 16) + ((ty.a1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+            s0 = p00.ns[ch] * tx.a0 + p01.ns[ch] * tx.a1; s1 = p10.ns[ch] * tx.a0 + p11.ns[ch] * tx.a1;
+            vs[ch] = min(max((((ty.a0 * (s0 >> 4)) >> 16) + ((ty.a1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+            s0 = p00.nd[ch] * tx.a0 + p01.nd[ch] * tx.a1; s1 = p10.nd[ch] * tx.a0 + p11.nd[ch] * tx.a1;
+            vd[ch] = min(max((((ty.a0 * (s0 >> 4)) >> 16) + ((ty.a1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+        }
+    }
+    if (vs[0] == 0 && vs[1] == 0 && vs[2] == 0) vm[0] = vm[1] = vm[2] = 255;      // trajectory_inference.py:219-220
+    const size_t plane = (size_t)res * res;
+    float *xb = x + (size_t)b * 6 * plane + p, *yb = y + (size_t)b * 3 * plane + p;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        xb[ch * plane] = to_tensor1(vm[ch]);                  // x_1: masked frame crop, channel order kept
+        xb[(3 + ch) * plane] = to_tensor1(vs[2 - ch]);        // x_2: source normals, [..., ::-1]
+        yb[ch * plane] = to_tensor1(vd[2 - ch]);              // y_tilde: destination normals, [..., ::-1]
+    }
+}
+
 }  // namespace fusg
 
 using namespace fusg;
+
+extern "C" int fusg_mask_bbox(const uint8_t *masks, const long long *mask_off, const int32_t *mask_rect, int32_t *bbox, int B, int max_mask_pixels,
+                              void *stream) {
+    if (!masks || !mask_off || !mask_rect || !bbox || B <= 0 || max_mask_pixels <= 0) return FUSG_ERR_ARG;
+    if (B > 65535) return FUSG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_bbox_init<<<(B + 255) / 256, 256, 0, st>>>(bbox, B);      // rows start as (INT_MAX, INT_MAX, -1, -1): an empty mask stays that way
+    int gx = (max_mask_pixels + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    k_mask_bbox<<<dim3(gx, B), 256, 0, st>>>(masks, mask_off, mask_rect, bbox);
+    fusg_count_launch(2);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_pack_vunet_inputs(const uint8_t *frames, const int32_t *frame_idx, const uint8_t *masks, const uint8_t *normal_src,
+                                      const uint8_t *normal_dst, const long long *off, const int32_t *rect, const int32_t *bbox, float *x,
+                                      float *y, int B, int Hf, int Wf, int res, void *stream) {
+    if (!frames || !frame_idx || !masks || !normal_src || !normal_dst || !off || !rect || !bbox || !x || !y) return FUSG_ERR_ARG;
+    if (B <= 0 || Hf <= 0 || Wf <= 0 || res <= 0) return FUSG_ERR_ARG;
+    if (B > 65535 || res > 4096) return FUSG_ERR_UNSUPPORTED;
+    k_pack_inputs<<<dim3((res * res + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(frames, frame_idx, masks, normal_src, normal_dst, off, rect, bbox,
+                                                                                      x, y, Hf, Wf, res);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
 
 extern "C" int fusg_resize_u8(const uint8_t *src, const long long *src_off, const int32_t *src_hw, uint8_t *dst, const long long *dst_off,
                               const int32_t *dst_hw, int B, int max_dst_pixels, void *stream) {

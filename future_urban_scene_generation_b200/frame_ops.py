@@ -165,3 +165,70 @@ def paste_back(img_output, net_image, crop_info, dst_sketch_mask):
     out = paste_back_batch(img_output[None], np.asarray(net_image)[None], [dst_sketch_mask], [crop_info], [0])
     img_output[...] = out[0].cpu().numpy()
     return img_output
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VUNet input packing: trajectory_inference.py:205-227 / :414-421 on the device
+# ---------------------------------------------------------------------------------------------------------------
+def pack_vunet_inputs_batch(frames, frame_index, src_sketch_masks, src_sketch_normals, dst_sketch_normals, rects=None, res=256):
+    """frames: (F, Hf, Wf, 3) uint8; per item b: `src_sketch_masks[b]` bool (True = background, as the reference holds it
+    at that point), `src_sketch_normals[b]` / `dst_sketch_normals[b]` uint8 (h, w, 3) -- full-frame arrays, or sub-rectangles
+    `rects[b] = (x, y, w, h)` outside of which the item is background.  Returns CUDA tensors
+    (x (B,6,res,res) f32, y_tilde (B,3,res,res) f32, bbox (B,4) int32) == the reference's `x`, `y_tilde` stacked."""
+    torch = _lib.require_cuda()
+    fr = _dev(torch, frames, torch.uint8)
+    if fr.dim() != 4 or fr.shape[3] != 3:
+        raise ValueError("pack_vunet_inputs_batch: frames must be (F, Hf, Wf, 3) uint8")
+    F, Hf, Wf = int(fr.shape[0]), int(fr.shape[1]), int(fr.shape[2])
+    B = len(frame_index)
+    if B == 0 or not (len(src_sketch_masks) == len(src_sketch_normals) == len(dst_sketch_normals) == B):
+        raise ValueError("pack_vunet_inputs_batch: one mask and two normal sketches per item")
+    if any(f < 0 or f >= F for f in frame_index):
+        raise ValueError("pack_vunet_inputs_batch: frame index out of range")
+    rect = np.zeros((B, 4), np.int32)
+    offs, fm, fs, fd, o = [], [], [], [], 0
+    for b in range(B):
+        m = torch.from_numpy(np.ascontiguousarray(src_sketch_masks[b])) if not isinstance(src_sketch_masks[b], torch.Tensor) else src_sketch_masks[b]
+        ns = torch.from_numpy(np.ascontiguousarray(src_sketch_normals[b])) if not isinstance(src_sketch_normals[b], torch.Tensor) else src_sketch_normals[b]
+        nd = torch.from_numpy(np.ascontiguousarray(dst_sketch_normals[b])) if not isinstance(dst_sketch_normals[b], torch.Tensor) else dst_sketch_normals[b]
+        h, w = int(m.shape[0]), int(m.shape[1])
+        if rects is None:
+            if (h, w) != (Hf, Wf):
+                raise ValueError(f"pack_vunet_inputs_batch: mask {b} is {(h, w)}, frame is {(Hf, Wf)}")
+            rect[b] = (0, 0, Wf, Hf)
+        else:
+            x, y, rw, rh = (int(v) for v in rects[b])
+            if (h, w) != (rh, rw):
+                raise ValueError(f"pack_vunet_inputs_batch: mask {b} is {(h, w)}, its rect says {(rh, rw)}")
+            rect[b] = (x, y, rw, rh)
+        if tuple(ns.shape) != (h, w, 3) or tuple(nd.shape) != (h, w, 3) or ns.dtype != torch.uint8 or nd.dtype != torch.uint8:
+            raise ValueError(f"pack_vunet_inputs_batch: normal sketches of item {b} must be uint8 {(h, w, 3)}")
+        offs.append(o)
+        fm.append((m == 0).to(torch.uint8).reshape(-1))          # vehicle = logical_not(src_sketch_mask)
+        fs.append(ns.reshape(-1))
+        fd.append(nd.reshape(-1))
+        o += h * w
+    dev = fr.device
+    masks, nsrc, ndst = torch.cat(fm).to(dev), torch.cat(fs).to(dev), torch.cat(fd).to(dev)
+    t_off = torch.tensor(offs, dtype=torch.int64, device=dev)
+    t_rect = torch.from_numpy(rect).to(dev)
+    t_fidx = torch.tensor(list(frame_index), dtype=torch.int32, device=dev)
+    bbox = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    mx = int((rect[:, 2].astype(np.int64) * rect[:, 3]).max())
+    _lib.check(L.fusg_mask_bbox(_lib.ptr(masks), _lib.ptr(t_off), _lib.ptr(t_rect), _lib.ptr(bbox), B, mx, _lib.stream_ptr(torch)), "fusg_mask_bbox")
+    if bool((bbox[:, 2] < 0).any()):
+        raise ValueError("pack_vunet_inputs_batch: empty vehicle mask (np.min of an empty array in the reference)")
+    x = torch.empty((B, 6, res, res), dtype=torch.float32, device=dev)
+    y = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+    _lib.check(L.fusg_pack_vunet_inputs(_lib.ptr(fr), _lib.ptr(t_fidx), _lib.ptr(masks), _lib.ptr(nsrc), _lib.ptr(ndst), _lib.ptr(t_off),
+                                        _lib.ptr(t_rect), _lib.ptr(bbox), _lib.ptr(x), _lib.ptr(y), B, Hf, Wf, res, _lib.stream_ptr(torch)),
+               "fusg_pack_vunet_inputs")
+    return x, y, bbox
+
+
+def pack_vunet_inputs(frame, src_sketch_mask, src_sketch_normal, dst_sketch_normal):
+    """One vehicle, reference-style: returns (x (1,6,256,256), y_tilde (1,3,256,256)) CUDA float tensors, the arguments of
+    `model_VUnet.forward_enc_up(x)` / `forward_dec_up(y_tilde)` at trajectory_inference.py:230-233."""
+    x, y, _ = pack_vunet_inputs_batch(np.asarray(frame)[None], [0], [src_sketch_mask], [src_sketch_normal], [dst_sketch_normal])
+    return x, y

@@ -154,3 +154,22 @@ def make_paste_case(idx: int, frame_hw=(1080, 1920), crop_res: int = 256):
     bbox = [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())]          # as warp_learn/models.py:330-332
     net_image = rng.integers(0, 256, (crop_res, crop_res, 3), dtype=np.uint8)
     return bbox, mask, net_image
+
+
+def make_pack_case(idx: int, frame_hw=(1080, 1920)):
+    """One synthetic vehicle for VUNet input packing (trajectory_inference.py:205-227): the reference's
+    `src_sketch_mask` (True = background), and source / destination normal sketches (uint8 RGB, black outside the
+    vehicle, with a few black holes inside so the background-fill rule fires inside the box too)."""
+    H, W = frame_hw
+    bbox, veh, _ = make_paste_case(idx, frame_hw)
+    rng = np.random.default_rng(80_000 + idx)
+    yy, xx = np.mgrid[0:H, 0:W]
+
+    def sketch(seed_shift):
+        r = np.random.default_rng(81_000 + idx * 7 + seed_shift)
+        n = np.stack([(xx * int(r.integers(1, 5)) + yy * int(r.integers(1, 5)) + int(r.integers(0, 255))) % 256 for _ in range(3)], -1).astype(np.uint8)
+        n[~veh] = 0
+        hx, hy = int(r.integers(bbox[0], bbox[2] + 1)), int(r.integers(bbox[1], bbox[3] + 1))
+        n[max(hy - 6, 0):hy + 6, max(hx - 9, 0):hx + 9] = 0
+        return n
+    return np.logical_not(veh), sketch(0), sketch(1)

@@ -204,6 +204,22 @@ size_t fusg_paste_workspace_bytes(int F, int Hf, int Wf);
 int fusg_paste_back(uint8_t *frames, const uint8_t *crops, const uint8_t *masks, const long long *mask_off, const int32_t *mask_rect,
                     const int32_t *info, void *workspace, size_t workspace_bytes, int B, int F, int Hf, int Wf, int S,
                     int max_mask_pixels, void *stream);
+/* ---- VUNet input packing (trajectory_inference.py:205-227, :414-421) -----------------
+ * Item b owns a rectangle rect[4b..] = (x, y, w, h) of frame frame_idx[b]; inside it: a uint8 vehicle mask (non-zero =
+ * vehicle, i.e. logical_not(src_sketch_mask)) at masks + off[b], and two uint8 RGB normal sketches at
+ * normal_* + 3*off[b]; outside it everything is background (0).  A full-frame item has rect (0, 0, Wf, Hf).
+ * fusg_mask_bbox: bbox[b] = (x_min, y_min, x_max, y_max) of the vehicle pixels in frame coordinates
+ *   (np.nonzero + min/max at trajectory_inference.py:207-209); an empty mask gives (INT_MAX, INT_MAX, -1, -1). */
+int fusg_mask_bbox(const uint8_t *masks, const long long *mask_off, const int32_t *mask_rect, int32_t *bbox, int B, int max_mask_pixels,
+                   void *stream);
+/* x [B,6,res,res] f32 = cat(to_tensor(resize(square_crop(mask * frame)) with background -> 255),
+ *                           to_tensor(resize(square_crop(normal_src))[..., ::-1]));
+ * y [B,3,res,res] f32 = to_tensor(resize(square_crop(normal_dst))[..., ::-1])
+ * with square_crop = utils/crop_utils.py:4-52 on bbox[b], resize = cv2.resize(..., (res, res)), background = pixels whose
+ * resized source normal is (0,0,0), to_tensor = utils/misc_utils.py:35-50.  frames [F,Hf,Wf,3] u8. */
+int fusg_pack_vunet_inputs(const uint8_t *frames, const int32_t *frame_idx, const uint8_t *masks, const uint8_t *normal_src,
+                           const uint8_t *normal_dst, const long long *off, const int32_t *rect, const int32_t *bbox, float *x, float *y,
+                           int B, int Hf, int Wf, int res, void *stream);
 /* NHWC elementwise ELU (activation dtype) over n elements. */
 int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
 

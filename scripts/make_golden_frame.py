@@ -4,6 +4,8 @@ tests/golden/frame_golden.json
   * resize: sha1 of cv2.resize(src, dsize) for seeded random uint8 images over a list of (src, dst) size pairs
     (incl. identity, exact halving, 256 -> vehicle-sized, strong up/down-scaling, tiny images)
   * crop_info: utils/crop_utils.py square_crop_from_bbox geometry for synthetic boxes (synth.make_paste_case)
+  * pack: sha1 of x / y_tilde from the reference lines trajectory_inference.py:205-227 (cv2.resize, the reference's
+    square_crop_from_bbox and to_tensor, torch cat / interpolate) on synthetic vehicles (synth.make_pack_case)
   * paste: sha1 of the frame after the five reference lines (trajectory_inference.py:236-250) executed with cv2.resize
     for a sequence of vehicles pasted into one frame in order
 
@@ -59,8 +61,31 @@ for idx in range(24):
     assert np.array_equal(img_cv, img_or), idx
     paste_cases.append({"idx": idx, "sha1_after": sha(img_cv)})
 
-out = {"cv2": cv2.__version__, "resize": resize_cases, "frame_hw": list(FRAME_HW), "frame_seed": 123, "crop_info": info_cases,
+# ---- VUNet input packing: the reference lines (trajectory_inference.py:205-227) with the reference's own helpers
+import torch
+import torch.nn.functional as F
+from utils.misc_utils import to_tensor
+pack_cases = []
+for idx in range(16):
+    src_sketch_mask, src_sketch_normal, dst_sketch_normal = synth.make_pack_case(idx, FRAME_HW)
+    smb = np.bitwise_not(src_sketch_mask)[..., np.newaxis] * frame
+    ys, xs = np.nonzero(np.logical_not(src_sketch_mask))
+    bb = [np.min(xs), np.min(ys), np.max(xs), np.max(ys)]
+    smb = square_crop_from_bbox(smb, bb)[0]
+    snb = square_crop_from_bbox(src_sketch_normal, bb)[0]
+    dnb = square_crop_from_bbox(dst_sketch_normal, bb)[0]
+    smb, snb, dnb = cv2.resize(smb, (256, 256)), cv2.resize(snb, (256, 256)), cv2.resize(dnb, (256, 256))
+    smb[np.all(snb == 0, axis=-1)] = 255
+    x_1 = F.interpolate(to_tensor(smb).unsqueeze(0), 256)
+    x_2 = F.interpolate(to_tensor(snb[..., ::-1].copy()).unsqueeze(0), 256)
+    x = torch.cat([x_1, x_2], 1)[0].numpy()
+    y = to_tensor(dnb[..., ::-1].copy()).numpy()
+    ox, oy, obb = FO.pack_vunet_inputs(frame, src_sketch_mask, src_sketch_normal, dst_sketch_normal)
+    assert np.array_equal(ox.view(np.uint32), x.view(np.uint32)) and np.array_equal(oy.view(np.uint32), y.view(np.uint32)), idx
+    pack_cases.append({"idx": idx, "bbox": [int(v) for v in bb], "sha1_x": sha(x.astype(np.float32)), "sha1_y": sha(y.astype(np.float32))})
+
+out = {"cv2": cv2.__version__, "pack": pack_cases, "resize": resize_cases, "frame_hw": list(FRAME_HW), "frame_seed": 123, "crop_info": info_cases,
        "paste": paste_cases}
 path = os.path.join(ROOT, "tests", "golden", "frame_golden.json")
 json.dump(out, open(path, "w"), indent=0)
-print("wrote", path, len(resize_cases), "resize cases,", len(paste_cases), "paste steps; oracle == cv2 on all")
+print("wrote", path, len(resize_cases), "resize cases,", len(paste_cases), "paste steps,", len(pack_cases), "pack cases; oracle == cv2/reference on all")

@@ -199,3 +199,7 @@ def test_frame_oracle_matches_cv2_goldens():
             assert list(info[k]) == ci[k], (ci["idx"], k)
         FO.paste_back(img, net, info, mask)
         assert sha(img) == p["sha1_after"], ci["idx"]
+    frame = np.random.default_rng(gold["frame_seed"]).integers(0, 256, (Hf, Wf, 3), dtype=np.uint8)
+    for c in gold["pack"][:8]:
+        x, y, bbox = FO.pack_vunet_inputs(frame, *synth.make_pack_case(c["idx"], (Hf, Wf)))
+        assert bbox == c["bbox"] and sha(x) == c["sha1_x"] and sha(y) == c["sha1_y"], c["idx"]

@@ -104,3 +104,50 @@ def test_paste_back_rejects_what_the_reference_rejects(cuda):
     bad = {"crop_xy_min": (40, 0), "pad_xy_before": (0, 0), "pad_xy_after": (0, 0), "crop_size_orig": (30, 30)}   # 40 + 30 > 64
     with pytest.raises(ValueError):
         paste_back_batch(frame, crop, [mask], [bad], [0])
+
+
+def test_pack_vunet_inputs_matches_reference_goldens(cuda):
+    """x / y_tilde from the device == the reference lines (cv2 + the reference's helpers) recorded in the goldens, bit for
+    bit; full-frame inputs (reference form) and bbox rectangles give the same tensors."""
+    from future_urban_scene_generation_b200.frame_ops import pack_vunet_inputs_batch, pack_vunet_inputs
+    Hf, Wf = GOLD["frame_hw"]
+    frame = np.random.default_rng(GOLD["frame_seed"]).integers(0, 256, (Hf, Wf, 3), dtype=np.uint8)
+    masks, ns, nd, rects, rm, rns, rnd = [], [], [], [], [], [], []
+    for c in GOLD["pack"]:
+        m, a, b = synth.make_pack_case(c["idx"], (Hf, Wf))
+        masks.append(m); ns.append(a); nd.append(b)
+        x0, y0, x1, y1 = c["bbox"]
+        rects.append((x0, y0, x1 - x0 + 1, y1 - y0 + 1))
+        rm.append(m[y0:y1 + 1, x0:x1 + 1]); rns.append(a[y0:y1 + 1, x0:x1 + 1]); rnd.append(b[y0:y1 + 1, x0:x1 + 1])
+    n = len(masks)
+    x, y, bbox = pack_vunet_inputs_batch(frame[None], [0] * n, masks, ns, nd)
+    xr, yr, bboxr = pack_vunet_inputs_batch(frame[None], [0] * n, rm, rns, rnd, rects=rects)
+    assert cuda.equal(x, xr) and cuda.equal(y, yr) and cuda.equal(bbox, bboxr)
+    for i, c in enumerate(GOLD["pack"]):
+        assert bbox[i].tolist() == c["bbox"]
+        assert sha(x[i].cpu().numpy()) == c["sha1_x"], c["idx"]
+        assert sha(y[i].cpu().numpy()) == c["sha1_y"], c["idx"]
+    x1, y1 = pack_vunet_inputs(frame, masks[3], ns[3], nd[3])
+    assert x1.shape == (1, 6, 256, 256) and y1.shape == (1, 3, 256, 256) and cuda.equal(x1[0], x[3]) and cuda.equal(y1[0], y[3])
+
+
+def test_pack_vunet_inputs_feeds_the_model_like_host_tensors(cuda):
+    """The packed device tensors are what the reference would hand to the VUNet: same completed crop as from the
+    oracle's host-side packing."""
+    from argparse import Namespace
+    from future_urban_scene_generation_b200.frame_ops import pack_vunet_inputs_batch
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from oracle import frame_oracle as FO
+    torch = cuda
+    Hf, Wf = 300, 500
+    frame = np.random.default_rng(9).integers(0, 256, (Hf, Wf, 3), dtype=np.uint8)
+    cases = [synth.make_pack_case(200 + i, (Hf, Wf)) for i in range(2)]
+    x, y, _ = pack_vunet_inputs_batch(frame[None], [0, 0], [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases])
+    ref = [FO.pack_vunet_inputs(frame, *c) for c in cases]
+    assert np.array_equal(x.cpu().numpy(), np.stack([r[0] for r in ref])) and np.array_equal(y.cpu().numpy(), np.stack([r[1] for r in ref]))
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).cuda().eval()
+    torch.manual_seed(4)
+    a = m(y, x)[0]
+    torch.manual_seed(4)
+    b = m(torch.from_numpy(np.stack([r[1] for r in ref])).cuda(), torch.from_numpy(np.stack([r[0] for r in ref])).cuda())[0]
+    assert torch.equal(a, b)
