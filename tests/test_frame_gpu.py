@@ -151,3 +151,47 @@ def test_pack_vunet_inputs_feeds_the_model_like_host_tensors(cuda):
     torch.manual_seed(4)
     b = m(torch.from_numpy(np.stack([r[1] for r in ref])).cuda(), torch.from_numpy(np.stack([r[0] for r in ref])).cuda())[0]
     assert torch.equal(a, b)
+
+
+def test_clip_chain_pack_vunet_paste_matches_oracle_chain(cuda):
+    """The widened path end to end on the device -- pack inputs -> VUNet -> to_image -> paste back into the frames --
+    against the same chain built from the CPU oracles (fp32 VUNet): the pasted pixels agree within the bf16 image
+    tolerance (2 grey levels before the resize), everything outside the vehicle masks is untouched."""
+    from argparse import Namespace
+    from future_urban_scene_generation_b200.frame_ops import pack_vunet_inputs_batch, paste_back_batch
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from future_urban_scene_generation_b200.warp_learn.planes_utils import to_image_batch, to_image
+    from oracle import frame_oracle as FO, vunet_oracle as VO
+    torch = cuda
+    Hf, Wf, F, V = 240, 400, 2, 2
+    frames = np.random.default_rng(21).integers(0, 256, (F, Hf, Wf, 3), dtype=np.uint8)
+    sd = VO.make_state_dict(0)
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    cases, fidx = [], []
+    for f in range(F):
+        for v in range(V):
+            cases.append(synth.make_pack_case(300 + f * V + v, (Hf, Wf)))
+            fidx.append(f)
+    # device chain
+    x, y, bbox = pack_vunet_inputs_batch(frames, fidx, [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases])
+    torch.manual_seed(8)
+    crops = to_image_batch(m(y, x)[0])
+    infos = [FO.square_crop_info((Hf, Wf), bb) for bb in bbox.tolist()]          # crop_info of get_icn_inputs (same bbox rule)
+    veh = [np.logical_not(c[0]) for c in cases]                                    # dst_sketch_mask after :176 = vehicle pixels
+    out = paste_back_batch(frames.copy(), crops, veh, infos, fidx).cpu().numpy()
+    # oracle chain
+    ref = frames.copy()
+    packed = [FO.pack_vunet_inputs(frames[f], *c) for f, c in zip(fidx, cases)]
+    torch.manual_seed(8)
+    with torch.no_grad():
+        xt = VO.forward(sd, torch.from_numpy(np.stack([p[1] for p in packed])), torch.from_numpy(np.stack([p[0] for p in packed])))[0]
+    for i, f in enumerate(fidx):
+        FO.paste_back(ref[f], to_image(xt[i], from_LAB=False), infos[i], veh[i])
+    union = np.zeros((F, Hf, Wf), bool)
+    for i, f in enumerate(fidx):
+        union[f] |= veh[i]
+    assert np.array_equal(out[~union], frames[~union])                             # untouched outside the masks
+    diff = np.abs(out.astype(int) - ref.astype(int))
+    assert diff.max() <= 3 and (diff > 1).mean() < 0.01, (diff.max(), (diff > 1).mean())
