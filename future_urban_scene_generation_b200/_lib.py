@@ -46,6 +46,7 @@ def _load():
         "fusg_resize_u8": ([vp] * 6 + [i, i, vp], i),
         "fusg_paste_workspace_bytes": ([i, i, i], sz),
         "fusg_paste_back": ([vp] * 7 + [sz, i, i, i, i, i, i, vp], i),
+        "fusg_u8_to_vunet_inputs": ([vp] * 5 + [i, i, vp], i),
         "fusg_mask_bbox": ([vp] * 4 + [i, i, vp], i),
         "fusg_pack_vunet_inputs": ([vp] * 10 + [i, i, i, i, vp], i),
     }

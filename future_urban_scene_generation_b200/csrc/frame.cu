@@ -248,9 +248,34 @@ __global__ void __launch_bounds__(256) k_pack_inputs(const uint8_t *__restrict__
     }
 }
 
+// to_tensor + channel flip + concat of the three already-resized uint8 images of trajectory_inference.py:215-227
+__global__ void __launch_bounds__(256) k_u8_to_inputs(const uint8_t *__restrict__ m, const uint8_t *__restrict__ ns, const uint8_t *__restrict__ nd,
+                                                      float *__restrict__ x, float *__restrict__ y, int res) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= res * res) return;
+    const size_t plane = (size_t)res * res, q = ((size_t)b * plane + p) * 3;
+    float *xb = x + (size_t)b * 6 * plane + p, *yb = y + (size_t)b * 3 * plane + p;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        xb[ch * plane] = to_tensor1(m[q + ch]);
+        xb[(3 + ch) * plane] = to_tensor1(ns[q + 2 - ch]);
+        yb[ch * plane] = to_tensor1(nd[q + 2 - ch]);
+    }
+}
+
 }  // namespace fusg
 
 using namespace fusg;
+
+extern "C" int fusg_u8_to_vunet_inputs(const uint8_t *mask_bbox, const uint8_t *normal_src, const uint8_t *normal_dst, float *x, float *y, int B,
+                                       int res, void *stream) {
+    if (!mask_bbox || !normal_src || !normal_dst || !x || !y || B <= 0 || res <= 0) return FUSG_ERR_ARG;
+    if (B > 65535 || res > 4096) return FUSG_ERR_UNSUPPORTED;
+    k_u8_to_inputs<<<dim3((res * res + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(mask_bbox, normal_src, normal_dst, x, y, res);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
 
 extern "C" int fusg_mask_bbox(const uint8_t *masks, const long long *mask_off, const int32_t *mask_rect, int32_t *bbox, int B, int max_mask_pixels,
                               void *stream) {

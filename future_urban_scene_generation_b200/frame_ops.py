@@ -232,3 +232,18 @@ def pack_vunet_inputs(frame, src_sketch_mask, src_sketch_normal, dst_sketch_norm
     `model_VUnet.forward_enc_up(x)` / `forward_dec_up(y_tilde)` at trajectory_inference.py:230-233."""
     x, y, _ = pack_vunet_inputs_batch(np.asarray(frame)[None], [0], [src_sketch_mask], [src_sketch_normal], [dst_sketch_normal])
     return x, y
+
+
+def u8_to_vunet_inputs(mask_bbox_u8, normal_src_u8, normal_dst_u8):
+    """The three resized uint8 images of trajectory_inference.py:215-220, batched (B,res,res,3) CUDA tensors ->
+    (x (B,6,res,res), y_tilde (B,3,res,res)) fp32 on the device == lines :221-225 (to_tensor, [..., ::-1], cat)."""
+    torch = _lib.require_cuda()
+    B, res = int(mask_bbox_u8.shape[0]), int(mask_bbox_u8.shape[1])
+    for t in (mask_bbox_u8, normal_src_u8, normal_dst_u8):
+        if tuple(t.shape) != (B, res, res, 3) or t.dtype != torch.uint8:
+            raise ValueError("u8_to_vunet_inputs: expected three (B, res, res, 3) uint8 tensors")
+    x = torch.empty((B, 6, res, res), dtype=torch.float32, device=mask_bbox_u8.device)
+    y = torch.empty((B, 3, res, res), dtype=torch.float32, device=mask_bbox_u8.device)
+    _lib.check(_lib.lib().fusg_u8_to_vunet_inputs(_lib.ptr(mask_bbox_u8), _lib.ptr(normal_src_u8), _lib.ptr(normal_dst_u8), _lib.ptr(x), _lib.ptr(y),
+                                                  B, res, _lib.stream_ptr(torch)), "fusg_u8_to_vunet_inputs")
+    return x, y

@@ -18,6 +18,7 @@ import threading
 import torch
 
 from . import _lib
+from .frame_ops import u8_to_vunet_inputs
 from .warp_learn.batch import warp_batch
 from .warp_learn.planes_utils import to_image_batch
 
@@ -71,7 +72,11 @@ class NovelViewPipeline:
         self.side_stream.wait_stream(cur)
         with torch.cuda.stream(self.side_stream):
             res = warp_batch(*(inp[k] for k in self.WARP_KEYS), device=self.dev)
-        x_tilde, _, _ = self.model(inp["y"], inp["x"])
+        if "x" in inp:
+            x, y = inp["x"], inp["y"]
+        else:                                   # uint8 form: to_tensor / flip / concat on the device (frame_ops.u8_to_vunet_inputs)
+            x, y = u8_to_vunet_inputs(inp["x_mask_u8"], inp["x_normal_u8"], inp["y_normal_u8"])
+        x_tilde, _, _ = self.model(y, x)
         crops = to_image_batch(x_tilde)
         cur.wait_stream(self.side_stream)
         for t in (res.warped, res.plane_j, res.vis):
@@ -154,7 +159,8 @@ class NovelViewPipeline:
 
     # ------------------------------------------------------------------ public API
     def submit(self, batch: dict, resident: bool = False) -> int:
-        """batch: pinned host tensors `x` (B,6,256,256) f32, `y` (B,3,256,256) f32 and the warp inputs
+        """batch: pinned host tensors `x` (B,6,256,256) f32, `y` (B,3,256,256) f32 -- or, 4x smaller, the three uint8
+        images they are made of, `x_mask_u8`, `x_normal_u8`, `y_normal_u8` (B,256,256,3), see frame_ops -- and the warp inputs
         `src` (B,256,256,3) u8, `src_kp`/`dst_kp` (B,12,2) i32, `K` (B,3,3), `E_src`/`E_dst` (B,3,4), `kp3d` (B,12,3) f64.
         resident=True skips the host copies (inputs / noise already in the slot; outputs stay on the device)."""
         ticket = self.n

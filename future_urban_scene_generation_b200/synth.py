@@ -130,6 +130,21 @@ def make_vunet_inputs(start: int, count: int, res: int = 256):
     return np.stack(xs).astype(np.float32), np.stack(ys).astype(np.float32)
 
 
+def make_vunet_inputs_u8(start: int, count: int, res: int = 256):
+    """The same data as `make_vunet_inputs`, as the three uint8 images the reference holds before `to_tensor`
+    (trajectory_inference.py:215-220): (src_sketch_mask_bbox, src_sketch_normal_bbox, dst_sketch_normal_bbox), each
+    (B,res,res,3) -- `to_tensor` + `[..., ::-1]` + `cat` of them is exactly `make_vunet_inputs(start, count)`."""
+    m, ns, nd = [], [], []
+    for i in range(count):
+        rng = np.random.default_rng(55_000 + start + i)
+        x8 = rng.integers(0, 256, (6, res, res), dtype=np.uint8)
+        y8 = rng.integers(0, 256, (3, res, res), dtype=np.uint8)
+        m.append(np.transpose(x8[0:3], (1, 2, 0)))
+        ns.append(np.transpose(x8[3:6][::-1], (1, 2, 0)))
+        nd.append(np.transpose(y8[::-1], (1, 2, 0)))
+    return np.ascontiguousarray(np.stack(m)), np.ascontiguousarray(np.stack(ns)), np.ascontiguousarray(np.stack(nd))
+
+
 def make_paste_case(idx: int, frame_hw=(1080, 1920), crop_res: int = 256):
     """One synthetic vehicle for the paste-back step (trajectory_inference.py:236-250): a bounding box (every fourth one
     hangs over a frame border so the square crop needs padding), the full-frame vehicle mask `dst_sketch_mask`

@@ -220,6 +220,11 @@ int fusg_mask_bbox(const uint8_t *masks, const long long *mask_off, const int32_
 int fusg_pack_vunet_inputs(const uint8_t *frames, const int32_t *frame_idx, const uint8_t *masks, const uint8_t *normal_src,
                            const uint8_t *normal_dst, const long long *off, const int32_t *rect, const int32_t *bbox, float *x, float *y,
                            int B, int Hf, int Wf, int res, void *stream);
+/* The tail of the same assembly when the three 256x256 uint8 images already exist (trajectory_inference.py:221-225):
+ *   x = cat(to_tensor(mask_bbox), to_tensor(normal_src[..., ::-1])), y = to_tensor(normal_dst[..., ::-1]);
+ * inputs [B,res,res,3] u8 -> x [B,6,res,res] f32, y [B,3,res,res] f32.  Lets a host ship 9 bytes per pixel instead of 36. */
+int fusg_u8_to_vunet_inputs(const uint8_t *mask_bbox, const uint8_t *normal_src, const uint8_t *normal_dst, float *x, float *y, int B,
+                            int res, void *stream);
 /* NHWC elementwise ELU (activation dtype) over n elements. */
 int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
 

@@ -97,3 +97,32 @@ def test_noise_prefetch_keeps_generator_semantics(cuda):
         assert torch.equal(x, y)
     assert torch.equal(sa, sb)                     # the global generator ends in the same state
     assert not torch.equal(a[0], a[1])             # different noise every step
+
+
+def test_pipeline_uint8_inputs_equal_float_inputs(cuda):
+    """Shipping the three uint8 images (9 B/pixel) and doing to_tensor / flip / concat on the device gives the same
+    completed crops as shipping the float tensors the reference builds on the host (36 B/pixel)."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.frame_ops import u8_to_vunet_inputs
+    from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    B = 2
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).cuda().eval()
+    wb = synth.make_warp_batch(7, B)
+    xs, ys = synth.make_vunet_inputs(7, B)
+    mk, ns, nd = synth.make_vunet_inputs_u8(7, B)
+    x, y = u8_to_vunet_inputs(torch.from_numpy(mk).cuda(), torch.from_numpy(ns).cuda(), torch.from_numpy(nd).cuda())
+    assert torch.equal(x.cpu(), torch.from_numpy(xs)) and torch.equal(y.cpu(), torch.from_numpy(ys))
+    base = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
+    hf = dict(base, x=torch.from_numpy(xs).pin_memory(), y=torch.from_numpy(ys).pin_memory())
+    hu = dict(base, x_mask_u8=torch.from_numpy(mk).pin_memory(), x_normal_u8=torch.from_numpy(ns).pin_memory(),
+              y_normal_u8=torch.from_numpy(nd).pin_memory())
+    outs = []
+    for host in (hf, hu):
+        pipe = NovelViewPipeline(m, depth=2)
+        torch.manual_seed(2)
+        r = [pipe.result(pipe.submit(host))["crops"].clone() for _ in range(3)]
+        outs.append(r)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
