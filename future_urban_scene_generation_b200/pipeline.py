@@ -40,6 +40,7 @@ class _Slot:
         self.stream = None       # this slot's compute stream: the small-grid tail layers of one batch overlap the
                                  # full-grid layers of the next batch in flight
         self.prefetch = None     # (thread, state_before, result holder) of a background noise draw into noise_stage
+        self.crops_all = None    # multi-GPU: the all-gathered completed crops of the last step, on the device
 
 
 class NovelViewPipeline:
@@ -197,8 +198,12 @@ class NovelViewPipeline:
                 slot.dev_out = self._compute(slot.inp)
                 eng.noise_provider = prev
             dev_out = dict(slot.dev_out)
+            gathered = None
             if self.gather_fn is not None:
-                dev_out["crops"] = self.gather_fn(dev_out["crops"])
+                # the exchange step: every rank gets all completed crops ON THE DEVICE (for a device-side paste-back,
+                # frame_ops.paste_back_batch); the host copy below stays this rank's own shard
+                gathered = self.gather_fn(dev_out["crops"])
+                slot.crops_all = gathered
             computed = torch.cuda.Event()
             computed.record(slot.stream)
         if resident:
@@ -231,7 +236,11 @@ class NovelViewPipeline:
         self.slots[ticket % self.depth].done.synchronize()
 
     def device_outputs(self, ticket: int) -> dict:
-        return self.slots[ticket % self.depth].dev_out
+        sl = self.slots[ticket % self.depth]
+        out = dict(sl.dev_out)
+        if sl.crops_all is not None:
+            out["crops_all"] = sl.crops_all
+        return out
 
     def launches_per_step(self) -> int:
         return self.slots[0].launches
