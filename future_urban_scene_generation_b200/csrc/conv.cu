@@ -1108,8 +1108,8 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     // at least ~4 tiles per SM; halves the weight traffic per output pixel
     static const int msub_max = getenv("FUSG_MSUB1") ? 1 : 2;
     const long long rows = (long long)d.B * Ho * Wo;
-    // (only for 3x3 layers: a 1x1 layer has one or two k-blocks per tile and is bound by its output writes)
-    p.msub = (msub_max == 2 && d.ksize == 3 && rows / 256 * p.n_tiles >= 4LL * num_sms && rows % 256 == 0) ? 2 : 1;
+    // (1x1 layers too: half as many barrier round trips per output row -- 0.51 -> 0.46 ms on the 6->128 NiN)
+    p.msub = (msub_max == 2 && rows / 256 * p.n_tiles >= 4LL * num_sms && rows % 256 == 0) ? 2 : 1;
     const int trows = TC_BLOCK_M * p.msub;
     p.Wt = Wo < 128 ? Wo : 128;
     p.Ht = (trows / p.Wt) < Ho ? (trows / p.Wt) : Ho;
