@@ -718,8 +718,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const int row = q * 32 + lane;                         // tile row == TMEM lane
         int nparts = TC_EPI_WARPS / 4;
         while (nparts > 1 && p.block_n % (16 * nparts)) nparts >>= 1;
-        const int ncols = part < nparts ? p.block_n / nparts : 0;
-        const int c_begin = part * ncols;
+        // narrow layers (one 16-column chunk): the two warps of a lane quadrant split the two sub-tiles instead of the columns
+        const bool sub_split = TC_EPI_WARPS == 8 && nparts == 1 && p.msub == 2 && p.ksplit == 1;
+        const int ncols = sub_split ? p.block_n : (part < nparts ? p.block_n / nparts : 0);
+        const int c_begin = sub_split ? 0 : part * ncols;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x / p.ksplit; tile < total_tiles; tile += gridDim.x / p.ksplit) {
@@ -829,6 +831,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             if (p.fast_epi && p.fe.res && ncols > 0) {
                 // the residual rows this thread will add: pull them into L2 while the MMAs of this tile run
                 for (int sub = 0; sub < p.msub; ++sub) {
+                    if (sub_split && sub != part) continue;
                     const int trow = row + sub * TC_BLOCK_M;
                     const int wt = trow & (p.Wt - 1), ht = (trow >> p.wt_shift) & (p.Ht - 1), bt = trow >> (p.wt_shift + p.ht_shift);
                     const int b = tb * p.Bt + bt;
@@ -842,6 +845,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             for (int sub = 0; sub < p.msub && ncols > 0; ++sub) {
+                if (sub_split && sub != part) continue;
                 const int trow = row + sub * TC_BLOCK_M;               // row of the CTA tile
                 const int wt = trow & (p.Wt - 1), ht = (trow >> p.wt_shift) & (p.Ht - 1), bt = trow >> (p.wt_shift + p.ht_shift);
                 const int ox = tx * p.Wt + wt, oy = ty * p.Ht + ht, b = tb * p.Bt + bt;
