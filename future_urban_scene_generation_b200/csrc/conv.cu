@@ -294,6 +294,60 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster share one M = 256 MMA; each holds its own 128 A rows
+// and HALF of the weight rows; TMA loads of both CTAs signal the leader's mbarrier; the leader's commit arrives on the
+// barriers of both CTAs (multicast).  Checked in isolation by scripts/umma_2cta_probe.cu.
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void *dst, const CUtensorMap *tm, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            s_addr(dst)),
+        "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *tm, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s_addr(dst)),
+        "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_addr(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// wait on a barrier of this CTA that a PEER CTA arrives on (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
 // thread-block cluster helpers (split-K layers)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -452,6 +506,7 @@ struct alignas(64) ConvTcParams {
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
     int halo;                       // 1: sliding-window A tiles -- one TMA load of an image-row segment + 2 halo pixels serves the
                                     //    three horizontal taps (3x3, stride 1, Wt = 128, one image row per 128-row sub-tile)
+    int pair;                       // halo mode on CTA pairs (cta_group::2): M = 256 per MMA, each CTA holds half of the weight rows
     int pdl;                        // launched with programmatic stream serialization (griddepcontrol in the kernel)
     int ksplit;                     // > 1: thread-block cluster of `ksplit` CTAs per tile, each reducing 1/ksplit of K (few-tile layers)
     int kb_local;                   // k-blocks per CTA = num_kblocks / ksplit
@@ -524,10 +579,13 @@ __device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uin
 // The A descriptor of tap kx simply starts kx rows (kx * 128 bytes) into the buffer: the 128-byte swizzle is a
 // function of the absolute shared-memory address, so a start address that is 128- but not 1024-byte aligned
 // addresses the same swizzled rows (checked on the device by scripts/umma_shift_probe.cu).
+template <bool PAIR>
 __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA, uint8_t *sB, uint64_t *full_bar, uint64_t *empty_bar,
                                               uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *w_bar, uint32_t tmem_base, int total_tiles) {
     const uint32_t block_n = (uint32_t)p.block_n;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    constexpr bool pair = PAIR;
+    if (pair && cluster_ctarank() != 0) return;                        // the leader CTA issues for the pair
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)((pair ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2u << 61);
     const int stages = p.stages, cpt = p.chunks0 + p.chunks1, nst = 3 * cpt;
     const uint32_t b_kb16 = (uint32_t)p.b_bytes >> 4;
@@ -539,8 +597,10 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
     uint32_t phase = 0;
     uint32_t acc = 0, acc_phase = 0;
     if (resident) mbar_wait(w_bar, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    const int tstep = pair ? (int)gridDim.x >> 1 : (int)gridDim.x, tcount = pair ? total_tiles >> 1 : total_tiles;
+    for (int tile = pair ? (int)blockIdx.x >> 1 : (int)blockIdx.x; tile < tcount; tile += tstep) {
+        if constexpr (PAIR) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int st = 0; st < nst; ++st) {
@@ -560,12 +620,18 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t a_desc = desc_hi | (uint64_t)(a16 + (uint32_t)sub * (TC_HALO_BYTES >> 4) + (uint32_t)kx * 8u + (uint32_t)ks * 2u);
                             const uint64_t b_desc = desc_hi | (uint64_t)(b16 + (uint32_t)kx * b_step + (uint32_t)ks * 2u);
-                            umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st | kx | ks) != 0 ? 1u : 0u);
+                            if constexpr (PAIR) umma_bf16_2cta(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st | kx | ks) != 0 ? 1u : 0u);
+                            else umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st | kx | ks) != 0 ? 1u : 0u);
                         }
                     }
                 }
-                umma_commit(&empty_bar[stage]);
-                if (st == nst - 1) umma_commit(&tfull_bar[acc]);
+                if constexpr (PAIR) {
+                    umma_commit_2cta(&empty_bar[stage]);
+                    if (st == nst - 1) umma_commit_2cta(&tfull_bar[acc]);
+                } else {
+                    umma_commit(&empty_bar[stage]);
+                    if (st == nst - 1) umma_commit(&tfull_bar[acc]);
+                }
             }
             __syncwarp();
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -575,6 +641,9 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
     }
 }
 
+// PAIR = true is the cta_group::2 instantiation: it must be launched as clusters of two CTAs (the driver rejects a
+// kernel that contains 2-CTA tcgen05 instructions otherwise), so the single-CTA paths keep their own instantiation.
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (swizzle atoms)
@@ -600,14 +669,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         if (d.in1) tma_prefetch_desc(&p.tmA1);
         tma_prefetch_desc(&p.tmW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 1) {
+        if constexpr (PAIR) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
+        else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
     for (int i = threadIdx.x; i < p.d.cout_pad; i += TC_THREADS) s_bias[i] = p.d.bias[i];
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // programmatic dependent launch: everything above (barriers, TMEM, tensor-map prefetch, bias) touched nothing the
@@ -644,7 +717,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             uint32_t phase = 0;
             if (p.halo) {
                 const uint32_t tx_bytes = 2u * (uint32_t)(TC_HALO_ROWS * 128) + (p.w_resident ? 0u : 3u * (uint32_t)p.b_bytes);
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                constexpr bool pair = PAIR;
+                const int rank = pair ? (int)cluster_ctarank() : 0;
+                const int tstep = pair ? (int)gridDim.x >> 1 : (int)gridDim.x, tcount = pair ? total_tiles >> 1 : total_tiles;
+                for (int it = pair ? (int)blockIdx.x >> 1 : (int)blockIdx.x; it < tcount; it += tstep) {
+                    const int tile = pair ? 2 * it + rank : it;        // the two CTAs of a pair take neighbouring M tiles
                     const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                     const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
                     const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt, n0 = nt * p.block_n;
@@ -652,16 +729,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         for (int c = 0; c < cpt; ++c) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (elect_one()) {
-                                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                                 uint8_t *a_dst = sA + (size_t)stage * 2 * TC_HALO_BYTES;
+                                uint8_t *b_dst = sB + (size_t)stage * 3 * p.b_bytes;
+                                if constexpr (PAIR) {
+                                    // both CTAs' bytes land on the leader's barrier; only the leader arrives on it
+                                    const uint32_t lead = dsmem_addr(s_addr(&full_bar[stage]), 0);
+                                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_bytes);
+                                    for (int sub = 0; sub < 2; ++sub) {
+                                        if (c < p.chunks0) tma_load_4d_2sm(a_dst + sub * TC_HALO_BYTES, &p.tmA0, lead, c * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
+                                        else tma_load_4d_2sm(a_dst + sub * TC_HALO_BYTES, &p.tmA1, lead, (c - p.chunks0) * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
+                                    }
+                                    for (int kx = 0; kx < 3; ++kx)       // this CTA's half of the weight rows
+                                        tma_load_2d_2sm(b_dst + (size_t)kx * p.b_bytes, &p.tmW, lead, ((ky * 3 + kx) * cpt + c) * 64, n0 + rank * (p.block_n >> 1));
+                                } else {
+                                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                                 for (int sub = 0; sub < 2; ++sub) {      // sub-tile = image row oy0 + sub, pixels ox0-1 .. ox0+128
                                     if (c < p.chunks0) tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA0, &full_bar[stage], c * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
                                     else tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA1, &full_bar[stage], (c - p.chunks0) * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
                                 }
                                 if (!p.w_resident) {
-                                    uint8_t *b_dst = sB + (size_t)stage * 3 * p.b_bytes;
                                     for (int kx = 0; kx < 3; ++kx)
                                         tma_load_2d(b_dst + (size_t)kx * p.b_bytes, &p.tmW, &full_bar[stage], ((ky * 3 + kx) * cpt + c) * 64, n0);
+                                }
                                 }
                             }
                             __syncwarp();
@@ -702,7 +791,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
     } else if (warp == 1) {
         // =================== MMA issuer (whole warp runs the loop; one elected lane issues) ===================
-        if (p.halo) mma_role_halo(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+        if (p.halo) mma_role_halo<PAIR>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
         else if (p.kc == 64) {
             if (p.msub == 2) mma_role<4, 2>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
             else mma_role<4, 1>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
@@ -724,7 +813,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const int c_begin = sub_split ? 0 : part * ncols;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x / p.ksplit; tile < total_tiles; tile += gridDim.x / p.ksplit) {
+        constexpr bool pair = PAIR;
+        const int prank = pair ? (int)cluster_ctarank() : 0;
+        // CTA pair: the leader's MMA warp waits for the epilogues of BOTH CTAs; the peer arrives on the leader's barrier
+        const uint32_t tempty_lead0 = pair ? dsmem_addr(s_addr(&tempty_bar[0]), 0) : 0u, tempty_lead1 = pair ? dsmem_addr(s_addr(&tempty_bar[1]), 0) : 0u;
+        const int e_step = pair ? (int)gridDim.x >> 1 : (int)gridDim.x / p.ksplit, e_count = pair ? total_tiles >> 1 : total_tiles;
+        for (int it = pair ? (int)blockIdx.x >> 1 : (int)blockIdx.x / p.ksplit; it < e_count; it += e_step) {
+            const int tile = pair ? 2 * it + prank : it;
             const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
             if (p.ksplit > 1) {
@@ -813,7 +908,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     __syncwarp();
                     if (sub == p.msub - 1) {                       // all TMEM reads of this tile are done: release the buffer early
                         tc_fence_before();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) {
+                            if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty_lead1 : tempty_lead0);
+                            else mbar_arrive(&tempty_bar[acc]);
+                        }
                     }
                     if (valid) {                                   // transposed read-back: 8 lanes cover one pixel's 128 bytes
                         for (int rw = rw0; rw < 32; rw += rw_step) {
@@ -873,7 +971,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty_lead1 : tempty_lead0);
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -922,9 +1023,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();    // the peer may still be signalling this CTA's barriers / reading its operands
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if constexpr (PAIR) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+        else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -1177,11 +1280,18 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.halo = 0;
     if (halo_on && p.ksplit == 1 && d.ksize == 3 && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
         p.block_n <= halo_nmax) {
+        // CTA pairs (cta_group::2) for the 128-wide layers: each CTA keeps half of the weight rows, which makes room for
+        // a third pipeline stage, and every MMA reads a quarter less shared memory
+        static const int pair_on = getenv("FUSG_NO_PAIR2") ? 0 : 1;
+        const int tiles_all = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+        p.pair = (pair_on && p.block_n == 128 && p.n_tiles == 1 && !p.w_resident && tiles_all % 2 == 0 && tiles_all >= 4 * num_sms) ? 1 : 0;
+        if (p.pair) p.b_bytes = (p.block_n / 2) * p.kc * 2;                 // half of the weight rows per CTA and k-block
         const int budget = (want_staged ? 192 : 222) * 1024 - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
         const int stage_bytes = 2 * TC_HALO_BYTES + (p.w_resident ? 0 : 3 * p.b_bytes);
         int st = budget / stage_bytes;
         if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
         if (st >= 2) { p.halo = 1; p.stages = st; p.group = 1; }
+        else if (p.pair) return FUSG_ERR_UNSUPPORTED;
     }
     int cols = 2 * p.msub * p.block_n;
     p.tmem_cols = cols < 32 ? 32 : cols;
@@ -1234,7 +1344,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         const int ktot = taps * (d.c0 + d.c1);
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.cout_pad};
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.block_n};
+        cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)(p.pair ? p.block_n / 2 : p.block_n)};
         cuuint32_t estr[2] = {1, 1};
         if (enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.weight), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -1246,13 +1356,15 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
                         1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
+        if (cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
+        if (cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
         attr_set = true;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
     static const int pdl_on = getenv("FUSG_NO_PDL") ? 0 : 1;
     p.pdl = pdl_on;
-    const int grid = p.ksplit > 1 ? total_tiles * p.ksplit /* one cluster per tile */ : (total_tiles < num_sms ? total_tiles : num_sms);
+    int grid = p.ksplit > 1 ? total_tiles * p.ksplit /* one cluster per tile */ : (total_tiles < num_sms ? total_tiles : num_sms);
+    if (p.pair) grid &= ~1;                                                  // whole CTA pairs
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
@@ -1261,9 +1373,9 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (p.ksplit > 1) {
+    if (p.ksplit > 1 || p.pair) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = (unsigned)p.ksplit;
+        attr[na].val.clusterDim.x = p.pair ? 2u : (unsigned)p.ksplit;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;
@@ -1275,7 +1387,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = (unsigned)na;
-    if (cudaLaunchKernelEx(&cfg, k_conv_tc, p) != cudaSuccess) return fusg_check_launch();
+    if ((p.pair ? cudaLaunchKernelEx(&cfg, k_conv_tc<true>, p) : cudaLaunchKernelEx(&cfg, k_conv_tc<false>, p)) != cudaSuccess) return fusg_check_launch();
     fusg_count_launch(1);
     return fusg_check_launch();
 }
