@@ -230,23 +230,19 @@ __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128) k_homography_list(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
-                                                         int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
-                                                         const int *__restrict__ counters, const int *__restrict__ list6,
-                                                         const int *__restrict__ list4) {
-    // blocks [0, ceil(n6/128)) take the 6-point list (longest solves first), the following blocks the 4-point list
-    const int n6 = counters[0], n4 = counters[1];
-    const int blocks6 = (n6 + 127) >> 7;
-    int t;
-    if ((int)blockIdx.x < blocks6) {
-        const int idx = blockIdx.x * 128 + threadIdx.x;
-        if (idx >= n6) return;
-        t = list6[idx];
-    } else {
-        const int idx = (blockIdx.x - blocks6) * 128 + threadIdx.x;
-        if (idx >= n4) return;
-        t = list4[idx];
-    }
+constexpr int HL_THREADS = 32;                     // one warp per block: 3 blocks (6-point, 72 KB) or 5 blocks (4-point, 40.5 KB) per SM
+constexpr int HL_DOUBLES6 = 288, HL_DOUBLES4 = 162;   // scratch doubles per thread: LM arrays alias the Jacobi matrices
+
+// which = 0: the 6-point list (Jacobi + LM refinement), which = 1: the 4-point list (Jacobi only)
+__global__ void __launch_bounds__(HL_THREADS) k_homography_list(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                                int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
+                                                                const int *__restrict__ counters, const int *__restrict__ list6,
+                                                                const int *__restrict__ list4, int which) {
+    extern __shared__ double hl_scratch[];
+    const int count = counters[which];
+    const int idx = blockIdx.x * HL_THREADS + threadIdx.x;
+    if (idx >= count) return;
+    const int t = which == 0 ? list6[idx] : list4[idx];
     const int b = t / N_TEX, i = t % N_TEX, j = plane_j[t];
     const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
     const int n = c_plane_n[i];
@@ -257,7 +253,7 @@ __global__ void __launch_bounds__(128) k_homography_list(const int32_t *__restri
     }
     double Hm[9], Mi[9];
     // H21 is only ever used through its "is None" test, the same (symmetric) degeneracy test as H12's
-    if (!find_homography_thread(s, d, n, Hm)) {
+    if (!find_homography_thread(s, d, n, Hm, StridedArr<HL_THREADS>{hl_scratch + threadIdx.x})) {
         plane_j[t] = -1;
         for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
     } else {
@@ -748,8 +744,18 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
         int *list6 = counters + 4, *list4 = list6 + 2 * (size_t)B;
         if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
         k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
-        k_homography_list<<<(2 * B + 127) / 128 + (3 * B + 127) / 128, 128, 0, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4);
-        fusg_count_launch(1);
+        static bool hl_attr = false;
+        if (!hl_attr) {
+            if (cudaFuncSetAttribute(k_homography_list, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_DOUBLES6 * HL_THREADS * 8) != cudaSuccess)
+                return fusg_check_launch();
+            hl_attr = true;
+        }
+        // longest solves first: the 6-point list (at most 2 side planes per crop), then the 4-point list (at most 3)
+        k_homography_list<<<(2 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES6 * HL_THREADS * 8, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
+                                                                                                                   list6, list4, 0);
+        k_homography_list<<<(3 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES4 * HL_THREADS * 8, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
+                                                                                                                   list6, list4, 1);
+        fusg_count_launch(2);
     }
     if (!frame_path) {
         k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);

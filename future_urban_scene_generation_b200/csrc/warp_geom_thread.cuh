@@ -1,5 +1,10 @@
 // warp_geom_thread.cuh -- thread-per-point-set variant of cv2.findHomography (same arithmetic as
-// warp_geom.cuh's warp-cooperative solver, one thread per solve, matrices in local memory).
+// warp_geom.cuh's warp-cooperative solver, one thread per solve).  The large matrices (9x9 LtL / V of the
+// Jacobi solve, then J / A / Ap / L of the LM refinement, 288 doubles per thread) live in SHARED memory,
+// element i of thread t at base[i * 32 + t]: with 255 registers and 3.2 KB of local arrays per thread the
+// first version kept only 8 warps per SM resident and still thrashed L1 (ncu: 11 long-scoreboard stalls per
+// issue, 485 MB of local-memory write-back per launch); the functions are templates over the array type so a
+// plain `double *` (local memory) instantiates the same arithmetic.
 // Higher throughput when tens of thousands of solves are in flight (BASELINE config 3); the
 // warp-cooperative variant has ~3x lower latency for small batches.  Both are bit-identical to the
 // oracle (tests/test_warp_gpu.py).
@@ -8,12 +13,21 @@
 
 namespace fusg {
 
+// array of doubles interleaved over the S threads of a block: element i at p[i * S]
+template <int S>
+struct StridedArr {
+    double *p;
+    __device__ __forceinline__ double &operator[](int i) const { return p[(size_t)i * S]; }
+    __device__ __forceinline__ StridedArr operator+(int off) const { return StridedArr{p + (size_t)off * S}; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // OpenCV's Jacobi eigen-solver (cv::eigen on a symmetric matrix), n <= 9.
 // A is destroyed; W = eigenvalues (descending); rows of V = eigenvectors.
 // ---------------------------------------------------------------------------------------------
 
-__device__ inline void jacobi_eig(double *A, double *W, double *V, const int n) {
+template <class AT, class VT>
+__device__ inline void jacobi_eig(AT A, double *W, VT V, const int n) {
     const double eps = DBL_EPSILON;
     int indR[9], indC[9];
     int i, j, k, m;
@@ -94,7 +108,8 @@ __device__ inline void jacobi_eig(double *A, double *W, double *V, const int n) 
 // LM refinement of the 8 free homography parameters (OpenCV LMSolver schedule, maxIters 10,
 // eps FLT_EPSILON); linear systems by square-root-free Cholesky.
 // ---------------------------------------------------------------------------------------------
-__device__ inline void lm_residual(const float *M, const float *m, int count, const double *h, double *err, double *J) {
+template <class JT>
+__device__ inline void lm_residual(const float *M, const float *m, int count, const double *h, double *err, JT J, bool want_J) {
     for (int i = 0; i < count; ++i) {
         const double Mx = M[2 * i], My = M[2 * i + 1];
         double ww = h[6] * Mx + h[7] * My + 1.;
@@ -103,8 +118,8 @@ __device__ inline void lm_residual(const float *M, const float *m, int count, co
         const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
         err[2 * i] = xi - m[2 * i];
         err[2 * i + 1] = yi - m[2 * i + 1];
-        if (J) {
-            double *Jp = J + 16 * i;
+        if (want_J) {
+            JT Jp = J + 16 * i;
             Jp[0] = Mx * ww; Jp[1] = My * ww; Jp[2] = ww;
             Jp[3] = Jp[4] = Jp[5] = 0.;
             Jp[6] = -Mx * ww * xi; Jp[7] = -My * ww * xi;
@@ -115,7 +130,8 @@ __device__ inline void lm_residual(const float *M, const float *m, int count, co
     }
 }
 
-__device__ inline void lm_normal_eq(const double *J, const double *r, int rows, double *A, double *v) {
+template <class JT, class AT>
+__device__ inline void lm_normal_eq(JT J, const double *r, int rows, AT A, double *v) {
     for (int i = 0; i < 8; ++i)
         for (int j = i; j < 8; ++j) {
             double s = 0;
@@ -145,8 +161,9 @@ __device__ inline double dot4(const double *a, const double *b, int n) {
     return res;
 }
 
-__device__ inline void ldl_solve8_serial(const double *A, const double *b, double *x) {
-    double L[64], Dg[8], y[8];
+template <class AT, class LT>
+__device__ inline void ldl_solve8_serial(AT A, const double *b, double *x, LT L) {
+    double Dg[8], y[8];
     for (int j = 0; j < 8; ++j) {
         double dj = A[j * 8 + j];
         for (int k = 0; k < j; ++k) dj -= L[j * 8 + k] * L[j * 8 + k] * Dg[k];
@@ -171,13 +188,15 @@ __device__ inline void ldl_solve8_serial(const double *A, const double *b, doubl
     }
 }
 
-__device__ inline void lm_refine(const float *M, const float *m, int count, double *h8) {
+template <class MT>
+__device__ inline void lm_refine(const float *M, const float *m, int count, double *h8, MT mem) {
     const int lx = 8, rows = 2 * count;
     const int maxIters = 10;
     const double epsx = FLT_EPSILON, epsf = FLT_EPSILON;
-    double x[8], xd[8], r[12], rd[12], J[12 * 8], A[64], Ap[64], v[8], d[8], D[8], temp_d[8];
+    double x[8], xd[8], r[12], rd[12], v[8], d[8], D[8], temp_d[8];
+    MT J = mem, A = mem + 96, Ap = mem + 160, L = mem + 224;        // 12x8 | 8x8 | 8x8 | 8x8
     for (int i = 0; i < 8; ++i) x[i] = h8[i];
-    lm_residual(M, m, count, x, r, J);
+    lm_residual(M, m, count, x, r, J, true);
     double S = 0;
     for (int i = 0; i < rows; ++i) S += r[i] * r[i];
     lm_normal_eq(J, r, rows, A, v);
@@ -188,9 +207,9 @@ __device__ inline void lm_refine(const float *M, const float *m, int count, doub
     for (;;) {
         for (int i = 0; i < 64; ++i) Ap[i] = A[i];
         for (int i = 0; i < lx; ++i) Ap[i * 8 + i] += lambda * D[i];
-        ldl_solve8_serial(Ap, v, d);
+        ldl_solve8_serial(Ap, v, d, L);
         for (int i = 0; i < lx; ++i) xd[i] = x[i] - d[i];
-        lm_residual(M, m, count, xd, rd, nullptr);
+        lm_residual(M, m, count, xd, rd, J, false);
         double Sd = 0;
         for (int i = 0; i < rows; ++i) Sd += rd[i] * rd[i];
         for (int i = 0; i < lx; ++i) {
@@ -217,7 +236,7 @@ __device__ inline void lm_refine(const float *M, const float *m, int count, doub
                 for (int c = 0; c < lx; ++c) {
                     double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, col[8];
                     e[c] = 1.;
-                    ldl_solve8_serial(A, e, col);
+                    ldl_solve8_serial(A, e, col, L);
                     maxval = fmax(maxval, fabs(col[c]));
                 }
                 lambda = lc = 1. / maxval;
@@ -228,7 +247,7 @@ __device__ inline void lm_refine(const float *M, const float *m, int count, doub
         if (Sd < S) {
             S = Sd;
             for (int i = 0; i < 8; ++i) x[i] = xd[i];
-            lm_residual(M, m, count, x, r, J);
+            lm_residual(M, m, count, x, r, J, true);
             lm_normal_eq(J, r, rows, A, v);
         }
         iter++;
@@ -258,7 +277,9 @@ __device__ inline bool homography_degenerate(const int *s, const int *d, int cou
 }
 
 // cv2.findHomography(src, dst), method 0, count in {4..6}.  Returns false where OpenCV returns None.
-__device__ inline bool find_homography_thread(const int *s, const int *d, int count, double *H) {
+// mem: 288 doubles of scratch (StridedArr over shared memory, or a plain double * to local memory).
+template <class MT>
+__device__ inline bool find_homography_thread(const int *s, const int *d, int count, double *H, MT mem) {
     float M[12], m[12];
     for (int i = 0; i < 2 * count; ++i) { M[i] = (float)s[i]; m[i] = (float)d[i]; }
     double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
@@ -276,7 +297,8 @@ __device__ inline bool find_homography_thread(const int *s, const int *d, int co
     smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
     const double invHnorm[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
     const double Hnorm2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
-    double LtL[81], W[9], V[81];
+    double W[9];
+    MT LtL = mem, V = mem + 81;
     for (int i = 0; i < 81; ++i) LtL[i] = 0;
     for (int i = 0; i < count; ++i) {
         const double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
@@ -289,8 +311,8 @@ __device__ inline bool find_homography_thread(const int *s, const int *d, int co
     }
     for (int j = 0; j < 9; ++j) for (int k = 0; k < j; ++k) LtL[j * 9 + k] = LtL[k * 9 + j];
     jacobi_eig(LtL, W, V, 9);
-    const double *H0 = V + 72;
-    double Ht[9], H1[9];
+    double H0[9], Ht[9], H1[9];
+    for (int i = 0; i < 9; ++i) H0[i] = V[72 + i];                 // last eigenvector, before the scratch is reused
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
         double acc = 0;
         for (int k = 0; k < 3; ++k) acc += invHnorm[i * 3 + k] * H0[k * 3 + j];
@@ -304,7 +326,7 @@ __device__ inline bool find_homography_thread(const int *s, const int *d, int co
     const double sc = 1. / H1[8];
     for (int i = 0; i < 9; ++i) H[i] = H1[i] * sc;
     if (count > 4) {
-        lm_refine(M, m, count, H);
+        lm_refine(M, m, count, H, mem);
         H[8] = 1.;
     }
     return true;
