@@ -506,6 +506,7 @@ struct alignas(64) ConvTcParams {
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
     int halo;                       // 1: sliding-window A tiles -- one TMA load of an image-row segment + 2 halo pixels serves the
                                     //    three horizontal taps (3x3, stride 1, Wt = 128, one image row per 128-row sub-tile)
+    uint32_t halo_skip;             // halo mode: bit (ky * chunks + chunk) set = all three taps of that stage have zero weights -> skipped
     int pair;                       // halo mode on CTA pairs (cta_group::2): M = 256 per MMA, each CTA holds half of the weight rows
     int pdl;                        // launched with programmatic stream serialization (griddepcontrol in the kernel)
     int ksplit;                     // > 1: thread-block cluster of `ksplit` CTAs per tile, each reducing 1/ksplit of K (few-tile layers)
@@ -588,6 +589,10 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)((pair ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2u << 61);
     const int stages = p.stages, cpt = p.chunks0 + p.chunks1, nst = 3 * cpt;
+    const uint32_t skip = p.halo_skip;
+    int st_first = 0, st_last = nst - 1;                       // first / last stage that is actually executed
+    while ((skip >> st_first) & 1u) ++st_first;
+    while ((skip >> st_last) & 1u) --st_last;
     const uint32_t b_kb16 = (uint32_t)p.b_bytes >> 4;
     const uint32_t a_stage16 = (2u * TC_HALO_BYTES) >> 4, b_stage16 = 3u * b_kb16;
     const bool resident = p.w_resident != 0;
@@ -604,6 +609,7 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int st = 0; st < nst; ++st) {
+            if ((skip >> st) & 1u) continue;
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (elect_one()) {
@@ -620,17 +626,17 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t a_desc = desc_hi | (uint64_t)(a16 + (uint32_t)sub * (TC_HALO_BYTES >> 4) + (uint32_t)kx * 8u + (uint32_t)ks * 2u);
                             const uint64_t b_desc = desc_hi | (uint64_t)(b16 + (uint32_t)kx * b_step + (uint32_t)ks * 2u);
-                            if constexpr (PAIR) umma_bf16_2cta(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st | kx | ks) != 0 ? 1u : 0u);
-                            else umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st | kx | ks) != 0 ? 1u : 0u);
+                            if constexpr (PAIR) umma_bf16_2cta(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st != st_first || (kx | ks) != 0) ? 1u : 0u);
+                            else umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st != st_first || (kx | ks) != 0) ? 1u : 0u);
                         }
                     }
                 }
                 if constexpr (PAIR) {
                     umma_commit_2cta(&empty_bar[stage]);
-                    if (st == nst - 1) umma_commit_2cta(&tfull_bar[acc]);
+                    if (st == st_last) umma_commit_2cta(&tfull_bar[acc]);
                 } else {
                     umma_commit(&empty_bar[stage]);
-                    if (st == nst - 1) umma_commit(&tfull_bar[acc]);
+                    if (st == st_last) umma_commit(&tfull_bar[acc]);
                 }
             }
             __syncwarp();
@@ -727,6 +733,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt, n0 = nt * p.block_n;
                     for (int ky = 0; ky < 3; ++ky) {
                         for (int c = 0; c < cpt; ++c) {
+                            if ((p.halo_skip >> (ky * cpt + c)) & 1u) continue;      // all-zero weights: nothing to accumulate
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (elect_one()) {
                                 uint8_t *a_dst = sA + (size_t)stage * 2 * TC_HALO_BYTES;
@@ -1292,6 +1299,17 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
         if (st >= 2) { p.halo = 1; p.stages = st; p.group = 1; }
         else if (p.pair) return FUSG_ERR_UNSUPPORTED;
+    }
+    p.halo_skip = 0;
+    if (p.halo && d.zero_kblocks) {
+        const int cpt = p.chunks0 + p.chunks1;
+        for (int ky = 0; ky < 3 && 9 * cpt <= 64; ++ky)
+            for (int c = 0; c < cpt; ++c) {
+                bool all = true;
+                for (int kx = 0; kx < 3; ++kx) all = all && ((d.zero_kblocks >> ((ky * 3 + kx) * cpt + c)) & 1ull);
+                if (all) p.halo_skip |= 1u << (ky * cpt + c);
+            }
+        if (p.halo_skip == (1u << (3 * cpt)) - 1u) p.halo_skip = 0;          // (a layer of zeros: keep the plain schedule)
     }
     int cols = 2 * p.msub * p.block_n;
     p.tmem_cols = cols < 32 ? 32 : cols;

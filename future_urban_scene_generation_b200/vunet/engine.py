@@ -25,12 +25,15 @@ class ConvOut(C.Structure):
                 ("mode", C.c_int32), ("blk", C.c_int32), ("reserved", C.c_int32)]
 
 
+FUSED_NIN = ("app_encoder_1.nin.layers.1", "app_encoder_1.residual_0.layers.2")
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("in0", C.c_void_p), ("in1", C.c_void_p), ("c0", C.c_int32), ("c1", C.c_int32),
                 ("pitch0", C.c_int32), ("pitch1", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("ksize", C.c_int32), ("stride", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("cout", C.c_int32), ("cout_pad", C.c_int32), ("residual", C.c_void_p), ("noise", C.c_void_p),
-                ("outs", ConvOut * MAX_OUTS), ("dtype", C.c_int32), ("impl", C.c_int32)]
+                ("outs", ConvOut * MAX_OUTS), ("dtype", C.c_int32), ("impl", C.c_int32), ("zero_kblocks", C.c_uint64)]
 
 
 class Act:
@@ -70,6 +73,8 @@ class VunetEngine:
         self._wkey = None
         self._w = {}
         self._wp = {}                  # pixel-pair packed weights of the narrow stride-1 layers
+        self._wfused = {}              # combined weights of fused layer pairs (see prepare_weights)
+        self.fuse_first_nin = os.environ.get("FUSG_NO_NIN_FUSE") is None   # fold app_encoder_1.nin into residual_0 (bf16 path)
         self.pair_narrow = os.environ.get("FUSG_NO_PAIR") is None   # run 32-channel stride-1 layers on pixel pairs (fusg_fold_weightnorm_paired)
         self.launches = 0
         self.profile = None            # list -> per-launch (path, impl, flops, start, end) CUDA-event records
@@ -119,6 +124,8 @@ class VunetEngine:
             for path, conv in self.m.convs.items():
                 cout, cin, k = conv.cout, conv.cin, conv.k
                 cin_pad = 32 if cin < 16 else cin            # the two RGB-ish first layers are padded to one 64B swizzle span
+                if path == FUSED_NIN[0] and self.fuse_first_nin and self.dtype == "bf16":
+                    cin_pad = 64                             # its input doubles as a 64-channel operand of the fused residual
                 cout_pad = _pad16(cout)
                 w = torch.empty((cout_pad, k * k, cin_pad), dtype=self.tdtype, device=dev)
                 bias = torch.zeros((cout_pad,), dtype=torch.float32, device=dev)
@@ -140,17 +147,39 @@ class VunetEngine:
                                                              cp2, self.cdtype, self._stream()), "fusg_fold_weightnorm_paired")
                     self.launches += 1
                     self._wp[path] = (wp, bp, 2 * cout, cp2, 2 * cin, k)
+            # NiN folded into the first residual of the appearance encoder: x0 + conv3x3(ELU(x0)) with x0 = NiN(ELU(in))
+            # becomes one convolution over [ELU(x0) | ELU(in)] whose weights for the second input are the NiN's at the
+            # centre tap and zero elsewhere -- the tensor core adds the residual, so x0 itself is never written or read
+            # (2.1 GB of HBM traffic per 64-crop forward); the kernel skips the all-zero k-blocks (zero_kblocks hint)
+            self._wfused = {}
+            if self.fuse_first_nin and self.dtype == "bf16":
+                nin_p, res_p = FUSED_NIN
+                wn, bn, cout, cout_pad, cinp_n, _ = self._w[nin_p]
+                wr, br, _, _, cinp_r, k = self._w[res_p]
+                wc = torch.zeros((cout_pad, k * k, cinp_r + cinp_n), dtype=self.tdtype, device=dev)
+                wc[:, :, :cinp_r] = wr
+                wc[:, (k * k) // 2, cinp_r:] = wn[:, 0, :]
+                chunks = (cinp_r + cinp_n) // 64
+                zero = 0
+                for tap in range(k * k):
+                    if tap != (k * k) // 2:
+                        for c in range(cinp_r // 64, chunks):
+                            zero |= 1 << (tap * chunks + c)
+                self._wfused[res_p] = (wc, (br + bn).contiguous(), cout, cout_pad, cinp_r + cinp_n, k, zero)
         self._wkey = key
 
     # ------------------------------------------------------------------ one conv launch
-    def conv(self, path, srcs, stride=1, residual=None, noise=None, outs=(), B=None):
+    def conv(self, path, srcs, stride=1, residual=None, noise=None, outs=(), B=None, fused=False):
         """srcs: list of (Act, 'raw'|'elu') -- one or two inputs concatenated along channels.
         outs: list of OutSpec with .tensor set.  Returns nothing (outputs are written in place)."""
-        w, bias, cout, cout_pad, cin_pad, k = self._w[path]
         d = ConvDesc()
+        if fused:
+            w, bias, cout, cout_pad, cin_pad, k, d.zero_kblocks = self._wfused[path]
+        else:
+            w, bias, cout, cout_pad, cin_pad, k = self._w[path]
         a0, which0 = srcs[0]
         # pixel-pair packing: [B,H,W,32] viewed as [B,H,W/2,64] (same bytes) for narrow stride-1 layers
-        pair = (self.pair_narrow and path in self._wp and stride == 1 and noise is None and a0.W >= 64 and a0.W % 2 == 0
+        pair = (not fused and self.pair_narrow and path in self._wp and stride == 1 and noise is None and a0.W >= 64 and a0.W % 2 == 0
                 and all(a.C == 32 and a.pitch == 32 and a.off == 0 for a, _ in srcs) and all(o.mode == PLAIN for o in outs))
         if pair:
             w, bias, cout, cout_pad, cin_pad, k = self._wp[path]
@@ -315,6 +344,14 @@ class VunetEngine:
     def init_block(self, path, x_elu, B, last_elu=False):
         """InitBlock (models.py:141-163); x_elu already holds ELU(x) padded to the weight's cin."""
         cout = self._w[path + ".nin.layers.1"][2]
+        if path + ".residual_0.layers.2" in self._wfused:
+            # fused form: only ELU(NiN(x)) is materialised; the residual term is recomputed by the tensor core
+            h = self._act(B, cout, x_elu.H, x_elu.W, raw=False, elu=True)
+            self.conv(path + ".nin.layers.1", [(x_elu, "elu")], outs=self._plain_outs(h), B=B)
+            s0 = self._act(B, cout, x_elu.H, x_elu.W)
+            self.conv(path + ".residual_0.layers.2", [(h, "elu"), (x_elu, "elu")], outs=self._plain_outs(s0), B=B, fused=True)
+            s1 = self.residual(path + ".residual_1", s0, B=B, elu=last_elu)
+            return s1, [s0, s1]
         h = self._act(B, cout, x_elu.H, x_elu.W)
         self.conv(path + ".nin.layers.1", [(x_elu, "elu")], outs=self._plain_outs(h), B=B)
         s0 = self.residual(path + ".residual_0", h, B=B)
@@ -388,7 +425,7 @@ class VunetEngine:
     def enc_up(self, x_nchw):
         """models.py:333-353 -> (outputs [Act,Act], skips [Act,Act])."""
         B = x_nchw.shape[0]
-        xin = self.from_nchw(x_nchw, elu_only=True, cpad=32)
+        xin = self.from_nchw(x_nchw, elu_only=True, cpad=self._w["app_encoder_1.nin.layers.1"][4])
         x, _ = self.init_block("app_encoder_1", xin, B)
         for name in ("app_encoder_1_a", "app_encoder_1_b", "app_encoder_1_c", "app_encoder_2"):
             x, _ = self.down_block(name, x, B)

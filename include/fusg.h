@@ -156,6 +156,9 @@ typedef struct fusg_conv_desc {
     fusg_conv_out outs[FUSG_CONV_MAX_OUTS];
     int32_t dtype;              /* FUSG_DTYPE_*                                                  */
     int32_t impl;               /* FUSG_IMPL_*                                                   */
+    uint64_t zero_kblocks;      /* optional hint: bit (tap * chunks + chunk) set = the weights of that 64-channel
+                                 * k-block (chunks = (c0+c1)/64, in0 chunks first) are all zero and the kernel
+                                 * may skip it; 0 = no hint.  Never changes the result.              */
 } fusg_conv_desc;
 
 int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
