@@ -25,7 +25,7 @@ def rnd(c, h):
 
 
 if layer == "nin6":
-    x = rnd(32, 256)
+    x = rnd(e._w["app_encoder_1.nin.layers.1"][4], 256)
     fn = lambda: e.init_block("app_encoder_1", x, B)          # nin + 2 residuals
     fn = lambda: e.conv("app_encoder_1.nin.layers.1", [(x, "elu")], outs=e._plain_outs(e._act(B, 128, 256, 256)), B=B)
     flops = 2.0 * B * 65536 * 128 * 6
