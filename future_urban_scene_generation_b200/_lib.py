@@ -43,6 +43,10 @@ def _load():
         "fusg_nhwc_to_nchw": ([vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_to_image": ([vp, vp, i, i, i, vp], i),
         "fusg_elu": ([vp, vp, sz, i, vp], i),
+        "fusg_nchw_to_nhwc_reflect": ([vp, vp, i, i, i, i, i, i, i, vp], i),
+        "fusg_norm_stats": ([vp, vp, i, i, i, i, i, vp], i),
+        "fusg_norm_finalize": ([vp, vp, vp, vp, i, i, i, i, i, C.c_float, vp], i),
+        "fusg_norm_apply": ([vp, vp, vp, i, vp, i, i, i, i, i, i, i, i, vp], i),
         "fusg_resize_u8": ([vp] * 6 + [i, i, vp], i),
         "fusg_paste_workspace_bytes": ([i, i, i], sz),
         "fusg_paste_back": ([vp] * 7 + [sz, i, i, i, i, i, i, vp], i),

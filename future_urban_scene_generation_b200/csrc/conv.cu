@@ -43,6 +43,9 @@ __device__ __forceinline__ float elu1(float x) {
 
 struct OutAddr { size_t pix; int ch; int Ct, Ht, Wt, py, px; };
 
+// fusg_conv_out.elu: 0 raw, 1 ELU, 2 tanh
+__device__ __forceinline__ float out_act(int kind, float v) { return kind == 1 ? elu1(v) : (kind == 2 ? tanhf(v) : v); }
+
 // logical destination of output channel group starting at n (16-aligned) for pixel (y,x)
 __device__ __forceinline__ OutAddr out_address(const fusg_conv_out &o, int cout, int Ho, int Wo, int b, int y, int x, int n) {
     OutAddr a;
@@ -122,7 +125,7 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
             for (int i = 0; i < 16; ++i) {             // constant trip count keeps val[] in registers
                 if (i < nvalid) {
                     const int nn = n + i, dx = nn >= cq ? 1 : 0, c = nn - dx * cq;   // nn < 2*cq
-                    p[(((size_t)b * cq + c) * Ho + y) * (2 * Wo) + 2 * x + dx] = o.elu ? elu1(val[i]) : val[i];
+                    p[(((size_t)b * cq + c) * Ho + y) * (2 * Wo) + 2 * x + dx] = out_act(o.elu, val[i]);
                 }
             }
         } else if (o.layout == 1) {                          // NCHW fp32, unrounded
@@ -131,7 +134,7 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
             const size_t base = ((size_t)b * a.Ct + a.ch) * plane + (size_t)a.py * a.Wt + a.px;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (i < nvalid) p[base + (size_t)i * plane] = o.elu ? elu1(val[i]) : val[i];
+                if (i < nvalid) p[base + (size_t)i * plane] = out_act(o.elu, val[i]);
         } else if constexpr (sizeof(T) == 2) {
             __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(o.ptr) + a.pix * a.Ct + a.ch;
             uint32_t w[8];
@@ -140,7 +143,7 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
                 // ELU is taken of the bf16-rounded raw value, so a consumer that re-derives it from
                 // the stored raw tensor gets the same bits.
                 float f0 = __bfloat162float(__float2bfloat16_rn(val[2 * i])), f1 = __bfloat162float(__float2bfloat16_rn(val[2 * i + 1]));
-                if (o.elu) { f0 = elu1(f0); f1 = elu1(f1); }
+                if (o.elu) { f0 = out_act(o.elu, f0); f1 = out_act(o.elu, f1); }
                 const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
                 w[i] = *reinterpret_cast<const uint32_t *>(&h);
             }
@@ -156,7 +159,7 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
             float *p = reinterpret_cast<float *>(o.ptr) + a.pix * a.Ct + a.ch;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (i < nvalid) p[i] = o.elu ? elu1(val[i]) : val[i];
+                if (i < nvalid) p[i] = out_act(o.elu, val[i]);
         }
     }
 }
@@ -179,15 +182,17 @@ __global__ void __launch_bounds__(128) k_conv_direct(const __grid_constant__ fus
     const bool active = pix < total;
     int b = 0, y = 0, x = 0;
     if (active) { b = (int)(pix / ((long long)Ho * Wo)); const int r = (int)(pix - (long long)b * Ho * Wo); y = r / Wo; x = r - y * Wo; }
-    const int pad = d.ksize >> 1, ctot = d.c0 + d.c1, taps = d.ksize * d.ksize;
+    // pad_mode 1: the padding values live in the input tensor's own border (fusg.h)
+    const int pad = d.pad_mode ? d.pad : d.ksize >> 1, bd = d.pad_mode ? d.border : 0, ctot = d.c0 + d.c1, taps = d.ksize * d.ksize;
+    const int Hp = d.H + 2 * bd, Wp = d.W + 2 * bd;
     const T *wbase = reinterpret_cast<const T *>(d.weight);
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     for (int tap = 0; tap < taps; ++tap) {
         const int ky = tap / d.ksize, kx = tap - ky * d.ksize;
-        const int iy = y * d.stride + ky - pad, ix = x * d.stride + kx - pad;
-        const bool inb = active && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+        const int iy = y * d.stride + ky - pad + bd, ix = x * d.stride + kx - pad + bd;      // physical coordinates
+        const bool inb = active && iy >= 0 && iy < Hp && ix >= 0 && ix < Wp;
         for (int c0 = 0; c0 < ctot; c0 += DC_CHUNK) {
             const int cn = min(DC_CHUNK, ctot - c0);
             __syncthreads();
@@ -202,8 +207,8 @@ __global__ void __launch_bounds__(128) k_conv_direct(const __grid_constant__ fus
                 for (int c = 0; c < cn; ++c) {
                     const int cc = c0 + c;
                     float a;
-                    if (cc < d.c0) a = to_f<T>(reinterpret_cast<const T *>(d.in0)[(((size_t)b * d.H + iy) * d.W + ix) * d.pitch0 + cc]);
-                    else a = to_f<T>(reinterpret_cast<const T *>(d.in1)[(((size_t)b * d.H + iy) * d.W + ix) * d.pitch1 + (cc - d.c0)]);
+                    if (cc < d.c0) a = to_f<T>(reinterpret_cast<const T *>(d.in0)[(((size_t)b * Hp + iy) * Wp + ix) * d.pitch0 + cc]);
+                    else a = to_f<T>(reinterpret_cast<const T *>(d.in1)[(((size_t)b * Hp + iy) * Wp + ix) * d.pitch1 + (cc - d.c0)]);
 #pragma unroll
                     for (int n = 0; n < 16; ++n) acc[n] = fmaf(a, s_w[n][c], acc[n]);
                 }
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     const int total_tiles = m_tiles * p.n_tiles;
-    const int pad = d.ksize >> 1;
+    const int pad = d.pad_mode ? d.pad - d.border : d.ksize >> 1;    // pad_mode 1: TMA coordinates are physical (bordered tensor)
     const int cpt = p.chunks0 + p.chunks1;        // k-blocks per tap
     int split_tile = -1;                          // split-K: the tile whose partial accumulator this epilogue warp parked
 
@@ -1190,7 +1195,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int conv_out_size(int in, int ks, int stride) { return (in + 2 * (ks / 2) - ks) / stride + 1; }
+static int conv_out_size(int in, int ks, int stride, int pad) { return (in + 2 * pad - ks) / stride + 1; }
+static int desc_pad(const fusg_conv_desc &d) { return d.pad_mode ? d.pad : d.ksize / 2; }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -1262,7 +1268,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.kb_local = p.num_kblocks / p.ksplit;
     // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
     static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
-    const bool want_staged = p.ksplit == 1 && staged_on && (d.ksize == 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
+    const bool want_staged = p.ksplit == 1 && staged_on && (d.ksize >= 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
     const int smem_budget = (want_staged ? 168 : 200) * 1024 - (p.ksplit > 1 ? p.block_n * TC_BLOCK_M * 4 : 0);
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.ksplit == 1 && p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
@@ -1285,7 +1291,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     static const int halo_on = getenv("FUSG_NO_HALO") ? 0 : 1;
     static const int halo_nmax = getenv("FUSG_HALO_NMAX") ? atoi(getenv("FUSG_HALO_NMAX")) : 128;
     p.halo = 0;
-    if (halo_on && p.ksplit == 1 && d.ksize == 3 && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
+    if (halo_on && !d.pad_mode && p.ksplit == 1 && d.ksize == 3 && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
         p.block_n <= halo_nmax) {
         // CTA pairs (cta_group::2) for the 128-wide layers: each CTA keeps half of the weight rows, which makes room for
         // a third pipeline stage, and every MMA reads a quarter less shared memory
@@ -1324,7 +1330,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         for (int sidx = 0; sidx < FUSG_CONV_MAX_OUTS && ok; ++sidx) {
             const fusg_conv_out &o = d.outs[sidx];
             if (!o.ptr) continue;
-            if (o.layout != 0 || o.source != 0) { ok = false; break; }
+            if (o.layout != 0 || o.source != 0 || o.elu > 1) { ok = false; break; }
             if (mode == -1) { mode = o.mode; fe.blk = o.blk; }
             else if (mode != o.mode || fe.blk != o.blk) { ok = false; break; }
             if (o.elu) { if (fe.elu) ok = false; fe.elu = reinterpret_cast<__nv_bfloat16 *>(o.ptr); }
@@ -1348,8 +1354,10 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     PFN_encodeTiled enc = get_encode();
     const CUtensorMapSwizzle sw = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     auto encodeA = [&](CUtensorMap *tm, const void *ptr, int c, int pitch) -> bool {
-        cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
-        cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)d.W * pitch * 2, (cuuint64_t)d.H * d.W * pitch * 2};
+        const int bd = d.pad_mode ? d.border : 0;
+        const cuuint64_t Wp = (cuuint64_t)(d.W + 2 * bd), Hp = (cuuint64_t)(d.H + 2 * bd);
+        cuuint64_t dims[4] = {(cuuint64_t)c, Wp, Hp, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, Wp * pitch * 2, Hp * Wp * pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.Wt * d.stride), (cuuint32_t)(p.Ht * d.stride), (cuuint32_t)p.Bt};
         if (p.halo) { box[1] = TC_HALO_ROWS; box[2] = 1; box[3] = 1; }
         cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
@@ -1414,7 +1422,7 @@ extern "C" size_t fusg_sizeof_conv_desc(void) { return sizeof(fusg_conv_desc); }
 
 extern "C" int fusg_conv2d_select(const fusg_conv_desc *desc) {
     if (!desc) return FUSG_ERR_ARG;
-    const int Ho = conv_out_size(desc->H, desc->ksize, desc->stride), Wo = conv_out_size(desc->W, desc->ksize, desc->stride);
+    const int Ho = conv_out_size(desc->H, desc->ksize, desc->stride, desc_pad(*desc)), Wo = conv_out_size(desc->W, desc->ksize, desc->stride, desc_pad(*desc));
     return tc_supported(*desc, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT;
 }
 
@@ -1422,7 +1430,12 @@ extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
     if (!desc || !desc->in0 || !desc->weight || !desc->bias) return FUSG_ERR_ARG;
     const fusg_conv_desc &d = *desc;
     if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.c0 <= 0 || d.cout <= 0 || d.cout_pad < d.cout) return FUSG_ERR_ARG;
-    if ((d.ksize != 1 && d.ksize != 3) || (d.stride != 1 && d.stride != 2)) return FUSG_ERR_UNSUPPORTED;
+    if (d.stride != 1 && d.stride != 2) return FUSG_ERR_UNSUPPORTED;
+    if (d.pad_mode == 0) {
+        if (d.ksize != 1 && d.ksize != 3) return FUSG_ERR_UNSUPPORTED;
+    } else {
+        if (d.pad_mode != 1 || d.ksize < 1 || d.ksize > 7 || d.pad < 0 || d.border < d.pad) return FUSG_ERR_UNSUPPORTED;
+    }
     if (d.in1 == nullptr && d.c1 != 0) return FUSG_ERR_ARG;
     if (d.dtype != FUSG_DTYPE_BF16 && d.dtype != FUSG_DTYPE_F32) return FUSG_ERR_ARG;
     bool any_out = false, need_noise = false;
@@ -1433,7 +1446,8 @@ extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
         if (d.outs[s].mode == FUSG_OUT_D2S && (d.cout % 4 != 0 || (d.cout / 4) % 16 != 0)) return FUSG_ERR_UNSUPPORTED;
     }
     if (!any_out || (need_noise && !d.noise)) return FUSG_ERR_ARG;
-    const int Ho = conv_out_size(d.H, d.ksize, d.stride), Wo = conv_out_size(d.W, d.ksize, d.stride);
+    const int Ho = conv_out_size(d.H, d.ksize, d.stride, desc_pad(d)), Wo = conv_out_size(d.W, d.ksize, d.stride, desc_pad(d));
+    if (Ho <= 0 || Wo <= 0) return FUSG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     int impl = d.impl;
     if (impl == FUSG_IMPL_AUTO) impl = tc_supported(d, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT;

@@ -130,6 +130,17 @@ def make_vunet_inputs(start: int, count: int, res: int = 256):
     return np.stack(xs).astype(np.float32), np.stack(ys).astype(np.float32)
 
 
+def make_icn_inputs(start: int, count: int, res: int = 256, channels: int = 21):
+    """ICN generator input (B,21,res,res) fp32 in [-1,1]: the value grid of `get_icn_inputs`
+    (warp_learn/models.py:354-366: Normalize(0.5, 0.5)(ToTensor(uint8))) filled with uint8 noise."""
+    xs = []
+    for i in range(count):
+        rng = np.random.default_rng(77_000 + start + i)
+        x8 = rng.integers(0, 256, (channels, res, res), dtype=np.uint8)
+        xs.append((np.float32(x8) / 255 - 0.5) / 0.5)
+    return np.stack(xs).astype(np.float32)
+
+
 def make_vunet_inputs_u8(start: int, count: int, res: int = 256):
     """The same data as `make_vunet_inputs`, as the three uint8 images the reference holds before `to_tensor`
     (trajectory_inference.py:215-220): (src_sketch_mask_bbox, src_sketch_normal_bbox, dst_sketch_normal_bbox), each

@@ -33,7 +33,8 @@ class ConvDesc(C.Structure):
                 ("pitch0", C.c_int32), ("pitch1", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("ksize", C.c_int32), ("stride", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("cout", C.c_int32), ("cout_pad", C.c_int32), ("residual", C.c_void_p), ("noise", C.c_void_p),
-                ("outs", ConvOut * MAX_OUTS), ("dtype", C.c_int32), ("impl", C.c_int32), ("zero_kblocks", C.c_uint64)]
+                ("outs", ConvOut * MAX_OUTS), ("dtype", C.c_int32), ("impl", C.c_int32), ("zero_kblocks", C.c_uint64),
+                ("pad_mode", C.c_int32), ("pad", C.c_int32), ("border", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class Act:

@@ -128,7 +128,8 @@ int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8_t *out, in
 typedef struct fusg_conv_out {
     void *ptr;          /* NULL = unused slot                                                    */
     int32_t source;     /* 0: value, 1: value + noise                                            */
-    int32_t elu;        /* 0: raw, 1: ELU(raw) -- pre-activation for the next layer              */
+    int32_t elu;        /* 0: raw, 1: ELU(raw) -- pre-activation for the next layer, 2: tanh(raw)
+                         * (the ICN's last Conv2dBlock, warp_learn/models.py:174-175; NCHW fp32 slots)   */
     int32_t layout;     /* 0: NHWC in the activation dtype, 1: NCHW fp32 (API-visible tensors)   */
     int32_t mode;       /* FUSG_OUT_*                                                            */
     int32_t blk;        /* block index for FUSG_OUT_D2S_BLOCK                                    */
@@ -147,7 +148,7 @@ typedef struct fusg_conv_desc {
     int32_t c0, c1;             /* channels read from in0 / in1 (multiples of 16 for tcgen05)    */
     int32_t pitch0, pitch1;     /* elements between consecutive pixels (>= c)                    */
     int32_t B, H, W;            /* input batch / height / width                                  */
-    int32_t ksize, stride;      /* 1 or 3 (padding ksize/2); 1 or 2                              */
+    int32_t ksize, stride;      /* 1 or 3 (padding ksize/2), 1..7 with pad_mode = 1; 1 or 2      */
     const void *weight;         /* [cout_pad][ksize*ksize][c0+c1], activation dtype (folded w_norm) */
     const float *bias;          /* [cout_pad] fp32                                               */
     int32_t cout, cout_pad;     /* real / stored output channels                                 */
@@ -159,6 +160,12 @@ typedef struct fusg_conv_desc {
     uint64_t zero_kblocks;      /* optional hint: bit (tap * chunks + chunk) set = the weights of that 64-channel
                                  * k-block (chunks = (c0+c1)/64, in0 chunks first) are all zero and the kernel
                                  * may skip it; 0 = no hint.  Never changes the result.              */
+    int32_t pad_mode;           /* 0: zero padding of ksize/2 (VUNet).  1: explicit padding `pad` whose VALUES are
+                                 * stored in the input tensor itself: in0/in1 are [B, H+2*border, W+2*border, pitch]
+                                 * with the logical image at offset (border, border) and border >= pad -- how the
+                                 * ICN's ReflectionPad2d convolutions (warp_learn/models.py:43-46,86) are fed  */
+    int32_t pad, border;        /* pad_mode 1 only                                                  */
+    int32_t reserved2;
 } fusg_conv_desc;
 
 int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
@@ -228,6 +235,35 @@ int fusg_pack_vunet_inputs(const uint8_t *frames, const int32_t *frame_idx, cons
  * inputs [B,res,res,3] u8 -> x [B,6,res,res] f32, y [B,3,res,res] f32.  Lets a host ship 9 bytes per pixel instead of 36. */
 int fusg_u8_to_vunet_inputs(const uint8_t *mask_bbox, const uint8_t *normal_src, const uint8_t *normal_dst, float *x, float *y, int B,
                             int res, void *stream);
+/* ====================================================================================== */
+/* ICN generator G_Resnet (warp_learn/models.py:15-208): the pieces   */
+/* between its convolutions.  The convolutions themselves run on fusg_conv2d (pad_mode 1).    */
+/* ====================================================================================== */
+
+/* NCHW fp32 [B,C,H,W] -> NHWC [B, H+2*border, W+2*border, cpad] in `dtype`, channels zero padded, the border filled
+ * by reflection (nn.ReflectionPad2d, warp_learn/models.py:43-44): the input of the first 7x7 Conv2dBlock (:125-127). */
+int fusg_nchw_to_nhwc_reflect(const float *in, void *out, int B, int C, int H, int W, int cpad, int border, int dtype, void *stream);
+
+/* Per-(sample, channel) partial sums of an NHWC [B,HW,C] tensor: partial [B, nsplit, C, 2] fp32 = (sum, sum of squares)
+ * of the pixels of split s.  C a multiple of 8 and <= 256; deterministic (no atomics). */
+int fusg_norm_stats(const void *x, float *partial, int B, int HW, int C, int nsplit, int dtype, void *stream);
+
+/* Folds the partial sums into per-(sample, channel) scale/shift pairs, ss [B,C,2] fp32, y = x*scale + shift:
+ *   kind 0  nn.InstanceNorm2d(affine=False, eps) (warp_learn/models.py:55-56): per (b,c) biased variance,
+ *           scale = 1/sqrt(var + eps), shift = -mean*scale;
+ *   kind 1  the reference's own LayerNorm (warp_learn/models.py:15-35): per sample over C*H*W, UNBIASED std,
+ *           (x - mean)/(std + eps), then gamma[c], beta[c]. */
+int fusg_norm_finalize(const float *partial, const float *gamma, const float *beta, float *ss, int B, int HW, int C, int nsplit,
+                       int kind, float eps, void *stream);
+
+/* out[b, Y, X, c] = act( x[b, sy, sx, c]*scale[b,c] + shift[b,c] (+ residual[b, sy+rb, sx+rb, c]) ) for every pixel of the
+ * padded output [B, up*H + 2*border, up*W + 2*border, C]: (Y,X) -> reflect into the up*H x up*W image
+ * (ReflectionPad2d) -> nearest-neighbour source pixel (sy,sx) = (y/up, x/up) (Upsample, warp_learn/models.py:138-147).
+ * x [B,H,W,C]; residual (may be NULL) [B, H+2*rb, W+2*rb, C]; relu 0/1; up 1 or 2.  One launch = norm + activation +
+ * residual add of a ResBlock (:98-102) + upsample + padding for the next convolution. */
+int fusg_norm_apply(const void *x, const float *ss, const void *residual, int rb, void *out, int B, int H, int W, int C, int relu,
+                    int up, int border, int dtype, void *stream);
+
 /* NHWC elementwise ELU (activation dtype) over n elements. */
 int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
 

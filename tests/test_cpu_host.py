@@ -1,6 +1,7 @@
 """CPU suite, part 2: host logic and the C-ABI boundary (no compute calls without a GPU)."""
 import ctypes
 import hashlib
+import json
 import os
 import re
 from argparse import Namespace
@@ -75,6 +76,36 @@ def test_vunet_module_checkpoint_contract():
     if torch.cuda.is_available():
         with pytest.raises(NotImplementedError):
             m.cuda().train()(torch.zeros(1, 3, 256, 256).cuda(), torch.zeros(1, 6, 256, 256).cuda())
+
+
+def test_icn_module_checkpoint_contract():
+    """G_Resnet(21) keeps the reference's 40-key state_dict (order, shapes) and refuses to run on the CPU."""
+    from future_urban_scene_generation_b200.warp_learn.models import G_Resnet
+    from future_urban_scene_generation_b200._lib import FusgError
+    from oracle import icn_oracle as IO
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "icn_golden.json")))
+    m = G_Resnet(21)
+    sd = m.state_dict()
+    keys = list(sd.keys())
+    assert len(keys) == gold["n_keys"] == 40
+    assert hashlib.sha1("\n".join(keys).encode()).hexdigest() == gold["key_sha1"]
+    assert keys[0] == "enc_content.model.0.conv.weight" and keys[-1] == "dec.model.5.conv.bias"
+    assert keys.index("dec.model.2.norm.gamma") < keys.index("dec.model.2.conv.weight")      # Conv2dBlock builds its norm first
+    assert sd["dec.model.4.conv.weight"].shape == (64, 128, 5, 5) and sd["enc_content.model.2.conv.weight"].shape == (256, 128, 4, 4)
+    assert sum(v.numel() for v in sd.values()) == gold["n_params"]
+    assert float(sd["dec.model.2.norm.beta"].abs().max()) == 0.0 and 0.0 <= float(sd["dec.model.2.norm.gamma"].min())
+    res = m.load_state_dict(IO.make_state_dict(3), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    bad = dict(IO.make_state_dict(3))
+    bad.pop("dec.model.5.conv.bias")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    with pytest.raises(NotImplementedError):
+        G_Resnet(21, norm='batch')
+    with pytest.raises(FusgError):
+        m.eval()(torch.zeros(1, 21, 64, 64))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 21, 30, 30))
 
 
 def test_warp_mirror_surface_and_constants():
@@ -172,8 +203,10 @@ def test_import_shim_serves_reference_import_sites():
         "from warp_learn.planes_utils import to_image, warp_unwarp_planes, get_planes, planes_to_torch;"
         "assert Vunet_fix_res.__module__.startswith('future_urban_scene_generation_b200');"
         "assert get_planes.__module__.startswith('future_urban_scene_generation_b200');"
-        + ("from warp_learn.models import G_Resnet, get_icn_inputs; import warp_learn.models as wm;"
-           "assert wm.__file__.startswith('/root/reference');"
+        + "from warp_learn.models import G_Resnet;"
+        "assert G_Resnet.__module__.startswith('future_urban_scene_generation_b200');"
+        + ("from warp_learn.models import get_icn_inputs, G_Resnet_reference; import warp_learn.models as wm;"
+           "assert get_icn_inputs.__code__.co_filename.startswith('/root/reference');"
            "assert wm.planes_to_torch.__module__.startswith('future_urban_scene_generation_b200');" if os.path.isdir(ref) else "")
         + "print('ok')")
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")

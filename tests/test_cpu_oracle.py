@@ -164,6 +164,28 @@ def test_vunet_oracle_matches_golden_fingerprint():
         assert (flat[idx] - torch.tensor(case[name]["samples"])).abs().max().item() < 1e-4, name
 
 
+def test_icn_oracle_matches_golden_fingerprint():
+    """oracle/icn_oracle.py reproduces the fingerprints scripts/make_golden_icn.py recorded next to the imported reference
+    (where it agreed with the reference G_Resnet to ~1e-6)."""
+    import torch
+    from oracle import icn_oracle as IO
+    gold = json.load(open(os.path.join(GOLD, "icn_golden.json")))
+    sd = IO.make_state_dict(0)
+    assert hashlib.sha1("\n".join(sd.keys()).encode()).hexdigest() == gold["key_sha1"]
+    assert IO.flops_per_crop(256) == gold["flops_per_crop_256"] == 130124087296          # SURVEY.md 8f: 130.1 GFLOP/crop
+    for case in gold["cases"][1:]:                                                        # the 64 / 128 px cases (seconds on CPU)
+        assert max(case["oracle_vs_reference_maxabs"].values()) < 5e-5
+        x = torch.from_numpy(synth.make_icn_inputs(case["start"], case["B"], case["res"]))
+        with torch.no_grad():
+            c = IO.encode(sd, x)
+            o = IO.decode(sd, c)
+        for name, t in (("out", o), ("content", c)):
+            flat = t.flatten()
+            idx = torch.linspace(0, flat.numel() - 1, 64).long()
+            assert (flat[idx] - torch.tensor(case[name]["samples"])).abs().max().item() < 1e-4, name
+        assert -1.0 <= case["out_range"][0] and case["out_range"][1] <= 1.0
+
+
 def test_space_depth_permutations_are_block_major():
     import torch
     from oracle import vunet_oracle as VO

@@ -1,0 +1,181 @@
+"""GPU parity of the ICN generator row through the C ABI.
+
+ * the pieces between the convolutions (reflection-bordered layout, InstanceNorm / LayerNorm statistics, the fused
+   normalise + ReLU + residual + upsample + re-border pass) vs torch fp32;
+ * bordered (pad_mode 1) convolutions of every ICN shape class -- 7x7, 4x4 stride 2, 3x3, 5x5, tanh head -- tcgen05 kernel
+   and direct kernel vs torch conv2d on a reflection-padded input;
+ * the whole generator vs oracle/icn_oracle.py (pinned to the reference G_Resnet by scripts/make_golden_icn.py) with
+   identical weights: fp32 verification build <= 1e-4, bf16 product path <= 1e-2 on the tanh-bounded image.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 1e-2
+TOL_FP32 = 1e-4
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _engine(torch, dtype, impl="auto"):
+    from future_urban_scene_generation_b200.warp_learn.models import G_Resnet
+    from oracle import icn_oracle as IO
+    sd = IO.make_state_dict(0)
+    m = G_Resnet(21, dtype=dtype, impl=impl)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    return m, sd
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_reflect_layout_and_norm_passes(cuda, dtype):
+    torch = cuda
+    import torch.nn.functional as F
+    from future_urban_scene_generation_b200.warp_learn.icn_engine import Padded
+    m, _ = _engine(torch, dtype)
+    e = m.engine()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(3, 64, 16, 24, generator=g).cuda() * 2 + 0.5
+    # reflection-bordered NHWC copy
+    p = e.to_padded(x, 3)
+    ref = F.pad(x, (3, 3, 3, 3), mode="reflect").permute(0, 2, 3, 1)
+    assert torch.equal(p.t.float(), ref.to(e.tdtype).float())             # a pure (rounded) copy
+    # InstanceNorm + ReLU + residual + 2x upsample + border 2
+    raw = x.permute(0, 2, 3, 1).contiguous().to(e.tdtype)
+    rawf = raw.float().permute(0, 3, 1, 2)
+    resid = e.to_padded(torch.randn(3, 64, 16, 24, generator=g).cuda(), 1)
+    residf = resid.t[:, 1:-1, 1:-1, :].float().permute(0, 3, 1, 2)
+    out = e.norm("t", raw, 16, 24, "inst", residual=resid, relu=True, up=2, border=2)
+    want = F.relu(F.instance_norm(rawf, eps=1e-5) + residf)
+    want = F.pad(F.interpolate(want, scale_factor=2, mode="nearest"), (2, 2, 2, 2), mode="reflect").permute(0, 2, 3, 1)
+    assert out.t.shape == want.shape
+    assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 8e-3 * max(1.0, want.abs().max().item()))
+    # the reference's LayerNorm: unbiased std, (std + eps), per-channel affine; no activation, border 3
+    gamma, beta = torch.rand(64, generator=g).cuda(), torch.randn(64, generator=g).cuda() * 0.1
+    out = e.norm("t", raw, 16, 24, "ln", gamma, beta, relu=False, up=1, border=3)
+    flat = rawf.reshape(3, -1)
+    want = (rawf - flat.mean(1).view(-1, 1, 1, 1)) / (flat.std(1).view(-1, 1, 1, 1) + 1e-5)
+    want = want * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    want = F.pad(want, (3, 3, 3, 3), mode="reflect").permute(0, 2, 3, 1)
+    assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 8e-3 * max(1.0, want.abs().max().item()))
+
+
+@pytest.mark.parametrize("path,res,stride,pad", [
+    ("enc_content.model.0", 64, 1, 3),                 # 7x7 21(32)->64
+    ("enc_content.model.1", 64, 2, 1),                 # 4x4 s2 64->128
+    ("enc_content.model.2", 32, 2, 1),                 # 4x4 s2 128->256
+    ("enc_content.model.3.model.0.model.0", 16, 1, 1),  # 3x3 256->256
+    ("dec.model.2", 32, 1, 2),                         # 5x5 256->128
+    ("dec.model.4", 64, 1, 2),                         # 5x5 128->64
+    ("enc_content.model.0", 256, 1, 3),                # full-size first layer (256-row tiles)
+    ("dec.model.4", 256, 1, 2),
+])
+def test_bordered_convolutions(cuda, path, res, stride, pad):
+    torch = cuda
+    import torch.nn.functional as F
+    m, sd = _engine(torch, "bf16")
+    e = m.engine()
+    w, b = sd[path + ".conv.weight"].cuda(), sd[path + ".conv.bias"].cuda()
+    cin = w.shape[1]
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B = 2 if res < 256 else 1
+    x = torch.randn(B, cin, res, res, generator=g).cuda()
+    xp = e.to_padded(x, pad, cpad=32 if cin < 32 else cin)
+    xr = xp.t.float()[..., :cin].permute(0, 3, 1, 2)                      # the bf16-rounded, reflection-padded input
+    want = F.conv2d(xr, w.to(torch.bfloat16).float(), b, stride=stride).permute(0, 2, 3, 1)
+    from future_urban_scene_generation_b200 import _lib
+    from future_urban_scene_generation_b200.vunet.engine import IMPL_TC, IMPL_DIRECT
+    outs = {}
+    for name, impl in (("tcgen05", IMPL_TC), ("direct", IMPL_DIRECT)):
+        e.impl = impl
+        raw, Ho, Wo = e.conv(path, xp, stride, pad)
+        torch.cuda.synchronize()
+        outs[name] = raw.float()
+        assert raw.shape == want.shape
+        err = (outs[name] - want).abs().max().item()
+        assert err <= 2e-2 * max(1.0, want.abs().max().item()), (name, err)
+    assert (outs["tcgen05"] - outs["direct"]).abs().max().item() <= 1.6e-2 * max(1.0, want.abs().max().item())
+
+
+def test_tanh_head(cuda):
+    torch = cuda
+    import torch.nn.functional as F
+    m, sd = _engine(torch, "bf16")
+    e = m.engine()
+    path = "dec.model.5"
+    w, b = sd[path + ".conv.weight"].cuda(), sd[path + ".conv.bias"].cuda()
+    g = torch.Generator(device="cpu").manual_seed(12)
+    x = torch.randn(2, 64, 64, 64, generator=g).cuda()
+    xp = e.to_padded(x, 3)
+    want = torch.tanh(F.conv2d(xp.t.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b))
+    from future_urban_scene_generation_b200.vunet.engine import IMPL_TC, IMPL_DIRECT
+    for impl in (IMPL_TC, IMPL_DIRECT):
+        e.impl = impl
+        out = torch.empty(2, 3, 64, 64, device="cuda")
+        e.conv(path, xp, 1, 3, tanh_nchw=out)
+        torch.cuda.synchronize()
+        assert (out - want).abs().max().item() <= 5e-3, impl
+
+
+@pytest.mark.parametrize("res,B", [(64, 2), (128, 1)])
+def test_generator_fp32_build_vs_oracle(cuda, res, B):
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from oracle import icn_oracle as IO
+    m, sd = _engine(torch, "fp32")
+    x = torch.from_numpy(synth.make_icn_inputs(3, B, res))
+    with torch.no_grad():
+        want = IO.forward(sd, x)
+        want_c = IO.encode(sd, x)
+    got = m(x.cuda())
+    c = m.enc_content(x.cuda())
+    got2 = m.decode(c)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert (c.cpu() - want_c).abs().max().item() <= 2e-4          # unbounded content features
+    assert (got.cpu() - want).abs().max().item() <= TOL_FP32
+    assert torch.equal(got, got2)                                  # enc_content -> decode is the same program
+
+
+@pytest.mark.parametrize("res,B,start", [(64, 2, 3), (256, 1, 0), (256, 3, 20)])
+def test_generator_bf16_tcgen05_vs_oracle(cuda, res, B, start):
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth, _lib
+    from oracle import icn_oracle as IO
+    m, sd = _engine(torch, "bf16", impl="tcgen05")                 # every convolution must run on the tensor cores
+    x = torch.from_numpy(synth.make_icn_inputs(start, B, res))
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        want = IO.forward(sd, x)
+    n0 = _lib.kernel_launches()
+    got = m(x.cuda())
+    torch.cuda.synchronize()
+    assert _lib.kernel_launches() - n0 >= 18 + 3 * 17 + 1
+    err = (got.cpu() - want).abs().max().item()
+    assert err <= TOL_BF16, err
+    if res == 256 and B == 1:
+        gold = json.load(open(os.path.join(GOLD, "icn_golden.json")))["cases"][0]
+        flat = got.cpu().flatten()
+        idx = torch.linspace(0, flat.numel() - 1, 64).long()
+        assert (flat[idx] - torch.tensor(gold["out"]["samples"])).abs().max().item() <= TOL_BF16
+
+
+def test_foreign_content_tensor_and_reload(cuda):
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from oracle import icn_oracle as IO
+    m, sd = _engine(torch, "bf16")
+    x = torch.from_numpy(synth.make_icn_inputs(1, 1, 64)).cuda()
+    c = m.enc_content(x)
+    a = m.decode(c)
+    b = m.decode(c.clone())                                        # no engine tag: converted from the NCHW values
+    assert (a - b).abs().max().item() <= 2e-2
+    sd2 = IO.make_state_dict(7)
+    m.load_state_dict(sd2, strict=True)                            # weights are re-packed after a reload
+    with torch.no_grad():
+        want = IO.forward(sd2, x.cpu())
+    assert (m(x).cpu() - want).abs().max().item() <= TOL_BF16
