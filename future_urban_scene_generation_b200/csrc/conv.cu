@@ -20,6 +20,8 @@
 //                  verification build and as the in-library cross-check of k_conv_tc.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -40,6 +42,15 @@ __device__ __forceinline__ float elu1(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
     return x > 0.f ? x : e - 1.f;
 }
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 struct OutAddr { size_t pix; int ch; int Ct, Ht, Wt, py, px; };
 
@@ -80,7 +91,7 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
     if (d.residual) {
         const T *r = reinterpret_cast<const T *>(d.residual) + opix * d.cout + n;
         if (nvalid == 16) {
-            if constexpr (sizeof(T) == 2) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
                 const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(r)), q1 = __ldg(reinterpret_cast<const uint4 *>(r) + 1);
                 const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
@@ -91,12 +102,12 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += (float)r[i];
+                for (int i = 0; i < 16; ++i) v[i] += to_f<T>(r[i]);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (i < nvalid) v[i] += (float)r[i];
+                if (i < nvalid) v[i] += to_f<T>(r[i]);
         }
     }
     float z[16];
@@ -135,7 +146,7 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (i < nvalid) p[base + (size_t)i * plane] = out_act(o.elu, val[i]);
-        } else if constexpr (sizeof(T) == 2) {
+        } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(o.ptr) + a.pix * a.Ct + a.ch;
             uint32_t w[8];
 #pragma unroll
@@ -156,10 +167,10 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
                     if (i < nvalid) p[i] = __ushort_as_bfloat16((unsigned short)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu)));
             }
         } else {
-            float *p = reinterpret_cast<float *>(o.ptr) + a.pix * a.Ct + a.ch;
+            T *p = reinterpret_cast<T *>(o.ptr) + a.pix * a.Ct + a.ch;       // fp32 / fp16 NHWC (activation of the rounded value)
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (i < nvalid) p[i] = out_act(o.elu, val[i]);
+                if (i < nvalid) p[i] = from_f<T>(out_act(o.elu, to_f<T>(from_f<T>(val[i]))));
         }
     }
 }
@@ -167,10 +178,6 @@ __device__ __forceinline__ void epilogue16(const fusg_conv_desc &d, const float 
 // ------------------------------------------------------------------------------------------------
 // k_conv_direct: thread = (output pixel, group of 16 output channels)
 // ------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ float to_f(T v);
-template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-
 constexpr int DC_CHUNK = 32;   // channels staged per step
 
 template <typename T>
@@ -395,6 +402,7 @@ struct FastEpi {
     __nv_bfloat16 *raw, *elu;
     const __nv_bfloat16 *res;
     int mode, blk, cq_shift;
+    int f16;                  // activation dtype is fp16 (raw outputs only: no residual / ELU copy on this path)
     int stride_a, stride_b;   // elements between output pixels x -> x+2 and x -> x+1 (x even) of one image row under `mode`
 };
 
@@ -403,6 +411,12 @@ __device__ __forceinline__ float bf16hi_to_f(uint32_t w) { return __uint_as_floa
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
 
@@ -460,8 +474,13 @@ __device__ __forceinline__ void fast_chunk16(const FastEpi &fe, const float *s_b
         for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo_to_f(w[i]); v[2 * i + 1] += bf16hi_to_f(w[i]); }
     }
     uint32_t pk[8];
+    if (fe.f16) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    }
     const size_t off = fast_out_offset(fe, cout, Ho, Wo, b, y, x, n);
     if (fe.raw) {
         uint4 *o = reinterpret_cast<uint4 *>(fe.raw + off);
@@ -529,7 +548,8 @@ template <int KSTEPS, int MSUB>
 __device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uint8_t *sB, uint64_t *full_bar, uint64_t *empty_bar,
                                          uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *w_bar, uint32_t tmem_base, int total_tiles) {
     const uint32_t block_n = (uint32_t)p.block_n;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    // instruction descriptor: fp32 accumulate | A/B format (1 = bf16, 0 = fp16) | N >> 3 | M >> 4
+    const uint32_t idesc = (1u << 4) | (p.fe.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((block_n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
     const uint32_t kc = KSTEPS * 16;
     // descriptor high bits: LBO=1 | SBO = 8 rows of one swizzle span | version 1 | swizzle mode
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((kc * 2u * 8u) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KSTEPS == 4 ? 2u : 4u) << 61);
@@ -591,7 +611,7 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
     const uint32_t block_n = (uint32_t)p.block_n;
     constexpr bool pair = PAIR;
     if (pair && cluster_ctarank() != 0) return;                        // the leader CTA issues for the pair
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((block_n >> 3) << 17) | ((uint32_t)((pair ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (p.fe.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((block_n >> 3) << 17) | ((uint32_t)((pair ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2u << 61);
     const int stages = p.stages, cpt = p.chunks0 + p.chunks1, nst = 3 * cpt;
     const uint32_t skip = p.halo_skip;
@@ -914,8 +934,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
                             for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo_to_f(w[i]); v[2 * i + 1] += bf16hi_to_f(w[i]); }
                         }
-                        sts128(s0, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
-                        sts128(s1, make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
+                        if (fe.f16) {
+                            sts128(s0, make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7])));
+                            sts128(s1, make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15])));
+                        } else {
+                            sts128(s0, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+                            sts128(s1, make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
+                        }
                     }
                     __syncwarp();
                     if (sub == p.msub - 1) {                       // all TMEM reads of this tile are done: release the buffer early
@@ -1046,10 +1071,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // layout / weight helpers
 // ------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ T from_f(float v);
-template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-
 template <typename T>
 __global__ void k_fold_weightnorm(const float *__restrict__ v, const float *__restrict__ g, T *__restrict__ w, int cout, int cin, int ks,
                                   int cout_pad, int cin_pad) {
@@ -1201,7 +1222,13 @@ static int desc_pad(const fusg_conv_desc &d) { return d.pad_mode ? d.pad : d.ksi
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 static bool tc_supported(const fusg_conv_desc &d, int Ho, int Wo) {
-    if (d.dtype != FUSG_DTYPE_BF16) return false;
+    if (d.dtype != FUSG_DTYPE_BF16 && d.dtype != FUSG_DTYPE_F16) return false;
+    if (d.dtype == FUSG_DTYPE_F16) {
+        // fp16 activations (the ICN row): raw NHWC outputs or NCHW fp32 slots only -- no residual, noise or ELU copy
+        if (d.residual || d.noise) return false;
+        for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s)
+            if (d.outs[s].ptr && d.outs[s].layout == 0 && (d.outs[s].elu || d.outs[s].mode != FUSG_OUT_PLAIN || d.cout % 16)) return false;
+    }
     if (d.c0 % 32 != 0 || (d.in1 && d.c1 % 32 != 0)) return false;
     if (d.cout_pad % 16 != 0) return false;
     if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
@@ -1342,6 +1369,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             else { int sh = 0; while ((1 << sh) < cq) ++sh; fe.cq_shift = sh; }
         }
         fe.mode = mode < 0 ? 0 : mode;
+        fe.f16 = d.dtype == FUSG_DTYPE_F16 ? 1 : 0;
         switch (fe.mode) {
             default: fe.stride_a = 2 * d.cout; fe.stride_b = d.cout; break;
             case FUSG_OUT_D2S: fe.stride_a = d.cout; fe.stride_b = d.cout / 2; break;          // 4*cq, 2*cq with cq = cout/4
@@ -1361,7 +1389,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.Wt * d.stride), (cuuint32_t)(p.Ht * d.stride), (cuuint32_t)p.Bt};
         if (p.halo) { box[1] = TC_HALO_ROWS; box[2] = 1; box[3] = 1; }
         cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
-        return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        return enc(tm, d.dtype == FUSG_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
     if (!encodeA(&p.tmA0, d.in0, d.c0, d.pitch0)) return FUSG_ERR_UNSUPPORTED;
@@ -1372,7 +1400,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)(p.pair ? p.block_n / 2 : p.block_n)};
         cuuint32_t estr[2] = {1, 1};
-        if (enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.weight), dims, strides, box, estr,
+        if (enc(&p.tmW, d.dtype == FUSG_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.weight), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FUSG_ERR_UNSUPPORTED;
     }
@@ -1437,7 +1465,7 @@ extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
         if (d.pad_mode != 1 || d.ksize < 1 || d.ksize > 7 || d.pad < 0 || d.border < d.pad) return FUSG_ERR_UNSUPPORTED;
     }
     if (d.in1 == nullptr && d.c1 != 0) return FUSG_ERR_ARG;
-    if (d.dtype != FUSG_DTYPE_BF16 && d.dtype != FUSG_DTYPE_F32) return FUSG_ERR_ARG;
+    if (d.dtype != FUSG_DTYPE_BF16 && d.dtype != FUSG_DTYPE_F32 && d.dtype != FUSG_DTYPE_F16) return FUSG_ERR_ARG;
     bool any_out = false, need_noise = false;
     for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s) {
         if (!d.outs[s].ptr) continue;
@@ -1458,6 +1486,7 @@ extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
     const long long total = (long long)d.B * Ho * Wo;
     dim3 grid((unsigned)((total + 127) / 128), (unsigned)((d.cout_pad + 15) / 16));
     if (d.dtype == FUSG_DTYPE_BF16) k_conv_direct<__nv_bfloat16><<<grid, 128, 0, st>>>(d, Ho, Wo);
+    else if (d.dtype == FUSG_DTYPE_F16) k_conv_direct<__half><<<grid, 128, 0, st>>>(d, Ho, Wo);
     else k_conv_direct<float><<<grid, 128, 0, st>>>(d, Ho, Wo);
     fusg_count_launch(1);
     return fusg_check_launch();

@@ -3,6 +3,7 @@
 // normalise + activation + residual + nearest-upsample + reflection-pad pass that writes the next convolution's
 // (bordered) input.  The convolutions run on fusg_conv2d with pad_mode = 1 (conv.cu).  All HBM-bound, NHWC.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "../../include/fusg.h"
@@ -30,6 +31,27 @@ template <> struct Vec<__nv_bfloat16> {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+template <> struct Vec<__half> {
+    static constexpr int N = 8;
+    __device__ static void load(const __half *p, float *v) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ static void store(__half *p, const float *v) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
             w[i] = *reinterpret_cast<const uint32_t *>(&h);
         }
         *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -181,6 +203,7 @@ extern "C" int fusg_nchw_to_nhwc_reflect(const float *in, void *out, int B, int 
     const size_t npix = (size_t)B * (H + 2 * border) * (W + 2 * border);
     const unsigned grid = (unsigned)((npix + 255) / 256);
     if (dtype == FUSG_DTYPE_BF16) k_nchw_to_nhwc_reflect<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16 *)out, C, H, W, cpad, border, npix);
+    else if (dtype == FUSG_DTYPE_F16) k_nchw_to_nhwc_reflect<__half><<<grid, 256, 0, st>>>(in, (__half *)out, C, H, W, cpad, border, npix);
     else k_nchw_to_nhwc_reflect<float><<<grid, 256, 0, st>>>(in, (float *)out, C, H, W, cpad, border, npix);
     fusg_count_launch(1);
     return fusg_check_launch();
@@ -188,11 +211,12 @@ extern "C" int fusg_nchw_to_nhwc_reflect(const float *in, void *out, int B, int 
 
 extern "C" int fusg_norm_stats(const void *x, float *partial, int B, int HW, int C, int nsplit, int dtype, void *stream) {
     if (!x || !partial || B <= 0 || HW <= 0 || C <= 0 || nsplit <= 0) return FUSG_ERR_ARG;
-    if (C % 8 != 0 || C > 256 || B > 65535 || (256 % (C / 8)) != 0 || (dtype != FUSG_DTYPE_BF16 && (256 % (C / 4)) != 0)) return FUSG_ERR_UNSUPPORTED;
-    if (dtype != FUSG_DTYPE_BF16 && C / 4 > 256) return FUSG_ERR_UNSUPPORTED;
+    const bool half16 = dtype == FUSG_DTYPE_BF16 || dtype == FUSG_DTYPE_F16;
+    if (C % 8 != 0 || C > 256 || B > 65535 || (256 % (C / 8)) != 0 || (!half16 && (256 % (C / 4)) != 0)) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)nsplit, (unsigned)B);
     if (dtype == FUSG_DTYPE_BF16) k_norm_stats<__nv_bfloat16><<<grid, ST_THREADS, 0, st>>>((const __nv_bfloat16 *)x, partial, HW, C, nsplit);
+    else if (dtype == FUSG_DTYPE_F16) k_norm_stats<__half><<<grid, ST_THREADS, 0, st>>>((const __half *)x, partial, HW, C, nsplit);
     else k_norm_stats<float><<<grid, ST_THREADS, 0, st>>>((const float *)x, partial, HW, C, nsplit);
     fusg_count_launch(1);
     return fusg_check_launch();
@@ -212,11 +236,13 @@ extern "C" int fusg_norm_apply(const void *x, const float *ss, const void *resid
     if (!x || !ss || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || border < 0 || rb < 0) return FUSG_ERR_ARG;
     if (C % 8 != 0 || (up != 1 && up != 2) || border >= H * up || border >= W * up) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = dtype == FUSG_DTYPE_BF16 ? 8 : 4;
+    const int N = dtype == FUSG_DTYPE_F32 ? 4 : 8;
     const size_t total = (size_t)B * (H * up + 2 * border) * (W * up + 2 * border) * (C / N);
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (dtype == FUSG_DTYPE_BF16)
         k_norm_apply<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, ss, (const __nv_bfloat16 *)residual, rb, (__nv_bfloat16 *)out, H, W, C, relu, up, border, total);
+    else if (dtype == FUSG_DTYPE_F16)
+        k_norm_apply<__half><<<grid, 256, 0, st>>>((const __half *)x, ss, (const __half *)residual, rb, (__half *)out, H, W, C, relu, up, border, total);
     else
         k_norm_apply<float><<<grid, 256, 0, st>>>((const float *)x, ss, (const float *)residual, rb, (float *)out, H, W, C, relu, up, border, total);
     fusg_count_launch(1);

@@ -61,8 +61,9 @@ class _Seq(nn.Module):
 
 
 class G_Resnet(nn.Module):
-    def __init__(self, input_nc, output_nc=3, num_downs=2, n_res=3, ngf=64, norm='inst', nl_layer='relu', dtype: str = "bf16",
+    def __init__(self, input_nc, output_nc=3, num_downs=2, n_res=3, ngf=64, norm='inst', nl_layer='relu', dtype: str = "fp16",
                  impl: str = "auto"):
+        """dtype: 'fp16' (tcgen05 product path), 'bf16' (same kernels on bf16), 'fp32' (verification build on CUDA cores)."""
         super().__init__()
         if norm != 'inst' or nl_layer != 'relu' or num_downs < 1 or n_res < 1:
             raise NotImplementedError("the B200 path implements the shipped ICN configuration only (norm='inst', nl_layer='relu'; "
@@ -118,7 +119,7 @@ class G_Resnet(nn.Module):
         eng.prepare_weights()
         return eng
 
-    def set_compute(self, dtype="bf16", impl="auto"):
+    def set_compute(self, dtype="fp16", impl="auto"):
         self._dtype, self._impl = dtype, impl
         return self
 

@@ -106,6 +106,9 @@ int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8_t *out, in
 
 #define FUSG_DTYPE_BF16 0
 #define FUSG_DTYPE_F32 1          /* fp32 verification build: direct kernels only */
+#define FUSG_DTYPE_F16 2          /* fp16 activations/weights, fp32 accumulate: the ICN row (normalised activations;
+                                   * 8x finer rounding than bf16 at the same tensor-core rate).  tcgen05 path: raw NHWC
+                                   * outputs and NCHW fp32 slots only */
 
 #define FUSG_IMPL_AUTO 0
 #define FUSG_IMPL_TCGEN05 1       /* implicit-GEMM tcgen05/TMEM kernel fed by TMA (bf16 only) */

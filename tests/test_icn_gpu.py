@@ -5,7 +5,10 @@
  * bordered (pad_mode 1) convolutions of every ICN shape class -- 7x7, 4x4 stride 2, 3x3, 5x5, tanh head -- tcgen05 kernel
    and direct kernel vs torch conv2d on a reflection-padded input;
  * the whole generator vs oracle/icn_oracle.py (pinned to the reference G_Resnet by scripts/make_golden_icn.py) with
-   identical weights: fp32 verification build <= 1e-4, bf16 product path <= 1e-2 on the tanh-bounded image.
+   identical weights: fp32 verification build <= 1e-4, fp16 tcgen05 product path <= 1e-2 on the tanh-bounded image.
+   The same kernels on bf16 are held to 2.5e-2: rounding only the convolution operands to bf16 in the fp32 oracle already
+   gives 1.1e-2 on this 18-layer normalised stack (1.5e-2 with bf16 activations stored between layers), which is why the
+   product path of this row computes in fp16.
 """
 import ctypes as C
 import json
@@ -16,8 +19,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-TOL_BF16 = 1e-2
+TOL_F16 = 1e-2       # product path
+TOL_BF16 = 2.5e-2    # bf16 variant: operand-rounding floor 1.1e-2 (see the module docstring)
 TOL_FP32 = 1e-4
+T16 = {"fp16": 1.0, "bf16": 8.0}      # relative rounding of the 16-bit types, in units of 2^-11
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -31,7 +36,7 @@ def _engine(torch, dtype, impl="auto"):
     return m, sd
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
 def test_reflect_layout_and_norm_passes(cuda, dtype):
     torch = cuda
     import torch.nn.functional as F
@@ -53,7 +58,7 @@ def test_reflect_layout_and_norm_passes(cuda, dtype):
     want = F.relu(F.instance_norm(rawf, eps=1e-5) + residf)
     want = F.pad(F.interpolate(want, scale_factor=2, mode="nearest"), (2, 2, 2, 2), mode="reflect").permute(0, 2, 3, 1)
     assert out.t.shape == want.shape
-    assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 8e-3 * max(1.0, want.abs().max().item()))
+    assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 1e-3 * T16[dtype] * max(1.0, want.abs().max().item()))
     # the reference's LayerNorm: unbiased std, (std + eps), per-channel affine; no activation, border 3
     gamma, beta = torch.rand(64, generator=g).cuda(), torch.randn(64, generator=g).cuda() * 0.1
     out = e.norm("t", raw, 16, 24, "ln", gamma, beta, relu=False, up=1, border=3)
@@ -61,7 +66,7 @@ def test_reflect_layout_and_norm_passes(cuda, dtype):
     want = (rawf - flat.mean(1).view(-1, 1, 1, 1)) / (flat.std(1).view(-1, 1, 1, 1) + 1e-5)
     want = want * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
     want = F.pad(want, (3, 3, 3, 3), mode="reflect").permute(0, 2, 3, 1)
-    assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 8e-3 * max(1.0, want.abs().max().item()))
+    assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 1e-3 * T16[dtype] * max(1.0, want.abs().max().item()))
 
 
 @pytest.mark.parametrize("path,res,stride,pad", [
@@ -74,10 +79,11 @@ def test_reflect_layout_and_norm_passes(cuda, dtype):
     ("enc_content.model.0", 256, 1, 3),                # full-size first layer (256-row tiles)
     ("dec.model.4", 256, 1, 2),
 ])
-def test_bordered_convolutions(cuda, path, res, stride, pad):
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_bordered_convolutions(cuda, path, res, stride, pad, dtype):
     torch = cuda
     import torch.nn.functional as F
-    m, sd = _engine(torch, "bf16")
+    m, sd = _engine(torch, dtype)
     e = m.engine()
     w, b = sd[path + ".conv.weight"].cuda(), sd[path + ".conv.bias"].cuda()
     cin = w.shape[1]
@@ -86,7 +92,7 @@ def test_bordered_convolutions(cuda, path, res, stride, pad):
     x = torch.randn(B, cin, res, res, generator=g).cuda()
     xp = e.to_padded(x, pad, cpad=32 if cin < 32 else cin)
     xr = xp.t.float()[..., :cin].permute(0, 3, 1, 2)                      # the bf16-rounded, reflection-padded input
-    want = F.conv2d(xr, w.to(torch.bfloat16).float(), b, stride=stride).permute(0, 2, 3, 1)
+    want = F.conv2d(xr, w.to(e.tdtype).float(), b, stride=stride).permute(0, 2, 3, 1)
     from future_urban_scene_generation_b200 import _lib
     from future_urban_scene_generation_b200.vunet.engine import IMPL_TC, IMPL_DIRECT
     outs = {}
@@ -97,28 +103,29 @@ def test_bordered_convolutions(cuda, path, res, stride, pad):
         outs[name] = raw.float()
         assert raw.shape == want.shape
         err = (outs[name] - want).abs().max().item()
-        assert err <= 2e-2 * max(1.0, want.abs().max().item()), (name, err)
-    assert (outs["tcgen05"] - outs["direct"]).abs().max().item() <= 1.6e-2 * max(1.0, want.abs().max().item())
+        assert err <= 2.5e-3 * T16[dtype] * max(1.0, want.abs().max().item()), (name, err)     # output rounding + summation order
+    assert (outs["tcgen05"] - outs["direct"]).abs().max().item() <= 2e-3 * T16[dtype] * max(1.0, want.abs().max().item())
 
 
-def test_tanh_head(cuda):
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_tanh_head(cuda, dtype):
     torch = cuda
     import torch.nn.functional as F
-    m, sd = _engine(torch, "bf16")
+    m, sd = _engine(torch, dtype)
     e = m.engine()
     path = "dec.model.5"
     w, b = sd[path + ".conv.weight"].cuda(), sd[path + ".conv.bias"].cuda()
     g = torch.Generator(device="cpu").manual_seed(12)
     x = torch.randn(2, 64, 64, 64, generator=g).cuda()
     xp = e.to_padded(x, 3)
-    want = torch.tanh(F.conv2d(xp.t.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b))
+    want = torch.tanh(F.conv2d(xp.t.float().permute(0, 3, 1, 2), w.to(e.tdtype).float(), b))
     from future_urban_scene_generation_b200.vunet.engine import IMPL_TC, IMPL_DIRECT
     for impl in (IMPL_TC, IMPL_DIRECT):
         e.impl = impl
         out = torch.empty(2, 3, 64, 64, device="cuda")
         e.conv(path, xp, 1, 3, tanh_nchw=out)
         torch.cuda.synchronize()
-        assert (out - want).abs().max().item() <= 5e-3, impl
+        assert (out - want).abs().max().item() <= 1e-4, impl          # fp32 accumulation of identical operands
 
 
 @pytest.mark.parametrize("res,B", [(64, 2), (128, 1)])
@@ -141,12 +148,13 @@ def test_generator_fp32_build_vs_oracle(cuda, res, B):
     assert torch.equal(got, got2)                                  # enc_content -> decode is the same program
 
 
-@pytest.mark.parametrize("res,B,start", [(64, 2, 3), (256, 1, 0), (256, 3, 20)])
-def test_generator_bf16_tcgen05_vs_oracle(cuda, res, B, start):
+@pytest.mark.parametrize("res,B,start,dtype", [(64, 2, 3, "fp16"), (256, 1, 0, "fp16"), (256, 3, 20, "fp16"), (64, 2, 3, "bf16"), (256, 1, 0, "bf16")])
+def test_generator_tcgen05_vs_oracle(cuda, res, B, start, dtype):
     torch = cuda
     from future_urban_scene_generation_b200 import synth, _lib
     from oracle import icn_oracle as IO
-    m, sd = _engine(torch, "bf16", impl="tcgen05")                 # every convolution must run on the tensor cores
+    tol = TOL_F16 if dtype == "fp16" else TOL_BF16
+    m, sd = _engine(torch, dtype, impl="tcgen05")                  # every convolution must run on the tensor cores
     x = torch.from_numpy(synth.make_icn_inputs(start, B, res))
     torch.set_num_threads(os.cpu_count() or 8)
     with torch.no_grad():
@@ -156,26 +164,26 @@ def test_generator_bf16_tcgen05_vs_oracle(cuda, res, B, start):
     torch.cuda.synchronize()
     assert _lib.kernel_launches() - n0 >= 18 + 3 * 17 + 1
     err = (got.cpu() - want).abs().max().item()
-    assert err <= TOL_BF16, err
+    assert err <= tol, err
     if res == 256 and B == 1:
         gold = json.load(open(os.path.join(GOLD, "icn_golden.json")))["cases"][0]
         flat = got.cpu().flatten()
         idx = torch.linspace(0, flat.numel() - 1, 64).long()
-        assert (flat[idx] - torch.tensor(gold["out"]["samples"])).abs().max().item() <= TOL_BF16
+        assert (flat[idx] - torch.tensor(gold["out"]["samples"])).abs().max().item() <= tol
 
 
 def test_foreign_content_tensor_and_reload(cuda):
     torch = cuda
     from future_urban_scene_generation_b200 import synth
     from oracle import icn_oracle as IO
-    m, sd = _engine(torch, "bf16")
+    m, sd = _engine(torch, "fp16")
     x = torch.from_numpy(synth.make_icn_inputs(1, 1, 64)).cuda()
     c = m.enc_content(x)
     a = m.decode(c)
     b = m.decode(c.clone())                                        # no engine tag: converted from the NCHW values
-    assert (a - b).abs().max().item() <= 2e-2
+    assert (a - b).abs().max().item() <= 5e-3
     sd2 = IO.make_state_dict(7)
     m.load_state_dict(sd2, strict=True)                            # weights are re-packed after a reload
     with torch.no_grad():
         want = IO.forward(sd2, x.cpu())
-    assert (m(x).cpu() - want).abs().max().item() <= TOL_BF16
+    assert (m(x).cpu() - want).abs().max().item() <= TOL_F16
