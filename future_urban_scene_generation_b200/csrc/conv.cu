@@ -507,8 +507,8 @@ constexpr int TC_EPI_WARPS = FUSG_TC_EPI_WARPS;          // 8 or 16: warps 2.. ;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_STAGE_BYTES = 32768 / TC_EPI_WARPS;     // per-warp staging block of the staged epilogue
 constexpr int TC_BLOCK_M = 128;
-constexpr int TC_HALO_ROWS = TC_BLOCK_M + 2;                       // pixels of one halo A buffer
-constexpr int TC_HALO_BYTES = ((TC_HALO_ROWS * 128 + 1023) / 1024) * 1024;   // 128-byte rows (kc = 64), 1024-aligned
+constexpr int TC_HALO_ROWS_MAX = TC_BLOCK_M + 6;                   // pixels of one halo A buffer: 128 + ksize - 1, ksize <= 7
+constexpr int TC_HALO_BYTES = ((TC_HALO_ROWS_MAX * 128 + 1023) / 1024) * 1024;   // 128-byte rows (kc = 64), 1024-aligned
 constexpr int TC_MAX_STAGES = 16;
 
 struct alignas(64) ConvTcParams {
@@ -530,6 +530,7 @@ struct alignas(64) ConvTcParams {
     int w_resident;                 // 1: the whole weight matrix of the (single) N tile stays in shared memory
     int halo;                       // 1: sliding-window A tiles -- one TMA load of an image-row segment + 2 halo pixels serves the
                                     //    three horizontal taps (3x3, stride 1, Wt = 128, one image row per 128-row sub-tile)
+    int hks;                        // halo mode: kernel size (3; 5 or 7 for the bordered ICN layers) -- hks horizontal taps per loaded row segment
     uint32_t halo_skip;             // halo mode: bit (ky * chunks + chunk) set = all three taps of that stage have zero weights -> skipped
     int pair;                       // halo mode on CTA pairs (cta_group::2): M = 256 per MMA, each CTA holds half of the weight rows
     int pdl;                        // launched with programmatic stream serialization (griddepcontrol in the kernel)
@@ -605,7 +606,7 @@ __device__ __forceinline__ void mma_role(const ConvTcParams &p, uint8_t *sA, uin
 // The A descriptor of tap kx simply starts kx rows (kx * 128 bytes) into the buffer: the 128-byte swizzle is a
 // function of the absolute shared-memory address, so a start address that is 128- but not 1024-byte aligned
 // addresses the same swizzled rows (checked on the device by scripts/umma_shift_probe.cu).
-template <bool PAIR>
+template <bool PAIR, int KS>
 __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA, uint8_t *sB, uint64_t *full_bar, uint64_t *empty_bar,
                                               uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *w_bar, uint32_t tmem_base, int total_tiles) {
     const uint32_t block_n = (uint32_t)p.block_n;
@@ -613,13 +614,13 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
     if (pair && cluster_ctarank() != 0) return;                        // the leader CTA issues for the pair
     const uint32_t idesc = (1u << 4) | (p.fe.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((block_n >> 3) << 17) | ((uint32_t)((pair ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2u << 61);
-    const int stages = p.stages, cpt = p.chunks0 + p.chunks1, nst = 3 * cpt;
+    const int stages = p.stages, cpt = p.chunks0 + p.chunks1, nst = KS * cpt;
     const uint32_t skip = p.halo_skip;
     int st_first = 0, st_last = nst - 1;                       // first / last stage that is actually executed
     while ((skip >> st_first) & 1u) ++st_first;
     while ((skip >> st_last) & 1u) --st_last;
     const uint32_t b_kb16 = (uint32_t)p.b_bytes >> 4;
-    const uint32_t a_stage16 = (2u * TC_HALO_BYTES) >> 4, b_stage16 = 3u * b_kb16;
+    const uint32_t a_stage16 = (2u * TC_HALO_BYTES) >> 4, b_stage16 = (uint32_t)KS * b_kb16;
     const bool resident = p.w_resident != 0;
     const uint32_t sA16 = (s_addr(sA) & 0x3FFFF) >> 4, sB16 = (s_addr(sB) & 0x3FFFF) >> 4;
     const uint32_t acc_cols = 2u * block_n;
@@ -641,10 +642,9 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
                 const uint32_t a16 = sA16 + (uint32_t)stage * a_stage16;
                 // weight k-block index of (ky, kx, chunk) is (ky*3 + kx)*cpt + chunk; st = ky*cpt + chunk
                 const int ky = st / cpt, c = st - ky * cpt;
-                const uint32_t b16 = resident ? sB16 + (uint32_t)(ky * 3 * cpt + c) * b_kb16 : sB16 + (uint32_t)stage * b_stage16;
+                const uint32_t b16 = resident ? sB16 + (uint32_t)(ky * KS * cpt + c) * b_kb16 : sB16 + (uint32_t)stage * b_stage16;
                 const uint32_t b_step = resident ? (uint32_t)cpt * b_kb16 : b_kb16;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
+                auto issue_tap = [&](int kx) {
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
@@ -655,6 +655,13 @@ __device__ __forceinline__ void mma_role_halo(const ConvTcParams &p, uint8_t *sA
                             else umma_bf16(d_tmem + (uint32_t)sub * block_n, a_desc, b_desc, idesc, (st != st_first || (kx | ks) != 0) ? 1u : 0u);
                         }
                     }
+                };
+                if constexpr (KS == 3) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) issue_tap(kx);
+                } else {
+#pragma unroll 1
+                    for (int kx = 0; kx < KS; ++kx) issue_tap(kx);
                 }
                 if constexpr (PAIR) {
                     umma_commit_2cta(&empty_bar[stage]);
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     uint8_t *sA = smem;
     uint8_t *sB = smem + (p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes);
     const size_t b_region = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes
-                                         : (p.halo ? (size_t)p.stages * 3 * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
+                                         : (p.halo ? (size_t)p.stages * p.hks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + b_region);
     uint64_t *full_bar = bars, *empty_bar = bars + TC_MAX_STAGES, *tfull_bar = bars + 2 * TC_MAX_STAGES, *tempty_bar = tfull_bar + 2;
     uint64_t *w_bar = tempty_bar + 2;
@@ -747,7 +754,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             if (p.halo) {
-                const uint32_t tx_bytes = 2u * (uint32_t)(TC_HALO_ROWS * 128) + (p.w_resident ? 0u : 3u * (uint32_t)p.b_bytes);
+                const int hks = p.hks;
+                // physical coordinate of the first loaded pixel / row: pad_mode 0 -> one pixel of zero fill, pad_mode 1 -> the stored border
+                const int hoff = d.pad_mode ? d.border - d.pad : -(hks >> 1);
+                const uint32_t tx_bytes = 2u * (uint32_t)((TC_BLOCK_M + hks - 1) * 128) + (p.w_resident ? 0u : (uint32_t)hks * (uint32_t)p.b_bytes);
                 constexpr bool pair = PAIR;
                 const int rank = pair ? (int)cluster_ctarank() : 0;
                 const int tstep = pair ? (int)gridDim.x >> 1 : (int)gridDim.x, tcount = pair ? total_tiles >> 1 : total_tiles;
@@ -756,32 +766,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                     const int tx = mt & (p.tiles_x - 1), ty = (mt >> p.txs) & (p.tiles_y - 1), tb = mt >> (p.txs + p.tys);
                     const int ox0 = tx * p.Wt, oy0 = ty * p.Ht, b0 = tb * p.Bt, n0 = nt * p.block_n;
-                    for (int ky = 0; ky < 3; ++ky) {
+                    for (int ky = 0; ky < hks; ++ky) {
                         for (int c = 0; c < cpt; ++c) {
                             if ((p.halo_skip >> (ky * cpt + c)) & 1u) continue;      // all-zero weights: nothing to accumulate
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (elect_one()) {
                                 uint8_t *a_dst = sA + (size_t)stage * 2 * TC_HALO_BYTES;
-                                uint8_t *b_dst = sB + (size_t)stage * 3 * p.b_bytes;
+                                uint8_t *b_dst = sB + (size_t)stage * hks * p.b_bytes;
                                 if constexpr (PAIR) {
                                     // both CTAs' bytes land on the leader's barrier; only the leader arrives on it
                                     const uint32_t lead = dsmem_addr(s_addr(&full_bar[stage]), 0);
                                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_bytes);
                                     for (int sub = 0; sub < 2; ++sub) {
-                                        if (c < p.chunks0) tma_load_4d_2sm(a_dst + sub * TC_HALO_BYTES, &p.tmA0, lead, c * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
-                                        else tma_load_4d_2sm(a_dst + sub * TC_HALO_BYTES, &p.tmA1, lead, (c - p.chunks0) * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
+                                        if (c < p.chunks0) tma_load_4d_2sm(a_dst + sub * TC_HALO_BYTES, &p.tmA0, lead, c * 64, ox0 + hoff, oy0 + sub + ky + hoff, b0);
+                                        else tma_load_4d_2sm(a_dst + sub * TC_HALO_BYTES, &p.tmA1, lead, (c - p.chunks0) * 64, ox0 + hoff, oy0 + sub + ky + hoff, b0);
                                     }
-                                    for (int kx = 0; kx < 3; ++kx)       // this CTA's half of the weight rows
-                                        tma_load_2d_2sm(b_dst + (size_t)kx * p.b_bytes, &p.tmW, lead, ((ky * 3 + kx) * cpt + c) * 64, n0 + rank * (p.block_n >> 1));
+                                    for (int kx = 0; kx < hks; ++kx)     // this CTA's half of the weight rows
+                                        tma_load_2d_2sm(b_dst + (size_t)kx * p.b_bytes, &p.tmW, lead, ((ky * hks + kx) * cpt + c) * 64, n0 + rank * (p.block_n >> 1));
                                 } else {
                                 mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                                 for (int sub = 0; sub < 2; ++sub) {      // sub-tile = image row oy0 + sub, pixels ox0-1 .. ox0+128
-                                    if (c < p.chunks0) tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA0, &full_bar[stage], c * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
-                                    else tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA1, &full_bar[stage], (c - p.chunks0) * 64, ox0 - 1, oy0 + sub + ky - 1, b0);
+                                    if (c < p.chunks0) tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA0, &full_bar[stage], c * 64, ox0 + hoff, oy0 + sub + ky + hoff, b0);
+                                    else tma_load_4d(a_dst + sub * TC_HALO_BYTES, &p.tmA1, &full_bar[stage], (c - p.chunks0) * 64, ox0 + hoff, oy0 + sub + ky + hoff, b0);
                                 }
                                 if (!p.w_resident) {
-                                    for (int kx = 0; kx < 3; ++kx)
-                                        tma_load_2d(b_dst + (size_t)kx * p.b_bytes, &p.tmW, &full_bar[stage], ((ky * 3 + kx) * cpt + c) * 64, n0);
+                                    for (int kx = 0; kx < hks; ++kx)
+                                        tma_load_2d(b_dst + (size_t)kx * p.b_bytes, &p.tmW, &full_bar[stage], ((ky * hks + kx) * cpt + c) * 64, n0);
                                 }
                                 }
                             }
@@ -823,7 +833,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
     } else if (warp == 1) {
         // =================== MMA issuer (whole warp runs the loop; one elected lane issues) ===================
-        if (p.halo) mma_role_halo<PAIR>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+        if (p.halo) {
+            if constexpr (PAIR) mma_role_halo<true, 3>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+            else if (p.hks == 3) mma_role_halo<false, 3>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+            else if (p.hks == 5) mma_role_halo<false, 5>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+            else mma_role_halo<false, 7>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
+        }
         else if (p.kc == 64) {
             if (p.msub == 2) mma_role<4, 2>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
             else mma_role<4, 1>(p, sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar, w_bar, tmem_base, total_tiles);
@@ -1295,7 +1310,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.kb_local = p.num_kblocks / p.ksplit;
     // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
     static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
-    const bool want_staged = p.ksplit == 1 && staged_on && (d.ksize >= 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
+    bool want_staged = p.ksplit == 1 && staged_on && (d.ksize >= 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
     const int smem_budget = (want_staged ? 168 : 200) * 1024 - (p.ksplit > 1 ? p.block_n * TC_BLOCK_M * 4 : 0);
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.ksplit == 1 && p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
@@ -1318,23 +1333,28 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     static const int halo_on = getenv("FUSG_NO_HALO") ? 0 : 1;
     static const int halo_nmax = getenv("FUSG_HALO_NMAX") ? atoi(getenv("FUSG_HALO_NMAX")) : 128;
     p.halo = 0;
-    if (halo_on && !d.pad_mode && p.ksplit == 1 && d.ksize == 3 && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
+    p.hks = d.ksize;
+    const bool halo_ks = d.pad_mode ? (d.ksize == 3 || d.ksize == 5 || d.ksize == 7) : d.ksize == 3;
+    if (halo_on && p.ksplit == 1 && halo_ks && d.stride == 1 && p.kc == 64 && p.msub == 2 && p.Wt == 128 && p.Ht == 2 && p.Bt == 1 &&
         p.block_n <= halo_nmax) {
         // CTA pairs (cta_group::2) for the 128-wide layers: each CTA keeps half of the weight rows, which makes room for
         // a third pipeline stage, and every MMA reads a quarter less shared memory
         static const int pair_on = getenv("FUSG_NO_PAIR2") ? 0 : 1;
         const int tiles_all = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
-        p.pair = (pair_on && p.block_n == 128 && p.n_tiles == 1 && !p.w_resident && tiles_all % 2 == 0 && tiles_all >= 4 * num_sms) ? 1 : 0;
+        p.pair = (pair_on && d.ksize == 3 && p.block_n == 128 && p.n_tiles == 1 && !p.w_resident && tiles_all % 2 == 0 && tiles_all >= 4 * num_sms) ? 1 : 0;
         if (p.pair) p.b_bytes = (p.block_n / 2) * p.kc * 2;                 // half of the weight rows per CTA and k-block
+        const int stage_bytes = 2 * TC_HALO_BYTES + (p.w_resident ? 0 : d.ksize * p.b_bytes);
+        // wide kernels (5x5 / 7x7): a third pipeline stage is worth more than the staged epilogue's 32 KB
+        static const int deep_pipe = getenv("FUSG_HALO_KEEP_STAGED") ? 0 : 1;
+        if (deep_pipe && d.ksize > 3 && want_staged && (192 * 1024) / stage_bytes < 3 && (222 * 1024) / stage_bytes >= 3) want_staged = false;
         const int budget = (want_staged ? 192 : 222) * 1024 - (p.w_resident ? p.num_kblocks * p.b_bytes : 0);
-        const int stage_bytes = 2 * TC_HALO_BYTES + (p.w_resident ? 0 : 3 * p.b_bytes);
         int st = budget / stage_bytes;
         if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
         if (st >= 2) { p.halo = 1; p.stages = st; p.group = 1; }
         else if (p.pair) return FUSG_ERR_UNSUPPORTED;
     }
     p.halo_skip = 0;
-    if (p.halo && d.zero_kblocks) {
+    if (p.halo && d.zero_kblocks && d.ksize == 3) {
         const int cpt = p.chunks0 + p.chunks1;
         for (int ky = 0; ky < 3 && 9 * cpt <= 64; ++ky)
             for (int c = 0; c < cpt; ++c) {
@@ -1387,7 +1407,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         cuuint64_t dims[4] = {(cuuint64_t)c, Wp, Hp, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, Wp * pitch * 2, Hp * Wp * pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.Wt * d.stride), (cuuint32_t)(p.Ht * d.stride), (cuuint32_t)p.Bt};
-        if (p.halo) { box[1] = TC_HALO_ROWS; box[2] = 1; box[3] = 1; }
+        if (p.halo) { box[1] = (cuuint32_t)(TC_BLOCK_M + d.ksize - 1); box[2] = 1; box[3] = 1; }
         cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
         return enc(tm, d.dtype == FUSG_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1405,7 +1425,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             return FUSG_ERR_UNSUPPORTED;
     }
     const size_t pipe_a = p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes;
-    const size_t pipe_b = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (p.halo ? (size_t)p.stages * 3 * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
+    const size_t pipe_b = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (p.halo ? (size_t)p.stages * d.ksize * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
     const size_t smem = pipe_a + pipe_b +
                         1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
     static bool attr_set = false;

@@ -160,36 +160,41 @@ __global__ void __launch_bounds__(256) k_norm_finalize(const float *__restrict__
     }
 }
 
-// ---- apply: one thread per (output pixel, N-channel group) -----------------------------------------------------------
+// ---- apply: one CTA per output row (b, Y); threads stride over (X, N-channel group) with 32-bit index math ---------
 template <typename T>
 __global__ void __launch_bounds__(256) k_norm_apply(const T *__restrict__ x, const float *__restrict__ ss, const T *__restrict__ residual, int rb,
-                                                    T *__restrict__ out, int H, int W, int C, int relu, int up, int border, size_t total) {
+                                                    T *__restrict__ out, int H, int W, int C, int relu, int up, int border) {
     constexpr int N = Vec<T>::N;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    extern __shared__ float2 s_ss[];                      // this sample's C scale/shift pairs
+    const int Y = blockIdx.x, b = blockIdx.y;
     const int groups = C / N;
-    const int g = (int)(i % groups);
-    const size_t pix = i / groups;
-    const int Hu = H * up, Wu = W * up, Hp = Hu + 2 * border, Wp = Wu + 2 * border;
-    const size_t b = pix / ((size_t)Hp * Wp);
-    const int r = (int)(pix - b * (size_t)Hp * Wp), Y = r / Wp, X = r - Y * Wp;
-    const int sy = reflect(Y - border, Hu) / up, sx = reflect(X - border, Wu) / up;
-    float v[N];
-    Vec<T>::load(x + ((b * H + sy) * (size_t)W + sx) * C + g * N, v);
-    const float2 *sp = reinterpret_cast<const float2 *>(ss) + b * C + g * N;
+    const int Hu = H * up, Wu = W * up, Wp = Wu + 2 * border, Hp = Hu + 2 * border;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_ss[c] = reinterpret_cast<const float2 *>(ss)[(size_t)b * C + c];
+    __syncthreads();
+    const int sy = reflect(Y - border, Hu) / up;
+    const T *xrow = x + ((size_t)b * H + sy) * (size_t)W * C;
+    const T *rrow = residual ? residual + (((size_t)b * (H + 2 * rb) + sy + rb) * (size_t)(W + 2 * rb) + rb) * C : nullptr;
+    T *orow = out + ((size_t)b * Hp + Y) * (size_t)Wp * C;
+    const int total = Wp * groups;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int X = i / groups, g = i - X * groups;
+        const int sx = reflect(X - border, Wu) / up;
+        float v[N];
+        Vec<T>::load(xrow + (size_t)sx * C + g * N, v);
 #pragma unroll
-    for (int k = 0; k < N; ++k) { const float2 t = __ldg(sp + k); v[k] = v[k] * t.x + t.y; }
-    if (residual) {
-        float rv[N];
-        Vec<T>::load(residual + ((b * (H + 2 * rb) + sy + rb) * (size_t)(W + 2 * rb) + sx + rb) * C + g * N, rv);
+        for (int k = 0; k < N; ++k) { const float2 t = s_ss[g * N + k]; v[k] = v[k] * t.x + t.y; }
+        if (rrow) {
+            float rv[N];
+            Vec<T>::load(rrow + (size_t)sx * C + g * N, rv);
 #pragma unroll
-        for (int k = 0; k < N; ++k) v[k] += rv[k];
+            for (int k = 0; k < N; ++k) v[k] += rv[k];
+        }
+        if (relu) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+        Vec<T>::store(orow + (size_t)i * N, v);
     }
-    if (relu) {
-#pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = fmaxf(v[k], 0.f);
-    }
-    Vec<T>::store(out + pix * C + g * N, v);
 }
 
 }  // namespace fusg_icn
@@ -236,15 +241,15 @@ extern "C" int fusg_norm_apply(const void *x, const float *ss, const void *resid
     if (!x || !ss || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || border < 0 || rb < 0) return FUSG_ERR_ARG;
     if (C % 8 != 0 || (up != 1 && up != 2) || border >= H * up || border >= W * up) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = dtype == FUSG_DTYPE_F32 ? 4 : 8;
-    const size_t total = (size_t)B * (H * up + 2 * border) * (W * up + 2 * border) * (C / N);
-    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (B > 65535) return FUSG_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)(H * up + 2 * border), (unsigned)B);
+    const size_t smem = (size_t)C * sizeof(float2);
     if (dtype == FUSG_DTYPE_BF16)
-        k_norm_apply<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, ss, (const __nv_bfloat16 *)residual, rb, (__nv_bfloat16 *)out, H, W, C, relu, up, border, total);
+        k_norm_apply<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x, ss, (const __nv_bfloat16 *)residual, rb, (__nv_bfloat16 *)out, H, W, C, relu, up, border);
     else if (dtype == FUSG_DTYPE_F16)
-        k_norm_apply<__half><<<grid, 256, 0, st>>>((const __half *)x, ss, (const __half *)residual, rb, (__half *)out, H, W, C, relu, up, border, total);
+        k_norm_apply<__half><<<grid, 256, smem, st>>>((const __half *)x, ss, (const __half *)residual, rb, (__half *)out, H, W, C, relu, up, border);
     else
-        k_norm_apply<float><<<grid, 256, 0, st>>>((const float *)x, ss, (const float *)residual, rb, (float *)out, H, W, C, relu, up, border, total);
+        k_norm_apply<float><<<grid, 256, smem, st>>>((const float *)x, ss, (const float *)residual, rb, (float *)out, H, W, C, relu, up, border);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
