@@ -175,3 +175,29 @@ def test_large_batch_solver_path_matches_small_batch(cuda):
         assert torch.equal(big.vis[sl], small.vis)
         assert torch.equal(big.H12[sl].view(torch.int64), small.H12.view(torch.int64))
         assert torch.equal(big.warped[sl], small.warped)
+
+
+def test_large_batch_overwrites_stale_output(cuda):
+    """The output contract is "fully written": every byte of a pre-dirtied output buffer must come out right on the
+    large-batch (list) path, call after call -- the planes nobody warps into are zero-filled by the kernel itself."""
+    from future_urban_scene_generation_b200.warp_learn import warp_batch
+    from future_urban_scene_generation_b200.warp_learn.batch import WarpResult
+    torch = cuda
+    U, R = 64, 30                                   # 1920 crops -> 9600 (crop, plane) tasks: the list path
+    batch = synth.make_warp_batch(500, U)
+    small = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"])
+    big_in = {k: np.concatenate([v] * R, 0) for k, v in batch.items()}
+    B = U * R
+    out = WarpResult(warped=torch.full((B, 5, 256, 256, 3), 0xCD, dtype=torch.uint8, device="cuda"),
+                     vis=torch.empty((B, 2, 7), dtype=torch.uint8, device="cuda"),
+                     plane_j=torch.empty((B, 5), dtype=torch.int8, device="cuda"),
+                     H12=torch.empty((B, 5, 3, 3), dtype=torch.float64, device="cuda"))
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in big_in.items()}
+    for it in range(2):
+        warp_batch(dev["src"], dev["src_kp"], dev["dst_kp"], dev["K"], dev["E_src"], dev["E_dst"], dev["kp3d"], out=out)
+        torch.cuda.synchronize()
+        for r in (0, 11, R - 1):
+            sl = slice(r * U, (r + 1) * U)
+            assert torch.equal(out.warped[sl], small.warped), (it, r)
+            assert torch.equal(out.plane_j[sl], small.plane_j)
+        out.warped.fill_(0x5A)
