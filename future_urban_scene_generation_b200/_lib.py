@@ -30,6 +30,8 @@ def _load():
         "fusg_warp_workspace_bytes": ([i], sz),
         "fusg_warp_workspace_bytes_hw": ([i, i, i], sz),
         "fusg_warp_fused": ([vp] * 11 + [vp, sz, i, i, i, vp], i),
+        "fusg_warp_fused_traj": ([vp] * 12 + [vp, sz, i, i, i, vp], i),
+        "fusg_step_keypoints": ([vp] * 10 + [i, i, i, vp], i),
         "fusg_visibility": ([vp] * 6 + [i, i, i, vp], i),
         "fusg_get_planes": ([vp] * 3 + [i, i, i, vp], i),
         "fusg_find_homography": ([vp, vp, i, vp, vp, i, vp], i),

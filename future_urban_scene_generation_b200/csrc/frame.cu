@@ -336,3 +336,53 @@ extern "C" int fusg_paste_back(uint8_t *frames, const uint8_t *crops, const uint
     fusg_count_launch(2);
     return fusg_check_launch();
 }
+
+// ================================================================================================
+// Per-step keypoint kinematics of the trajectory loop: for item n = (vehicle, future step)
+//   moved = v @ z_rot(theta) + tr            trajectory_inference.py:359-361 (z_rot is a float32 matrix, utils/geometry.py:80-113)
+//   kp2d  = cv2.projectPoints(moved, rvec, tvec, K, 0)                        trajectory_inference.py:363-367
+//   verts = np.int32((kp2d / (w,h)) * (w,h))      warp_learn/vehicle_utils.py:24-26, warp_learn/planes_utils.py:22-27
+// i.e. exactly the kp3d / dst_kp inputs fusg_warp_fused_traj takes for that item.  Bit-exact restatement (oracle/
+// kinematics_oracle.py): numpy's BLAS evaluates v @ M as the FMA chain fma(v2, M2c, fma(v1, M1c, v0*M0c)); projectPoints
+// with zero distortion is R X + t left to right, z -> 1/z, x*fx + cx.  This file is compiled with -fmad=false, so only the
+// explicit fma() calls fuse.
+// ================================================================================================
+__global__ void __launch_bounds__(128) k_step_keypoints(const double *__restrict__ kp3d, const int32_t *__restrict__ vehicle,
+                                                        const float *__restrict__ rot, const double *__restrict__ tr, const double *__restrict__ R,
+                                                        const double *__restrict__ t, const double *__restrict__ K, double *__restrict__ kp3d_out,
+                                                        double *__restrict__ kp2d_out, int32_t *__restrict__ verts, int N, int H, int W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;           // over N * 12
+    if (i >= N * 12) return;
+    const int n = i / 12, k = i - n * 12, v = vehicle[n];
+    const double *p = kp3d + ((size_t)v * 12 + k) * 3;
+    const float *M = rot + (size_t)n * 9;
+    double m[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) m[c] = fma(p[2], (double)M[6 + c], fma(p[1], (double)M[3 + c], p[0] * (double)M[c])) + tr[(size_t)n * 3 + c];
+    const double *Rv = R + (size_t)v * 9, *tv = t + (size_t)v * 3, *Kv = K + (size_t)v * 9;
+    double x = Rv[0] * m[0] + Rv[1] * m[1] + Rv[2] * m[2] + tv[0];
+    double y = Rv[3] * m[0] + Rv[4] * m[1] + Rv[5] * m[2] + tv[1];
+    double z = Rv[6] * m[0] + Rv[7] * m[1] + Rv[8] * m[2] + tv[2];
+    z = z != 0.0 ? 1. / z : 1.;
+    x *= z;
+    y *= z;
+    const double u = x * Kv[0] + Kv[2], w = y * Kv[4] + Kv[5];
+    kp3d_out[(size_t)i * 3] = m[0]; kp3d_out[(size_t)i * 3 + 1] = m[1]; kp3d_out[(size_t)i * 3 + 2] = m[2];
+    kp2d_out[(size_t)i * 2] = u; kp2d_out[(size_t)i * 2 + 1] = w;
+    // normalise by the frame size, scale back, truncate (far-out values are clamped; the warp stage rejects them anyway)
+    double px = (u / (double)W) * (double)W, py = (w / (double)H) * (double)H;
+    px = fmin(fmax(px, -1.0e9), 1.0e9);
+    py = fmin(fmax(py, -1.0e9), 1.0e9);
+    verts[(size_t)i * 2] = (int)px;
+    verts[(size_t)i * 2 + 1] = (int)py;
+}
+
+extern "C" int fusg_step_keypoints(const double *kp3d, const int32_t *vehicle, const float *rot, const double *tr, const double *R,
+                                   const double *t, const double *K, double *kp3d_out, double *kp2d_out, int32_t *verts, int N, int H, int W,
+                                   void *stream) {
+    if (!kp3d || !vehicle || !rot || !tr || !R || !t || !K || !kp3d_out || !kp2d_out || !verts || N <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_step_keypoints<<<(N * 12 + 127) / 128, 128, 0, st>>>(kp3d, vehicle, rot, tr, R, t, K, kp3d_out, kp2d_out, verts, N, H, W);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}

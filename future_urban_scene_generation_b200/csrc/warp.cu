@@ -38,10 +38,11 @@ struct VisShared {
 constexpr int VIS_WARPS = 4;     // poses per CTA (one warp each; no block-level barriers)
 
 // grid.x = ceil(poses / VIS_WARPS).  Pose g reads K[b], kp3d[b], and E0/E1[b] (fused src/dst layout, b = g/2)
-// when E1 != nullptr, else K[g], E0[g], kp3d[g].
+// when E1 != nullptr, else K[g], E0[g], kp3d[g].  kp3d1 (fused layout only, may be NULL): the destination pose's own
+// keypoints -- the trajectory loop moves the CAD keypoints instead of the camera (trajectory_inference.py:359-376).
 __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__restrict__ K, const double *__restrict__ E0,
                                                                const double *__restrict__ E1, const double *__restrict__ kp3d,
-                                                               uint8_t *__restrict__ vis, int32_t *__restrict__ pts,
+                                                               const double *__restrict__ kp3d1, uint8_t *__restrict__ vis, int32_t *__restrict__ pts,
                                                                int32_t *__restrict__ areas, int n_poses, int H, int W) {
     __shared__ VisShared sm_all[VIS_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
     const double *Kp, *Ep, *Xp;
     if (E1) {
         const int b = g >> 1;
-        Kp = K + 9 * b; Xp = kp3d + 36 * b;
+        Kp = K + 9 * b; Xp = (((g & 1) && kp3d1) ? kp3d1 : kp3d) + 36 * b;
         Ep = ((g & 1) ? E1 : E0) + 12 * b;
     } else {
         Kp = K + 9 * g; Xp = kp3d + 36 * g; Ep = E0 + 12 * g;
@@ -686,7 +687,7 @@ extern "C" int fusg_visibility(const double *K, const double *E, const double *k
                                int32_t *areas, int B, int H, int W, void *stream) {
     if (!K || !E || !kp3d || !vis || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    k_visibility<<<(B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E, nullptr, kp3d, vis, pts, areas, B, H, W);
+    k_visibility<<<(B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E, nullptr, kp3d, nullptr, vis, pts, areas, B, H, W);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
@@ -718,10 +719,10 @@ extern "C" int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8
     return fusg_check_launch();
 }
 
-extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp, const double *K,
-                               const double *E_src, const double *E_dst, const double *kp3d, uint8_t *warped, uint8_t *vis,
-                               int8_t *plane_j, double *H12, void *workspace, size_t workspace_bytes, int B, int H, int W,
-                               void *stream) {
+static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp, const double *K,
+                           const double *E_src, const double *E_dst, const double *kp3d, const double *kp3d_dst, uint8_t *warped, uint8_t *vis,
+                           int8_t *plane_j, double *H12, void *workspace, size_t workspace_bytes, int B, int H, int W,
+                           void *stream) {
     if (!src || !src_kp || !dst_kp || !K || !E_src || !E_dst || !kp3d || !warped || !vis || !plane_j || !workspace) return FUSG_ERR_ARG;
     if (B <= 0) return FUSG_ERR_ARG;
     if (H < 8 || W < 8 || H > 65535 || B > 65535) return FUSG_ERR_UNSUPPORTED;
@@ -736,7 +737,7 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
             return fusg_check_launch();
         attr_set = true;
     }
-    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, vis, nullptr, nullptr, 2 * B, H, W);
+    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, kp3d_dst, vis, nullptr, nullptr, 2 * B, H, W);
     // small batches: latency matters -> one warp per solve; large batches: throughput -> one thread per solve
     if (B * N_TEX <= 8192) k_homography<<<(B * N_TEX + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
     else {
@@ -768,4 +769,19 @@ extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const 
         fusg_count_launch(4);
     }
     return fusg_check_launch();
+}
+
+extern "C" int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp, const double *K,
+                               const double *E_src, const double *E_dst, const double *kp3d, uint8_t *warped, uint8_t *vis,
+                               int8_t *plane_j, double *H12, void *workspace, size_t workspace_bytes, int B, int H, int W,
+                               void *stream) {
+    return warp_fused_impl(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, nullptr, warped, vis, plane_j, H12, workspace, workspace_bytes, B, H, W, stream);
+}
+
+extern "C" int fusg_warp_fused_traj(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp, const double *K,
+                                    const double *E_src, const double *E_dst, const double *kp3d_src, const double *kp3d_dst,
+                                    uint8_t *warped, uint8_t *vis, int8_t *plane_j, double *H12, void *workspace, size_t workspace_bytes,
+                                    int B, int H, int W, void *stream) {
+    if (!kp3d_dst) return FUSG_ERR_ARG;
+    return warp_fused_impl(src, src_kp, dst_kp, K, E_src, E_dst, kp3d_src, kp3d_dst, warped, vis, plane_j, H12, workspace, workspace_bytes, B, H, W, stream);
 }

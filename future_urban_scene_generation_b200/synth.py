@@ -199,3 +199,23 @@ def make_pack_case(idx: int, frame_hw=(1080, 1920)):
         n[max(hy - 6, 0):hy + 6, max(hx - 9, 0):hx + 9] = 0
         return n
     return np.logical_not(veh), sketch(0), sketch(1)
+
+
+def make_trajectory_case(idx: int, steps: int = 20, h: int = 720, w: int = 1280):
+    """One vehicle of the trajectory loop (trajectory_inference.py:255-367): CAD keypoints, a camera (K, R, t with
+    X_cam = R X + t) that sees the vehicle, and `steps + 1` ground positions in metres (`meter_coords`, the output of
+    trajectories_to_meters) along a gently curving path; every third vehicle turns sharply enough to trip the
+    +-20 degree gates.  R is a plain look-at rotation; callers that need OpenCV's Rodrigues round trip apply it themselves."""
+    rng = np.random.default_rng(9100 + idx)
+    kp3d = cad_keypoints(idx % 10)
+    K = np.array([[1100.0 + 20 * (idx % 5), 0, w / 2.0], [0, 1100.0 + 20 * (idx % 5), h / 2.0], [0, 0, 1.0]], np.float64)
+    E = look_at_extrinsic(rng.uniform(0, 360), rng.uniform(10, 35), rng.uniform(14, 22))
+    heading = rng.uniform(-np.pi, np.pi)
+    turn = rng.uniform(-0.02, 0.02) if idx % 3 else rng.uniform(0.08, 0.16) * rng.choice([-1.0, 1.0])
+    pos = [np.array([rng.uniform(-30, 30), rng.uniform(-30, 30)])]
+    for n in range(steps):
+        heading += turn + rng.normal(0, 0.01)
+        if idx % 3 == 1 and n == steps // 2:
+            heading += 0.6                                    # one abrupt change of direction: the "instant theta" gate
+        pos.append(pos[-1] + rng.uniform(0.3, 0.7) * np.array([np.cos(heading), np.sin(heading)]))
+    return dict(kp3d=kp3d, K=K, R=E[:3, :3].copy(), t=E[:3, 3].copy(), meter_coords=np.stack(pos), h=h, w=w)

@@ -28,10 +28,12 @@ def _dev(torch, a, dtype, shape, device):
     return t.contiguous()
 
 
-def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None) -> WarpResult:
+def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None, kp3d_dst=None) -> WarpResult:
     """src (B,H,W,3) u8; src_kp/dst_kp (B,12,2) i32 plane vertices (_KP_NAMES order, already
     truncated as in planes_utils.py:22-27); K (B,3,3) or (3,3); E_* (B,3,4) or (B,4,4); kp3d (B,12,3).
-    numpy arrays or torch tensors on host or device.  Asynchronous on the current CUDA stream."""
+    numpy arrays or torch tensors on host or device.  Asynchronous on the current CUDA stream.
+    kp3d_dst (B,12,3), optional: the destination pose's own keypoints (trajectory loop: same camera, moved keypoints,
+    trajectory_inference.py:359-379 -- see kinematics.step_keypoints_batch); default: kp3d for both poses."""
     torch = _lib.require_cuda()
     device = torch.device(device if device is not None else "cuda")
     src = _dev(torch, src, torch.uint8, src.shape, device)
@@ -62,11 +64,17 @@ def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None
     L = _lib.lib()
     ws_bytes = L.fusg_warp_workspace_bytes_hw(B, H, W)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+    Xd = _dev(torch, kp3d_dst, torch.float64, (B, 12, 3), device) if kp3d_dst is not None else None
     with torch.cuda.device(device):
-        rc = L.fusg_warp_fused(_lib.ptr(src), _lib.ptr(skp), _lib.ptr(dkp), _lib.ptr(Kt), _lib.ptr(Es), _lib.ptr(Ed),
-                               _lib.ptr(X), _lib.ptr(out.warped), _lib.ptr(out.vis), _lib.ptr(out.plane_j),
-                               _lib.ptr(out.H12), _lib.ptr(ws), ws_bytes, B, H, W, _lib.stream_ptr(torch))
+        if Xd is None:
+            rc = L.fusg_warp_fused(_lib.ptr(src), _lib.ptr(skp), _lib.ptr(dkp), _lib.ptr(Kt), _lib.ptr(Es), _lib.ptr(Ed),
+                                   _lib.ptr(X), _lib.ptr(out.warped), _lib.ptr(out.vis), _lib.ptr(out.plane_j),
+                                   _lib.ptr(out.H12), _lib.ptr(ws), ws_bytes, B, H, W, _lib.stream_ptr(torch))
+        else:
+            rc = L.fusg_warp_fused_traj(_lib.ptr(src), _lib.ptr(skp), _lib.ptr(dkp), _lib.ptr(Kt), _lib.ptr(Es), _lib.ptr(Ed),
+                                        _lib.ptr(X), _lib.ptr(Xd), _lib.ptr(out.warped), _lib.ptr(out.vis), _lib.ptr(out.plane_j),
+                                        _lib.ptr(out.H12), _lib.ptr(ws), ws_bytes, B, H, W, _lib.stream_ptr(torch))
     _lib.check(rc, "fusg_warp_fused")
     # keep inputs/workspace alive until the stream has consumed them
-    out._keep = (src, skp, dkp, Kt, Es, Ed, X, ws)
+    out._keep = (src, skp, dkp, Kt, Es, Ed, X, Xd, ws)
     return out

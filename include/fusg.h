@@ -74,6 +74,29 @@ int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const int32_t *ds
                     int B, int H, int W, void *stream);
 
 /*
+ * The same call for the trajectory loop (trajectory_inference.py:359-379), where the destination pose is the SAME camera
+ * looking at MOVED keypoints: the destination visibility is computed from kp3d_dst [B,12,3] (e.g. fusg_step_keypoints'
+ * output) instead of kp3d_src.  E_dst is normally E_src there.
+ */
+int fusg_warp_fused_traj(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp,
+                         const double *K, const double *E_src, const double *E_dst, const double *kp3d_src, const double *kp3d_dst,
+                         uint8_t *warped, uint8_t *vis, int8_t *plane_j, double *H12,
+                         void *workspace, size_t workspace_bytes, int B, int H, int W, void *stream);
+
+/*
+ * Per-step keypoint kinematics of the trajectory loop for N (vehicle, future step) items:
+ *   moved = v @ z_rot(theta) + tr                         trajectory_inference.py:359-361, utils/geometry.py:80-113
+ *   kp2d  = cv2.projectPoints(moved, rvec, tvec, K, 0)    trajectory_inference.py:363-367
+ *   verts = np.int32((kp2d / (W,H)) * (W,H))              warp_learn/vehicle_utils.py:24-26, warp_learn/planes_utils.py:22-27
+ *   kp3d [V,12,3] f64 CAD keypoints per vehicle; vehicle [N] i32 index into the per-vehicle arrays; rot [N,3,3] f32 = z_rot(theta)
+ *   (the reference builds it in float32); tr [N,3] f64; R [V,3,3] f64 = cv2.Rodrigues(rvec); t [V,3]; K [V,3,3]
+ *   -> kp3d_out [N,12,3] f64, kp2d_out [N,12,2] f64, verts [N,12,2] i32: the kp3d_dst / dst_kp inputs of fusg_warp_fused_traj.
+ * theta / tr per step (the +-20 degree gates of trajectory_inference.py:267-298) are a few scalars per item and stay on the host.
+ */
+int fusg_step_keypoints(const double *kp3d, const int32_t *vehicle, const float *rot, const double *tr, const double *R, const double *t,
+                        const double *K, double *kp3d_out, double *kp2d_out, int32_t *verts, int N, int H, int W, void *stream);
+
+/*
  * Visibility only (compute_visibility, online_visibility.py:105-150) for B poses.
  *   K [B,3,3], E [B,3,4], kp3d [B,12,3] f64 -> vis [B,7] u8, pts [B,12,2] i32 (int()-truncated
  *   projections; may be NULL), areas [B,7,2] i32 (absolute, occluded; may be NULL).

@@ -108,6 +108,25 @@ def test_icn_module_checkpoint_contract():
         m(torch.zeros(1, 21, 30, 30))
 
 
+def test_kinematics_host_mirror():
+    """trajectory_poses mirrors trajectory_inference.py:258-298: rotation always by theta, translation gated at +-20 degrees."""
+    from future_urban_scene_generation_b200 import kinematics as KM
+    mc = np.array([[0, 0], [1, 0], [2, 0], [3, 0.1], [4, 0.1], [5, 0.2]], np.float64)
+    theta, tr, rot = KM.trajectory_poses(mc)
+    assert theta.shape == (5,) and tr.shape == (5, 3) and rot.shape == (5, 3, 3) and rot.dtype == np.float32
+    assert np.allclose(np.linalg.norm(tr, axis=1), np.linalg.norm(mc[1:] - mc[0], axis=1), rtol=1e-6)
+    assert np.array_equal(rot[2], KM.z_rot(theta[2])) and np.all(tr[:, 2] == 0)
+    # a hairpin: heading differs from the start heading by > 20 degrees -> translation along -y unrotated (z_rot(0))
+    hair = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float64)
+    th, tr2, _ = KM.trajectory_poses(hair)
+    assert abs(np.degrees(th[-1])) > 20 and tr2[-1, 0] == 0 and tr2[-1, 1] == -np.linalg.norm(hair[3] - hair[0])
+    with pytest.raises(ValueError):
+        KM.trajectory_poses(np.zeros((1, 2)))
+    L = __import__("future_urban_scene_generation_b200._lib", fromlist=["lib"]).lib()
+    assert L.fusg_step_keypoints(None, None, None, None, None, None, None, None, None, None, 1, 256, 256, None) == -1
+    assert L.fusg_norm_stats(None, None, 1, 1, 8, 1, 0, None) == -1
+
+
 def test_warp_mirror_surface_and_constants():
     from future_urban_scene_generation_b200.warp_learn import online_visibility as ov, planes_utils as pu
     assert list(ov.pascal_texture_planes['car'].keys()) == ['left', 'right', 'roof', 'front', 'back']

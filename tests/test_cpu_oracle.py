@@ -186,6 +186,31 @@ def test_icn_oracle_matches_golden_fingerprint():
         assert -1.0 <= case["out_range"][0] and case["out_range"][1] <= 1.0
 
 
+def test_kinematics_oracle_matches_reference_goldens():
+    """oracle/kinematics_oracle.py vs the reference lines run with numpy + cv2.projectPoints in the build container
+    (scripts/make_golden_kinematics.py): SHA-256 of the moved keypoints, their projections and the int32 plane vertices."""
+    from oracle import kinematics_oracle as KO
+    from future_urban_scene_generation_b200 import kinematics as KM
+    gold = json.load(open(os.path.join(GOLD, "kinematics_golden.json")))
+    tripped = 0
+    for g in gold["cases"]:
+        case = synth.make_trajectory_case(g["idx"])
+        R = np.array([float.fromhex(v) for v in g["R_cv_hex"]]).reshape(3, 3)
+        theta, tr, rot = KO.trajectory_poses(case["meter_coords"])
+        theta2, tr2, rot2 = KM.trajectory_poses(case["meter_coords"])          # the product's host-side mirror
+        assert np.array_equal(theta, theta2) and np.array_equal(tr, tr2) and np.array_equal(rot, rot2)
+        hm, h2, hv = hashlib.sha256(), hashlib.sha256(), hashlib.sha256()
+        for s in range(g["steps"]):
+            moved, kp2d, verts = KO.step(case["kp3d"], rot[s], tr[s], R, case["t"], case["K"], case["w"], case["h"])
+            hm.update(moved.tobytes()); h2.update(kp2d.tobytes()); hv.update(verts.tobytes())
+            if s == 0:
+                assert verts.tolist() == g["first_verts"]
+        assert hm.hexdigest() == g["sha256_moved"] and h2.hexdigest() == g["sha256_kp2d"] and hv.hexdigest() == g["sha256_verts"], g["idx"]
+        assert [float(v).hex() for v in kp2d.flatten()] == g["last_kp2d_hex"]
+        tripped += g["translation_gated_steps"]
+    assert tripped >= 5                                    # the +-20 degree gates are exercised
+
+
 def test_space_depth_permutations_are_block_major():
     import torch
     from oracle import vunet_oracle as VO
