@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(128) k_conv_direct(const __grid_constant__ fus
     // pad_mode 1: the padding values live in the input tensor's own border (fusg.h)
     const int pad = d.pad_mode ? d.pad : d.ksize >> 1, bd = d.pad_mode ? d.border : 0, ctot = d.c0 + d.c1, taps = d.ksize * d.ksize;
     const int Hp = d.H + 2 * bd, Wp = d.W + 2 * bd;
+    const int cph0 = d.cphys0 ? d.cphys0 : d.c0, cph1 = d.cphys1 ? d.cphys1 : d.c1;   // channels beyond these read as zero
     const T *wbase = reinterpret_cast<const T *>(d.weight);
     float acc[16];
 #pragma unroll
@@ -214,8 +215,8 @@ __global__ void __launch_bounds__(128) k_conv_direct(const __grid_constant__ fus
                 for (int c = 0; c < cn; ++c) {
                     const int cc = c0 + c;
                     float a;
-                    if (cc < d.c0) a = to_f<T>(reinterpret_cast<const T *>(d.in0)[(((size_t)b * Hp + iy) * Wp + ix) * d.pitch0 + cc]);
-                    else a = to_f<T>(reinterpret_cast<const T *>(d.in1)[(((size_t)b * Hp + iy) * Wp + ix) * d.pitch1 + (cc - d.c0)]);
+                    if (cc < d.c0) a = cc < cph0 ? to_f<T>(reinterpret_cast<const T *>(d.in0)[(((size_t)b * Hp + iy) * Wp + ix) * d.pitch0 + cc]) : 0.f;
+                    else a = cc - d.c0 < cph1 ? to_f<T>(reinterpret_cast<const T *>(d.in1)[(((size_t)b * Hp + iy) * Wp + ix) * d.pitch1 + (cc - d.c0)]) : 0.f;
 #pragma unroll
                     for (int n = 0; n < 16; ++n) acc[n] = fmaf(a, s_w[n][c], acc[n]);
                 }
@@ -1401,6 +1402,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     }
     PFN_encodeTiled enc = get_encode();
     const CUtensorMapSwizzle sw = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    // c = channels the tensor really holds: a k-block box that reaches beyond them is zero-filled by TMA
     auto encodeA = [&](CUtensorMap *tm, const void *ptr, int c, int pitch) -> bool {
         const int bd = d.pad_mode ? d.border : 0;
         const cuuint64_t Wp = (cuuint64_t)(d.W + 2 * bd), Hp = (cuuint64_t)(d.H + 2 * bd);
@@ -1412,8 +1414,8 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
         return enc(tm, d.dtype == FUSG_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
-    if (!encodeA(&p.tmA0, d.in0, d.c0, d.pitch0)) return FUSG_ERR_UNSUPPORTED;
-    if (d.in1 && !encodeA(&p.tmA1, d.in1, d.c1, d.pitch1)) return FUSG_ERR_UNSUPPORTED;
+    if (!encodeA(&p.tmA0, d.in0, d.cphys0 ? d.cphys0 : d.c0, d.pitch0)) return FUSG_ERR_UNSUPPORTED;
+    if (d.in1 && !encodeA(&p.tmA1, d.in1, d.cphys1 ? d.cphys1 : d.c1, d.pitch1)) return FUSG_ERR_UNSUPPORTED;
     {
         const int ktot = taps * (d.c0 + d.c1);
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.cout_pad};
@@ -1485,6 +1487,8 @@ extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
         if (d.pad_mode != 1 || d.ksize < 1 || d.ksize > 7 || d.pad < 0 || d.border < d.pad) return FUSG_ERR_UNSUPPORTED;
     }
     if (d.in1 == nullptr && d.c1 != 0) return FUSG_ERR_ARG;
+    if (d.cphys0 < 0 || d.cphys0 > d.c0 || d.cphys0 % 8 || d.cphys1 < 0 || d.cphys1 > d.c1 || d.cphys1 % 8) return FUSG_ERR_ARG;
+    if ((d.cphys0 && d.pitch0 < d.cphys0) || (d.cphys1 && d.pitch1 < d.cphys1)) return FUSG_ERR_ARG;
     if (d.dtype != FUSG_DTYPE_BF16 && d.dtype != FUSG_DTYPE_F32 && d.dtype != FUSG_DTYPE_F16) return FUSG_ERR_ARG;
     bool any_out = false, need_noise = false;
     for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s) {

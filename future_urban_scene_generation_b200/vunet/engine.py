@@ -34,13 +34,14 @@ class ConvDesc(C.Structure):
                 ("ksize", C.c_int32), ("stride", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("cout", C.c_int32), ("cout_pad", C.c_int32), ("residual", C.c_void_p), ("noise", C.c_void_p),
                 ("outs", ConvOut * MAX_OUTS), ("dtype", C.c_int32), ("impl", C.c_int32), ("zero_kblocks", C.c_uint64),
-                ("pad_mode", C.c_int32), ("pad", C.c_int32), ("border", C.c_int32), ("reserved2", C.c_int32)]
+                ("pad_mode", C.c_int32), ("pad", C.c_int32), ("border", C.c_int32), ("cphys0", C.c_int32), ("cphys1", C.c_int32),
+                ("reserved2", C.c_int32)]
 
 
 class Act:
     """An activation: NHWC device tensors `raw` / `elu` (either may be None), C channels of a
     buffer whose pixel pitch is `pitch`, channel offset already applied to the data pointer."""
-    __slots__ = ("raw", "elu", "C", "H", "W", "pitch", "off", "f32", "aux")
+    __slots__ = ("raw", "elu", "C", "H", "W", "pitch", "off", "f32", "aux", "cphys")
 
     def __init__(self, C_, H, W, raw=None, elu=None, pitch=None, off=0, f32=None):
         self.raw, self.elu, self.C, self.H, self.W = raw, elu, C_, H, W
@@ -48,6 +49,7 @@ class Act:
         self.off = off
         self.f32 = f32          # optional NCHW fp32 API copy
         self.aux = {}
+        self.cphys = None       # channels the buffer really holds when fewer than C (the rest read as zero: fusg_conv_desc.cphys)
 
     def slice(self, c0, c):
         a = Act(c, self.H, self.W, self.raw, self.elu, self.pitch, self.off + c0)
@@ -81,6 +83,8 @@ class VunetEngine:
         self.profile = None            # list -> per-launch (path, impl, flops, start, end) CUDA-event records
         self.noise_provider = None     # callable(B,C,H,W) -> NHWC fp32 device tensor; None = CPU torch.randn (reference semantics)
         self.raw_skips = True          # also keep raw copies of NiN skips (needed by the sub-forward API)
+        # the 6- / 3-channel network inputs are stored 16 channels wide; TMA zero-fills the rest of their 64- / 32-channel K block
+        self.input_cphys = None if os.environ.get("FUSG_NO_CPHYS") else 16
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -190,6 +194,7 @@ class VunetEngine:
         esz = t0.element_size()
         d.in0 = t0.data_ptr() + a0.off * esz
         d.c0, d.pitch0 = a0.C * pm, a0.pitch * pm
+        d.cphys0 = a0.cphys or 0
         ctot = a0.C * pm
         keep = [t0]
         if len(srcs) > 1:
@@ -199,6 +204,7 @@ class VunetEngine:
             assert (a1.H, a1.W) == (a0.H, a0.W)
             d.in1 = t1.data_ptr() + a1.off * esz
             d.c1, d.pitch1 = a1.C * pm, a1.pitch * pm
+            d.cphys1 = a1.cphys or 0
             ctot += a1.C * pm
             keep.append(t1)
         assert ctot == cin_pad, f"{path}: channels {ctot} != weight cin {cin_pad}"
@@ -248,8 +254,10 @@ class VunetEngine:
             outs.append(OutSpec(elu=1, tensor=act.elu))
         return outs
 
-    def from_nchw(self, t, elu_only=False, cpad=None):
-        """Foreign NCHW fp32 tensor -> Act (raw + elu, or only the ELU copy)."""
+    def from_nchw(self, t, elu_only=False, cpad=None, cphys=None):
+        """Foreign NCHW fp32 tensor -> Act (raw + elu, or only the ELU copy).  cphys: store only this many channels
+        (>= the tensor's, multiple of 8) although the Act is `cpad` channels wide for the convolutions that read it -- the
+        kernels zero-extend (fusg_conv_desc.cphys0/1), so the padding never exists in HBM."""
         torch = self.torch
         t = t.detach()
         if t.device != self.device():
@@ -259,6 +267,10 @@ class VunetEngine:
         cp = cpad or Cn
         L = _lib.lib()
         act = Act(cp, H, W)
+        if cphys is not None and cphys < cp:
+            assert cphys >= Cn and cphys % 8 == 0
+            act.pitch = act.cphys = cphys
+            cp = cphys
         if not elu_only:
             act.raw = self._empty(B, H, W, cp)
             _lib.check(L.fusg_nchw_to_nhwc(_lib.ptr(t), _lib.ptr(act.raw), B, Cn, H, W, cp, 0, self.cdtype, self._stream()), "nchw_to_nhwc")
@@ -426,7 +438,7 @@ class VunetEngine:
     def enc_up(self, x_nchw):
         """models.py:333-353 -> (outputs [Act,Act], skips [Act,Act])."""
         B = x_nchw.shape[0]
-        xin = self.from_nchw(x_nchw, elu_only=True, cpad=self._w["app_encoder_1.nin.layers.1"][4])
+        xin = self.from_nchw(x_nchw, elu_only=True, cpad=self._w["app_encoder_1.nin.layers.1"][4], cphys=self.input_cphys)
         x, _ = self.init_block("app_encoder_1", xin, B)
         for name in ("app_encoder_1_a", "app_encoder_1_b", "app_encoder_1_c", "app_encoder_2"):
             x, _ = self.down_block(name, x, B)
@@ -456,7 +468,7 @@ class VunetEngine:
     def dec_up(self, y_nchw):
         """models.py:355-388 -> (outputs [Act], skips [14 Acts])."""
         B = y_nchw.shape[0]
-        yin = self.from_nchw(y_nchw, elu_only=True, cpad=32)
+        yin = self.from_nchw(y_nchw, elu_only=True, cpad=32, cphys=self.input_cphys)
         rs = self.raw_skips
         skips = []
         x, sl = self.init_block("shape_encoder_1", yin, B, last_elu=True)

@@ -191,6 +191,9 @@ typedef struct fusg_conv_desc {
                                  * with the logical image at offset (border, border) and border >= pad -- how the
                                  * ICN's ReflectionPad2d convolutions (warp_learn/models.py:43-46,86) are fed  */
     int32_t pad, border;        /* pad_mode 1 only                                                  */
+    int32_t cphys0, cphys1;     /* 0, or the number of channels in0 / in1 really hold (< c0 / c1, multiple of 8): channels
+                                 * cphys..c-1 read as zero.  The network inputs (6 / 3 real channels) are stored 16 wide and
+                                 * widened to a 64- / 32-channel K block by TMA's out-of-bounds zero fill instead of in HBM  */
     int32_t reserved2;
 } fusg_conv_desc;
 
