@@ -264,6 +264,85 @@ __global__ void __launch_bounds__(256) k_u8_to_inputs(const uint8_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ICN input packing (warp_learn/models.py:323-366 get_icn_inputs): square crop (bbox of the sketch mask) + cv2.resize of the
+// destination normal sketch and of the five warped planes, cv2's 8-bit RGB/BGR -> Lab, ToTensor + Normalize(0.5, 0.5),
+// concat with the Lab central crop into 21 channels.  Pointwise in the output pixel like k_pack_inputs.
+// OpenCV's uint8 Lab is the integer pipeline below PLUS a sorted list of 1671 colours where its interpolated table deviates
+// by one in a or b (scripts/make_lab_tables.py: verified against cv2 on all 2^24 colours).
+// ---------------------------------------------------------------------------------------------------------------
+struct LabTables { const uint16_t *gamma_tab, *cbrt_tab; const uint32_t *exc_keys; const uint16_t *exc_vals; int n_exc; };
+
+__device__ __forceinline__ void rgb2lab_u8(const LabTables &T, int r, int g, int b, int *lab) {
+    const int R = __ldg(T.gamma_tab + r), G = __ldg(T.gamma_tab + g), B = __ldg(T.gamma_tab + b);
+    const int fX = __ldg(T.cbrt_tab + ((R * 1777 + G * 1541 + B * 778 + 2048) >> 12));
+    const int fY = __ldg(T.cbrt_tab + ((R * 871 + G * 2929 + B * 296 + 2048) >> 12));
+    const int fZ = __ldg(T.cbrt_tab + ((R * 73 + G * 448 + B * 3575 + 2048) >> 12));
+    lab[0] = min(max((296 * fY - 1336934 + 16384) >> 15, 0), 255);
+    lab[1] = min(max((500 * (fX - fY) + (128 << 15) + 16384) >> 15, 0), 255);
+    lab[2] = min(max((200 * (fY - fZ) + (128 << 15) + 16384) >> 15, 0), 255);
+    const uint32_t key = ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+    int lo = 0, hi = T.n_exc;                           // first index with exc_keys[i] >= key
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(T.exc_keys + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo < T.n_exc && __ldg(T.exc_keys + lo) == key) {
+        const int v = __ldg(T.exc_vals + lo);
+        lab[1] = v >> 8;
+        lab[2] = v & 0xff;
+    }
+}
+
+// pixel (cy, cx) of the square crop of a full-frame image (zero in the padding)
+__device__ __forceinline__ void crop_fetch3(const uint8_t *__restrict__ img, const CropGeom &g, int Hf, int Wf, int cy, int cx, int *v) {
+    const int fy = g.ny0 + cy - g.pyb, fx = g.nx0 + cx - g.pxb;
+    if (fy < 0 || fy >= Hf || fx < 0 || fx >= Wf) { v[0] = v[1] = v[2] = 0; return; }
+    const uint8_t *p = img + ((size_t)fy * Wf + fx) * 3;
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+}
+
+__global__ void __launch_bounds__(256) k_pack_icn(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ normals,
+                                                  const uint8_t *__restrict__ central, const int *__restrict__ bbox, LabTables T,
+                                                  float *__restrict__ out, int Hf, int Wf, int res) {
+    const int b = blockIdx.z, q = blockIdx.y;            // q: 0 normal sketch, 1 central crop, 2..6 warped plane q-2
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= res * res) return;
+    const int oy = p / res, ox = p - oy * res;
+    int v[3];
+    if (q == 1) {
+        const uint8_t *c = central + ((size_t)b * res * res + p) * 3;
+        v[0] = c[0]; v[1] = c[1]; v[2] = c[2];
+    } else {
+        const uint8_t *img = q == 0 ? normals + (size_t)b * Hf * Wf * 3 : planes + ((size_t)b * 5 + (q - 2)) * Hf * Wf * 3;
+        const CropGeom g = crop_geometry(bbox + 4 * b, Hf, Wf);
+        if (g.cw == 2 * res && g.ch == 2 * res) {                              // exact halving -> 2x2 box average
+            int a[3], bq[3], c[3], d[3];
+            crop_fetch3(img, g, Hf, Wf, 2 * oy, 2 * ox, a); crop_fetch3(img, g, Hf, Wf, 2 * oy, 2 * ox + 1, bq);
+            crop_fetch3(img, g, Hf, Wf, 2 * oy + 1, 2 * ox, c); crop_fetch3(img, g, Hf, Wf, 2 * oy + 1, 2 * ox + 1, d);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) v[ch] = (a[ch] + bq[ch] + c[ch] + d[ch] + 2) >> 2;
+        } else {
+            const Tap tx = resize_tap(res, g.cw, ox, true), ty = resize_tap(res, g.ch, oy, false);
+            int p00[3], p01[3], p10[3], p11[3];
+            crop_fetch3(img, g, Hf, Wf, ty.i0, tx.i0, p00); crop_fetch3(img, g, Hf, Wf, ty.i0, tx.i1, p01);
+            crop_fetch3(img, g, Hf, Wf, ty.i1, tx.i0, p10); crop_fetch3(img, g, Hf, Wf, ty.i1, tx.i1, p11);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int s0 = p00[ch] * tx.a0 + p01[ch] * tx.a1, s1 = p10[ch] * tx.a0 + p11[ch] * tx.a1;
+                v[ch] = min(max((((ty.a0 * (s0 >> 4)) >> 16) + ((ty.a1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+            }
+        }
+    }
+    int lab[3];
+    if (q >= 2) rgb2lab_u8(T, v[2], v[1], v[0], lab);    // planes are BGR (COLOR_BGR2LAB, planes_utils.py:88)
+    else rgb2lab_u8(T, v[0], v[1], v[2], lab);           // sketches are RGB (COLOR_RGB2LAB, models.py:355,358)
+    const size_t plane = (size_t)res * res;
+    float *o = out + ((size_t)b * 21 + q * 3) * plane + p;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) o[ch * plane] = ((float)lab[ch] / 255.f - 0.5f) / 0.5f;
+}
+
 }  // namespace fusg
 
 using namespace fusg;
@@ -383,6 +462,19 @@ extern "C" int fusg_step_keypoints(const double *kp3d, const int32_t *vehicle, c
     if (!kp3d || !vehicle || !rot || !tr || !R || !t || !K || !kp3d_out || !kp2d_out || !verts || N <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     k_step_keypoints<<<(N * 12 + 127) / 128, 128, 0, st>>>(kp3d, vehicle, rot, tr, R, t, K, kp3d_out, kp2d_out, verts, N, H, W);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_pack_icn_inputs(const uint8_t *planes, const uint8_t *normals, const uint8_t *central, const int32_t *bbox,
+                                    const uint16_t *gamma_tab, const uint16_t *cbrt_tab, const uint32_t *exc_keys, const uint16_t *exc_vals, int n_exc,
+                                    float *out, int B, int Hf, int Wf, int res, void *stream) {
+    if (!planes || !normals || !central || !bbox || !gamma_tab || !cbrt_tab || !out || B <= 0 || Hf <= 0 || Wf <= 0 || res <= 0 || n_exc < 0) return FUSG_ERR_ARG;
+    if (n_exc > 0 && (!exc_keys || !exc_vals)) return FUSG_ERR_ARG;
+    if (B > 65535) return FUSG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    LabTables T{gamma_tab, cbrt_tab, exc_keys, exc_vals, n_exc};
+    k_pack_icn<<<dim3((res * res + 255) / 256, 7, B), 256, 0, st>>>(planes, normals, central, bbox, T, out, Hf, Wf, res);
     fusg_count_launch(1);
     return fusg_check_launch();
 }

@@ -247,3 +247,90 @@ def u8_to_vunet_inputs(mask_bbox_u8, normal_src_u8, normal_dst_u8):
     _lib.check(_lib.lib().fusg_u8_to_vunet_inputs(_lib.ptr(mask_bbox_u8), _lib.ptr(normal_src_u8), _lib.ptr(normal_dst_u8), _lib.ptr(x), _lib.ptr(y),
                                                   B, res, _lib.stream_ptr(torch)), "fusg_u8_to_vunet_inputs")
     return x, y
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ICN input packing: warp_learn/models.py:323-366 get_icn_inputs on the device
+# ---------------------------------------------------------------------------------------------------------------------
+_LAB_DEV = {}
+
+
+def _lab_tables(torch, device):
+    """OpenCV's 8-bit Lab tables + exception list (data/lab8.npz, see scripts/make_lab_tables.py), uploaded once per device."""
+    key = str(device)
+    if key not in _LAB_DEV:
+        import os
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lab8.npz"))
+        _LAB_DEV[key] = (torch.from_numpy(z["gamma_tab"].astype(np.int32)).to(torch.uint16).to(device),
+                         torch.from_numpy(z["cbrt_tab"].astype(np.int32)).to(torch.uint16).to(device),
+                         torch.from_numpy(z["exc_keys"].astype(np.int64)).to(torch.uint32).to(device),
+                         torch.from_numpy(z["exc_vals"].astype(np.int32)).to(torch.uint16).to(device))
+    return _LAB_DEV[key]
+
+
+def square_crop_info(image_hw, bbox):
+    """crop_info of warp_learn/models.py:337-342 for a vehicle bounding box (utils/crop_utils.py:4-52 geometry)."""
+    image_h, image_w = image_hw
+    x_min, y_min, x_max, y_max = (int(v) for v in bbox)
+    side_x, side_y = x_max - x_min, y_max - y_min
+    major = max(side_x, side_y) * 1.1
+    cx, cy = x_min + side_x / 2, y_min + side_y / 2
+    pxb = pxa = pyb = pya = 0
+    nx0 = int(cx - major / 2.)
+    if nx0 < 0:
+        pxb, nx0 = -nx0, 0
+    nx1 = int(cx + major / 2.) + pxb
+    if nx1 > image_w:
+        pxa = nx1 - image_w
+        nx1 = image_w + pxa
+    ny0 = int(cy - major / 2.)
+    if ny0 < 0:
+        pyb, ny0 = -ny0, 0
+    ny1 = int(cy + major / 2.) + pyb
+    if ny1 > image_h:
+        pya = ny1 - image_h
+        ny1 = image_h + pya
+    return {"crop_xy_min": (nx0, ny0), "pad_xy_before": (pxb, pyb), "pad_xy_after": (pxa, pya),
+            "crop_size_orig": (min(ny1, image_h + pyb + pya) - ny0, min(nx1, image_w + pxb + pxa) - nx0)}
+
+
+def get_icn_inputs_batch(planes, sketch_normals, sketch_masks, central_crops, icn_w=256, icn_h=256):
+    """`get_icn_inputs` for B vehicles at once.  planes (B,5,Hf,Wf,3) uint8 BGR (e.g. `warp_batch(...).warped` for whole
+    frames, still on the device), sketch_normals (B,Hf,Wf,3) uint8 RGB, sketch_masks (B,Hf,Wf) bool / uint8 (non-zero =
+    vehicle), central_crops (B,icn_h,icn_w,3) uint8 RGB; numpy or torch, host or device.
+    Returns (gen_in (B,21,icn_h,icn_w) float32 CUDA tensor == the reference's tensors stacked, list of B crop_info dicts)."""
+    if icn_w != icn_h:
+        raise NotImplementedError("get_icn_inputs_batch: square ICN inputs only (the reference uses 256 x 256)")
+    torch = _lib.require_cuda()
+    pl = _dev(torch, planes, torch.uint8)
+    if pl.dim() != 5 or pl.shape[1] != 5 or pl.shape[4] != 3:
+        raise ValueError("get_icn_inputs_batch: planes must be (B, 5, Hf, Wf, 3) uint8")
+    B, Hf, Wf = int(pl.shape[0]), int(pl.shape[2]), int(pl.shape[3])
+    dev = pl.device
+    nm = _dev(torch, sketch_normals, torch.uint8).to(dev)
+    ct = _dev(torch, central_crops, torch.uint8).to(dev)
+    mk = sketch_masks if isinstance(sketch_masks, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(sketch_masks))
+    mk = (mk != 0).to(torch.uint8).to(dev).contiguous()
+    if tuple(nm.shape) != (B, Hf, Wf, 3) or tuple(mk.shape) != (B, Hf, Wf) or tuple(ct.shape) != (B, icn_h, icn_w, 3):
+        raise ValueError("get_icn_inputs_batch: sketch_normals (B,Hf,Wf,3), sketch_masks (B,Hf,Wf), central_crops (B,res,res,3) expected")
+    L = _lib.lib()
+    off = torch.arange(B, dtype=torch.int64, device=dev) * (Hf * Wf)
+    rect = torch.tensor([[0, 0, Wf, Hf]] * B, dtype=torch.int32, device=dev)
+    bbox = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    _lib.check(L.fusg_mask_bbox(_lib.ptr(mk), _lib.ptr(off), _lib.ptr(rect), _lib.ptr(bbox), B, Hf * Wf, _lib.stream_ptr(torch)), "fusg_mask_bbox")
+    bb = bbox.cpu().numpy()                              # crop_info is host data in the reference too (a few ints per vehicle)
+    if (bb[:, 2] < 0).any():
+        raise ValueError("get_icn_inputs_batch: empty sketch mask (np.min of an empty array in the reference)")
+    g, c, ek, ev = _lab_tables(torch, dev)
+    out = torch.empty((B, 21, icn_h, icn_w), dtype=torch.float32, device=dev)
+    _lib.check(L.fusg_pack_icn_inputs(_lib.ptr(pl), _lib.ptr(nm), _lib.ptr(ct), _lib.ptr(bbox), _lib.ptr(g), _lib.ptr(c), _lib.ptr(ek), _lib.ptr(ev),
+                                      int(ek.numel()), _lib.ptr(out), B, Hf, Wf, icn_h, _lib.stream_ptr(torch)), "fusg_pack_icn_inputs")
+    out._keep = (pl, nm, ct, bbox)
+    return out, [square_crop_info((Hf, Wf), bb[b]) for b in range(B)]
+
+
+def get_icn_inputs(planes, sketch_normal, sketch_mask, central_crop, icn_w, icn_h):
+    """Reference signature (warp_learn/models.py:323): one vehicle -> (gen_in (1,21,icn_h,icn_w) CUDA float tensor, crop_info)."""
+    out, infos = get_icn_inputs_batch(planes[None], np.asarray(sketch_normal)[None], np.asarray(sketch_mask)[None],
+                                      np.asarray(central_crop)[None], icn_w, icn_h)
+    return out, infos[0]

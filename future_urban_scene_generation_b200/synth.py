@@ -219,3 +219,22 @@ def make_trajectory_case(idx: int, steps: int = 20, h: int = 720, w: int = 1280)
             heading += 0.6                                    # one abrupt change of direction: the "instant theta" gate
         pos.append(pos[-1] + rng.uniform(0.3, 0.7) * np.array([np.cos(heading), np.sin(heading)]))
     return dict(kp3d=kp3d, K=K, R=E[:3, :3].copy(), t=E[:3, 3].copy(), meter_coords=np.stack(pos), h=h, w=w)
+
+
+def make_icn_pack_case(idx: int, frame_hw=(360, 640), res: int = 256):
+    """One synthetic vehicle for `get_icn_inputs` (warp_learn/models.py:323-366): five full-frame warped planes (uint8 BGR,
+    textured inside a per-plane polygon-ish region, zero elsewhere), the destination normal sketch (uint8 RGB) with its
+    vehicle mask (True = vehicle) and a res x res central crop."""
+    H, W = frame_hw
+    bbox, veh, _ = make_paste_case(idx, frame_hw)
+    rng = np.random.default_rng(83_000 + idx)
+    yy, xx = np.mgrid[0:H, 0:W]
+    normal = np.stack([(xx * int(rng.integers(1, 5)) + yy * int(rng.integers(1, 5)) + int(rng.integers(0, 255))) % 256 for _ in range(3)], -1).astype(np.uint8)
+    normal[~veh] = 0
+    planes = np.zeros((5, H, W, 3), np.uint8)
+    for p in range(5):
+        tex = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        band = veh & (((xx + yy * (p + 1)) // 23) % 5 == p)
+        planes[p][band] = tex[band]
+    central = rng.integers(0, 256, (res, res, 3), dtype=np.uint8)
+    return planes, normal, veh, central

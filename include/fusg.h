@@ -259,6 +259,17 @@ int fusg_mask_bbox(const uint8_t *masks, const long long *mask_off, const int32_
 int fusg_pack_vunet_inputs(const uint8_t *frames, const int32_t *frame_idx, const uint8_t *masks, const uint8_t *normal_src,
                            const uint8_t *normal_dst, const long long *off, const int32_t *rect, const int32_t *bbox, float *x, float *y,
                            int B, int Hf, int Wf, int res, void *stream);
+/* ---- ICN input packing (warp_learn/models.py:323-366 get_icn_inputs) --------------------------------
+ * Item b: planes [B,5,Hf,Wf,3] u8 (the warped planes, BGR -- fusg_warp_fused's `warped` for whole frames), normals [B,Hf,Wf,3] u8
+ * (destination normal sketch, RGB), central [B,res,res,3] u8 (central crop, RGB), bbox[b] = bounding box of the sketch mask
+ * (fusg_mask_bbox).  out [B,21,res,res] f32 = cat(Lab(resize(square_crop(normal))), Lab(central), Lab(resize(square_crop(plane_k))) k=0..4)
+ * with square_crop = utils/crop_utils.py:4-52, resize = cv2.resize(..., (res,res)), Lab = cv2.cvtColor(COLOR_RGB2LAB / COLOR_BGR2LAB) on
+ * uint8, then ToTensor + Normalize(0.5, 0.5).  The Lab tables (gamma_tab [256] u16, cbrt_tab [3072] u16) and the sorted exception list
+ * (exc_keys [n_exc] u32 = R<<16|G<<8|B, exc_vals [n_exc] u16 = a<<8|b) come from future_urban_scene_generation_b200/data/lab8.npz,
+ * generated and verified against cv2 on all 2^24 colours by scripts/make_lab_tables.py; all in device memory. */
+int fusg_pack_icn_inputs(const uint8_t *planes, const uint8_t *normals, const uint8_t *central, const int32_t *bbox,
+                         const uint16_t *gamma_tab, const uint16_t *cbrt_tab, const uint32_t *exc_keys, const uint16_t *exc_vals, int n_exc,
+                         float *out, int B, int Hf, int Wf, int res, void *stream);
 /* The tail of the same assembly when the three 256x256 uint8 images already exist (trajectory_inference.py:221-225):
  *   x = cat(to_tensor(mask_bbox), to_tensor(normal_src[..., ::-1])), y = to_tensor(normal_dst[..., ::-1]);
  * inputs [B,res,res,3] u8 -> x [B,6,res,res] f32, y [B,3,res,res] f32.  Lets a host ship 9 bytes per pixel instead of 36. */

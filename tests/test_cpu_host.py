@@ -224,8 +224,10 @@ def test_import_shim_serves_reference_import_sites():
         "assert get_planes.__module__.startswith('future_urban_scene_generation_b200');"
         + "from warp_learn.models import G_Resnet;"
         "assert G_Resnet.__module__.startswith('future_urban_scene_generation_b200');"
-        + ("from warp_learn.models import get_icn_inputs, G_Resnet_reference; import warp_learn.models as wm;"
-           "assert get_icn_inputs.__code__.co_filename.startswith('/root/reference');"
+        + "from warp_learn.models import get_icn_inputs;"
+        "assert get_icn_inputs.__module__.startswith('future_urban_scene_generation_b200');"
+        + ("from warp_learn.models import get_icn_inputs_reference, G_Resnet_reference, GANLoss; import warp_learn.models as wm;"
+           "assert get_icn_inputs_reference.__code__.co_filename.startswith('/root/reference');"
            "assert wm.planes_to_torch.__module__.startswith('future_urban_scene_generation_b200');" if os.path.isdir(ref) else "")
         + "print('ok')")
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")

@@ -211,6 +211,24 @@ def test_kinematics_oracle_matches_reference_goldens():
     assert tripped >= 5                                    # the +-20 degree gates are exercised
 
 
+def test_lab_and_icn_input_oracle_match_goldens():
+    """oracle/frame_oracle.py: the uint8 Lab restatement against a few known OpenCV values and its own table invariants, and
+    get_icn_inputs against the sha1 the reference function produced (scripts/make_golden_icn_inputs.py)."""
+    from oracle import frame_oracle as FO
+    z = np.load(os.path.join(os.path.dirname(GOLD), "..", "future_urban_scene_generation_b200", "data", "lab8.npz"))
+    assert len(z["gamma_tab"]) == 256 and len(z["cbrt_tab"]) == 3072 and len(z["exc_keys"]) == len(z["exc_vals"]) == 1671
+    assert np.all(np.diff(z["exc_keys"].astype(np.int64)) > 0)                       # sorted, unique: the device binary-searches it
+    known = np.array([[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [128, 128, 128]], np.uint8)
+    assert FO.rgb2lab_u8(known).tolist() == [[0, 128, 128], [255, 128, 128], [136, 208, 195], [224, 42, 211], [82, 207, 20], [137, 128, 128]]
+    gold = json.load(open(os.path.join(GOLD, "frame_golden.json")))["icn_inputs"]
+    for c in gold[:5]:
+        planes, normal, mask, central = synth.make_icn_pack_case(c["idx"], tuple(c["frame_hw"]))
+        got, info = FO.get_icn_inputs(planes, normal, mask, central)
+        assert got.shape == (21, 256, 256) and got.dtype == np.float32
+        assert hashlib.sha1(np.ascontiguousarray(got).tobytes()).hexdigest() == c["sha1"], c["idx"]
+        assert list(info["crop_size_orig"]) == c["crop_size_orig"]
+
+
 def test_space_depth_permutations_are_block_major():
     import torch
     from oracle import vunet_oracle as VO

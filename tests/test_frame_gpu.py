@@ -8,7 +8,10 @@ import pytest
 
 from future_urban_scene_generation_b200 import synth
 
+from oracle import frame_oracle as FO
+
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frame_golden.json")))
 
 
@@ -195,3 +198,90 @@ def test_clip_chain_pack_vunet_paste_matches_oracle_chain(cuda):
     assert np.array_equal(out[~union], frames[~union])                             # untouched outside the masks
     diff = np.abs(out.astype(int) - ref.astype(int))
     assert diff.max() <= 3 and (diff > 1).mean() < 0.01, (diff.max(), (diff > 1).mean())
+
+
+def test_lab_conversion_matches_oracle_on_colour_sweep(cuda):
+    """cv2's uint8 RGB -> Lab on the device (tables + exception list, exhaustively pinned to cv2 by scripts/make_lab_tables.py)
+    vs the numpy oracle: every exception colour, a strided sweep of the colour cube and random colours, through
+    fusg_pack_icn_inputs' central-crop channel (no resize involved)."""
+    torch = cuda
+    import os
+    from future_urban_scene_generation_b200.frame_ops import get_icn_inputs_batch
+    z = np.load(os.path.join(ROOT, "future_urban_scene_generation_b200", "data", "lab8.npz"))
+    keys = z["exc_keys"].astype(np.int64)
+    exc = np.stack([keys >> 16, (keys >> 8) & 255, keys & 255], -1).astype(np.uint8)
+    sweep = np.stack(np.meshgrid(np.arange(0, 256, 5), np.arange(0, 256, 3), np.arange(0, 256, 7), indexing="ij"), -1).reshape(-1, 3).astype(np.uint8)
+    rnd = np.random.default_rng(5).integers(0, 256, (60000, 3), dtype=np.uint8)
+    cols = np.concatenate([exc, sweep, rnd])
+    n = 256 * 256
+    B = (len(cols) + n - 1) // n
+    cols = np.concatenate([cols, np.zeros((B * n - len(cols), 3), np.uint8)]).reshape(B, 256, 256, 3)
+    planes = np.zeros((B, 5, 8, 8, 3), np.uint8)
+    normal = np.zeros((B, 8, 8, 3), np.uint8)
+    mask = np.zeros((B, 8, 8), bool)
+    mask[:, 2:6, 2:6] = True
+    out, _ = get_icn_inputs_batch(planes, normal, mask, cols)
+    torch.cuda.synchronize()
+    got = out[:, 3:6].cpu().numpy()
+    for b in range(B):
+        want = FO.lab_to_tensor(FO.rgb2lab_u8(cols[b]))
+        assert np.array_equal(got[b].view(np.int32), want.view(np.int32)), b
+
+
+def test_get_icn_inputs_matches_reference_goldens(cuda):
+    """fusg_mask_bbox + fusg_pack_icn_inputs vs the reference's own get_icn_inputs (cv2.resize, cv2.cvtColor, PIL, torchvision)
+    recorded by scripts/make_golden_icn_inputs.py, and vs the oracle bit for bit; the single-vehicle wrapper keeps the
+    reference signature."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.frame_ops import get_icn_inputs_batch, get_icn_inputs
+    for c in GOLD["icn_inputs"]:
+        planes, normal, mask, central = synth.make_icn_pack_case(c["idx"], tuple(c["frame_hw"]))
+        out, infos = get_icn_inputs_batch(planes[None], normal[None], mask[None], central[None])
+        torch.cuda.synchronize()
+        got = out[0].cpu().numpy()
+        assert hashlib.sha1(np.ascontiguousarray(got).tobytes()).hexdigest() == c["sha1"], c["idx"]
+        for k in ("crop_xy_min", "pad_xy_before", "pad_xy_after", "crop_size_orig"):
+            assert list(infos[0][k]) == c[k], (c["idx"], k)
+        want, winfo = FO.get_icn_inputs(planes, normal, mask, central)
+        assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    # a batch of same-sized frames in one launch == item by item; planes may already live on the device
+    cases = [synth.make_icn_pack_case(i, (360, 640)) for i in (0, 1, 3, 8)]
+    out, infos = get_icn_inputs_batch(torch.from_numpy(np.stack([c[0] for c in cases])).cuda(), np.stack([c[1] for c in cases]),
+                                      np.stack([c[2] for c in cases]), np.stack([c[3] for c in cases]))
+    for i, c in enumerate(cases):
+        one, info = get_icn_inputs(c[0], c[1], c[2], c[3], 256, 256)
+        assert one.shape == (1, 21, 256, 256) and torch.equal(one[0], out[i]) and info == infos[i]
+
+
+def test_warp_to_icn_chain_on_the_device(cuda):
+    """The reference's real data flow (trajectory_inference.py:165-182): fused warp -> get_icn_inputs -> G_Resnet, without
+    leaving the device, equals the oracle chain (bit-exact up to the generator's input, <= 1e-2 after it)."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.warp_learn import warp_batch
+    from future_urban_scene_generation_b200.warp_learn.models import G_Resnet
+    from future_urban_scene_generation_b200.frame_ops import get_icn_inputs_batch
+    from oracle import warp_oracle as WO, icn_oracle as IO
+    B = 3
+    batch = synth.make_warp_batch(40, B)
+    res = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"])
+    normals, masks, centrals = [], [], []
+    for i in range(B):
+        _, n, m, c = synth.make_icn_pack_case(20 + i, (256, 256))
+        normals.append(n); masks.append(m); centrals.append(c)
+    gen_in, infos = get_icn_inputs_batch(res.warped, np.stack(normals), np.stack(masks), np.stack(centrals))
+    sd = IO.make_state_dict(0)
+    g = G_Resnet(21)
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
+    img = g(gen_in)
+    torch.cuda.synchronize()
+    import torch as T
+    for i in range(B):
+        w, _, _, _ = WO.warp_fused(batch["src"][i], batch["src_kp"][i], batch["dst_kp"][i], batch["K"][i], batch["E_src"][i], batch["E_dst"][i], batch["kp3d"][i])
+        want_in, _ = FO.get_icn_inputs(w, normals[i], masks[i], centrals[i])
+        assert np.array_equal(gen_in[i].cpu().numpy().view(np.int32), want_in.view(np.int32))
+        with T.no_grad():
+            want = IO.forward(sd, T.from_numpy(want_in)[None])
+        assert (img[i].cpu() - want[0]).abs().max().item() <= 1e-2
