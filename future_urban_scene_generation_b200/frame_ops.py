@@ -102,6 +102,14 @@ def prepare_paste(masks, crop_infos, frame_index, frame_hw, n_frames, mask_rects
     if any(f < 0 or f >= n_frames for f in frame_index):
         raise ValueError("paste_back: frame index out of range")
     info = pack_crop_info(crop_infos, frame_index, (Hf, Wf))
+    if isinstance(masks, torch.Tensor) and mask_rects is None:
+        # stacked full-frame masks (B, Hf, Wf), e.g. already on the device: no per-item work on the host
+        if tuple(masks.shape) != (B, Hf, Wf):
+            raise ValueError(f"paste_back: stacked masks are {tuple(masks.shape)}, expected {(B, Hf, Wf)}")
+        mflat = (masks.view(torch.uint8) if masks.dtype == torch.bool else (masks != 0).to(torch.uint8)).contiguous().reshape(-1).cuda()
+        dev = mflat.device
+        rect_t = torch.tensor([0, 0, Wf, Hf], dtype=torch.int32, device=dev).repeat(B, 1)
+        return PastePlan(mflat, torch.arange(B, dtype=torch.int64, device=dev) * (Hf * Wf), rect_t, torch.from_numpy(info).to(dev), Hf * Wf, B, (Hf, Wf))
     rects = np.zeros((B, 4), np.int32)
     offs, flat, o = [], [], 0
     for b, m in enumerate(masks):
@@ -185,6 +193,17 @@ def pack_vunet_inputs_batch(frames, frame_index, src_sketch_masks, src_sketch_no
         raise ValueError("pack_vunet_inputs_batch: one mask and two normal sketches per item")
     if any(f < 0 or f >= F for f in frame_index):
         raise ValueError("pack_vunet_inputs_batch: frame index out of range")
+    if rects is None and all(isinstance(a, torch.Tensor) and a.dim() == d for a, d in ((src_sketch_masks, 3), (src_sketch_normals, 4), (dst_sketch_normals, 4))):
+        # stacked full-frame tensors (B, Hf, Wf[, 3]), e.g. already on the device: no per-item work on the host
+        if tuple(src_sketch_masks.shape) != (B, Hf, Wf) or tuple(src_sketch_normals.shape) != (B, Hf, Wf, 3) or tuple(dst_sketch_normals.shape) != (B, Hf, Wf, 3):
+            raise ValueError("pack_vunet_inputs_batch: stacked inputs must be (B,Hf,Wf), (B,Hf,Wf,3), (B,Hf,Wf,3)")
+        dev = fr.device
+        masks = (src_sketch_masks == 0).to(torch.uint8).to(dev).contiguous().reshape(-1)
+        nsrc = _dev(torch, src_sketch_normals, torch.uint8).to(dev).reshape(-1)
+        ndst = _dev(torch, dst_sketch_normals, torch.uint8).to(dev).reshape(-1)
+        t_off = torch.arange(B, dtype=torch.int64, device=dev) * (Hf * Wf)
+        t_rect = torch.tensor([0, 0, Wf, Hf], dtype=torch.int32, device=dev).repeat(B, 1)
+        return _pack_vunet_launch(torch, fr, frame_index, masks, nsrc, ndst, t_off, t_rect, Hf * Wf, B, Hf, Wf, res)
     rect = np.zeros((B, 4), np.int32)
     offs, fm, fs, fd, o = [], [], [], [], 0
     for b in range(B):
@@ -212,10 +231,14 @@ def pack_vunet_inputs_batch(frames, frame_index, src_sketch_masks, src_sketch_no
     masks, nsrc, ndst = torch.cat(fm).to(dev), torch.cat(fs).to(dev), torch.cat(fd).to(dev)
     t_off = torch.tensor(offs, dtype=torch.int64, device=dev)
     t_rect = torch.from_numpy(rect).to(dev)
+    return _pack_vunet_launch(torch, fr, frame_index, masks, nsrc, ndst, t_off, t_rect, int((rect[:, 2].astype(np.int64) * rect[:, 3]).max()), B, Hf, Wf, res)
+
+
+def _pack_vunet_launch(torch, fr, frame_index, masks, nsrc, ndst, t_off, t_rect, mx, B, Hf, Wf, res):
+    dev = fr.device
     t_fidx = torch.tensor(list(frame_index), dtype=torch.int32, device=dev)
     bbox = torch.empty((B, 4), dtype=torch.int32, device=dev)
     L = _lib.lib()
-    mx = int((rect[:, 2].astype(np.int64) * rect[:, 3]).max())
     _lib.check(L.fusg_mask_bbox(_lib.ptr(masks), _lib.ptr(t_off), _lib.ptr(t_rect), _lib.ptr(bbox), B, mx, _lib.stream_ptr(torch)), "fusg_mask_bbox")
     if bool((bbox[:, 2] < 0).any()):
         raise ValueError("pack_vunet_inputs_batch: empty vehicle mask (np.min of an empty array in the reference)")

@@ -115,8 +115,8 @@ def clip():
     ev["icn"][1].record()
     # 5. VUNet: appearance once per vehicle, shape path per item
     ev["vunet_inputs"][0].record()
-    x_src, _, _ = pack_vunet_inputs_batch(frames_dev.unsqueeze(0), [0] * V, [~m for m in src_masks], list(src_normals), list(src_normals))
-    _, y_all, _ = pack_vunet_inputs_batch(frames_dev.unsqueeze(0), [0] * N, [~m for m in dst_masks], list(dst_normals), list(dst_normals))
+    x_src, _, _ = pack_vunet_inputs_batch(frames_dev.unsqueeze(0), [0] * V, ~src_masks, src_normals, src_normals)
+    _, y_all, _ = pack_vunet_inputs_batch(frames_dev.unsqueeze(0), [0] * N, ~dst_masks, dst_normals, dst_normals)
     ev["vunet_inputs"][1].record()
     ev["vunet"][0].record()
     with torch.no_grad():
@@ -137,12 +137,12 @@ def clip():
     frames_icn = frames_dev.unsqueeze(0).repeat(S, 1, 1, 1)
     frames_vun = frames_icn.clone()
     order = np.argsort(step_of_item, kind="stable")                    # vehicles in selection order inside every frame
-    masks_l = [dst_masks[i] for i in order]
     infos_l = [crop_infos[i] for i in order]
     fidx = [int(step_of_item[i]) for i in order]
     oi = torch.as_tensor(order, device=dev)
-    paste_back_batch(frames_icn, to_image_batch(icn_img)[oi].contiguous(), masks_l, infos_l, fidx)
-    paste_back_batch(frames_vun, to_image_batch(vun_img)[oi].contiguous(), masks_l, infos_l, fidx)
+    masks_o = dst_masks[oi]
+    paste_back_batch(frames_icn, to_image_batch(icn_img)[oi].contiguous(), masks_o, infos_l, fidx)
+    paste_back_batch(frames_vun, to_image_batch(vun_img)[oi].contiguous(), masks_o, infos_l, fidx)
     ev["paste"][1].record()
     torch.cuda.synchronize()
     return {k: a.elapsed_time(b) for k, (a, b) in ev.items()}, res, frames_icn, frames_vun

@@ -285,3 +285,25 @@ def test_warp_to_icn_chain_on_the_device(cuda):
         with T.no_grad():
             want = IO.forward(sd, T.from_numpy(want_in)[None])
         assert (img[i].cpu() - want[0]).abs().max().item() <= 1e-2
+
+
+def test_stacked_tensor_inputs_equal_per_item_lists(cuda):
+    """The batched calls also take stacked full-frame tensors (already on the device) without per-item host work; results are
+    those of the per-item list form."""
+    torch = cuda
+    from future_urban_scene_generation_b200.frame_ops import pack_vunet_inputs_batch, paste_back_batch
+    Hf, Wf = 360, 640
+    frame = np.random.default_rng(3).integers(0, 256, (1, Hf, Wf, 3), dtype=np.uint8)
+    cases = [synth.make_pack_case(i, (Hf, Wf)) for i in range(5)]
+    xl, yl, bl = pack_vunet_inputs_batch(frame, [0] * 5, [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases])
+    xs, ys, bs = pack_vunet_inputs_batch(frame, [0] * 5, torch.from_numpy(np.stack([c[0] for c in cases])).cuda(),
+                                         torch.from_numpy(np.stack([c[1] for c in cases])).cuda(), torch.from_numpy(np.stack([c[2] for c in cases])).cuda())
+    assert torch.equal(xl, xs) and torch.equal(yl, ys) and torch.equal(bl, bs)
+    items = [synth.make_paste_case(i, (Hf, Wf)) for i in range(6)]
+    infos = [FO.square_crop_info((Hf, Wf), it[0]) for it in items]
+    crops = np.stack([it[2] for it in items])
+    fidx = [0, 1, 0, 1, 0, 1]
+    base = np.random.default_rng(4).integers(0, 256, (2, Hf, Wf, 3), dtype=np.uint8)
+    a = paste_back_batch(torch.from_numpy(base.copy()).cuda(), crops, [it[1] for it in items], infos, fidx)
+    b = paste_back_batch(torch.from_numpy(base.copy()).cuda(), crops, torch.from_numpy(np.stack([it[1] for it in items])).cuda(), infos, fidx)
+    assert torch.equal(a, b)
