@@ -44,6 +44,7 @@ def _load():
         "fusg_nchw_to_nhwc": ([vp, vp, i, i, i, i, i, i, i, vp], i),
         "fusg_nhwc_to_nchw": ([vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_to_image": ([vp, vp, i, i, i, vp], i),
+        "fusg_to_image_lab": ([vp, vp, vp, vp, i, i, i, vp], i),
         "fusg_elu": ([vp, vp, sz, i, vp], i),
         "fusg_nchw_to_nhwc_reflect": ([vp, vp, i, i, i, i, i, i, i, vp], i),
         "fusg_norm_stats": ([vp, vp, i, i, i, i, i, vp], i),

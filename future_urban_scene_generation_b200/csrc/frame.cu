@@ -343,6 +343,41 @@ __global__ void __launch_bounds__(256) k_pack_icn(const uint8_t *__restrict__ pl
     for (int ch = 0; ch < 3; ++ch) o[ch * plane] = ((float)lab[ch] / 255.f - 0.5f) / 0.5f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// to_image(x, from_LAB=True) (warp_learn/planes_utils.py:96-118), the ICN's output side: (x + 1) / 2 * 255, clip, truncating
+// uint8 cast, then cv2.cvtColor(COLOR_LAB2BGR) on uint8 -- OpenCV's integer pipeline (Lab2RGBinteger), bit-exact on all 2^24
+// (L, a, b) triples with the tables of data/lab8.npz (scripts/make_lab_tables.py).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ab_to_xz(int i) {                 // OpenCV's abToXZ_b table as the integer formula it is filled with
+    constexpr int BASE = 1 << 14;
+    if (i <= 3390) return i * 108 / 841 - BASE * 16 / 116 * 108 / 841;          // C division: truncation toward zero
+    return i * i / BASE * i / BASE;
+}
+
+__global__ void __launch_bounds__(256) k_to_image_lab(const float *__restrict__ in, uint8_t *__restrict__ out, const uint16_t *__restrict__ lab_to_yf,
+                                                      const uint8_t *__restrict__ inv_gamma, int HW, size_t npix) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over B*HW
+    if (i >= npix) return;
+    const size_t b = i / HW, pix = i - b * HW;
+    int lab[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = (in[(b * 3 + c) * HW + pix] + 1.f) / 2.f * 255.f;      // numpy float32 arithmetic of to_image
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        lab[c] = (int)v;                                                  // astype(np.uint8): truncation
+    }
+    constexpr int BASE = 1 << 14;
+    const int y = __ldg(lab_to_yf + 2 * lab[0]), ify = __ldg(lab_to_yf + 2 * lab[0] + 1);
+    const int adiv = ((5 * lab[1] * 53687 + (1 << 7)) >> 13) - 128 * BASE / 500;
+    const int bdiv = ((lab[2] * 41943 + (1 << 4)) >> 9) - 128 * BASE / 200 + 1;
+    const int x = ab_to_xz(ify + adiv), z = ab_to_xz(ify - bdiv);
+    const int r = min(max((12615 * x - 6296 * y - 2223 * z + (1 << 13)) >> 14, 0), 4095);
+    const int g = min(max((-3773 * x + 7684 * y + 185 * z + (1 << 13)) >> 14, 0), 4095);
+    const int bl = min(max((217 * x - 836 * y + 4715 * z + (1 << 13)) >> 14, 0), 4095);
+    uint8_t *o = out + i * 3;                                             // BGR
+    o[0] = __ldg(inv_gamma + bl); o[1] = __ldg(inv_gamma + g); o[2] = __ldg(inv_gamma + r);
+}
+
 }  // namespace fusg
 
 using namespace fusg;
@@ -475,6 +510,15 @@ extern "C" int fusg_pack_icn_inputs(const uint8_t *planes, const uint8_t *normal
     cudaStream_t st = (cudaStream_t)stream;
     LabTables T{gamma_tab, cbrt_tab, exc_keys, exc_vals, n_exc};
     k_pack_icn<<<dim3((res * res + 255) / 256, 7, B), 256, 0, st>>>(planes, normals, central, bbox, T, out, Hf, Wf, res);
+    fusg_count_launch(1);
+    return fusg_check_launch();
+}
+
+extern "C" int fusg_to_image_lab(const float *in, uint8_t *out, const uint16_t *lab_to_yf, const uint8_t *inv_gamma, int B, int H, int W, void *stream) {
+    if (!in || !out || !lab_to_yf || !inv_gamma || B <= 0 || H <= 0 || W <= 0) return FUSG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t npix = (size_t)B * H * W;
+    k_to_image_lab<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(in, out, lab_to_yf, inv_gamma, H * W, npix);
     fusg_count_launch(1);
     return fusg_check_launch();
 }

@@ -108,6 +108,11 @@ def planes_to_torch(planes, to_LAB: bool):
 def to_image(x: Union[np.ndarray, "torch.Tensor"], from_LAB: bool):
     """planes_utils.py:96-118: [-1,1] CHW tensor (or HWC ndarray) -> uint8 HWC BGR (truncating cast)."""
     assert len(x.shape) == 3, f'Unsupported image shape {x.shape}'
+    if from_LAB:
+        # the ICN's Lab output: float -> uint8 and OpenCV's 8-bit Lab -> BGR on the device (fusg_to_image_lab)
+        torch = _lib.require_cuda()
+        t = x.detach() if hasattr(x, "detach") else torch.from_numpy(np.ascontiguousarray(np.transpose(np.asarray(x, dtype=np.float32), (2, 0, 1))))
+        return to_image_batch(t.float().cuda()[None], from_LAB=True)[0].cpu().numpy()
     try:
         x = x.to('cpu').detach().numpy()
         x = np.transpose(x, (1, 2, 0))
@@ -116,20 +121,32 @@ def to_image(x: Union[np.ndarray, "torch.Tensor"], from_LAB: bool):
     x = (x + 1.) / 2 * 255
     x = np.clip(x, 0, 255)
     x = x.astype(np.uint8)
-    if from_LAB:
-        import cv2
-        x = cv2.cvtColor(x, cv2.COLOR_LAB2BGR)
     return x
 
 
-def to_image_batch(x):
-    """to_image for a batch on the device: (B,3,H,W) fp32 CUDA tensor in [-1,1] -> (B,H,W,3) uint8 CUDA tensor
-    (same arithmetic as `to_image(..., from_LAB=False)`, libfusg.so: fusg_to_image)."""
+_LAB_INV = {}
+
+
+def to_image_batch(x, from_LAB=False):
+    """to_image for a batch on the device: (B,3,H,W) fp32 CUDA tensor in [-1,1] -> (B,H,W,3) uint8 BGR CUDA tensor (same
+    arithmetic as `to_image(..., from_LAB)`; libfusg.so: fusg_to_image, and fusg_to_image_lab with OpenCV's 8-bit Lab -> BGR
+    for the ICN's Lab output)."""
     torch = _lib.require_cuda()
     assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
     x = x.float().contiguous()
     B, _, H, W = x.shape
     out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().fusg_to_image(_lib.ptr(x), _lib.ptr(out), B, H, W, _lib.stream_ptr(torch)), "fusg_to_image")
+        if from_LAB:
+            key = str(x.device)
+            if key not in _LAB_INV:
+                import os
+                z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "lab8.npz"))
+                _LAB_INV[key] = (torch.from_numpy(z["lab_to_yf"].astype(np.int32)).to(torch.uint16).to(x.device),
+                                 torch.from_numpy(z["inv_gamma"]).to(x.device))
+            yf, ig = _LAB_INV[key]
+            _lib.check(_lib.lib().fusg_to_image_lab(_lib.ptr(x), _lib.ptr(out), _lib.ptr(yf), _lib.ptr(ig), B, H, W, _lib.stream_ptr(torch)),
+                       "fusg_to_image_lab")
+        else:
+            _lib.check(_lib.lib().fusg_to_image(_lib.ptr(x), _lib.ptr(out), B, H, W, _lib.stream_ptr(torch)), "fusg_to_image")
     return out

@@ -225,6 +225,11 @@ int fusg_nhwc_to_nchw(const void *in, float *out, int B, int C, int H, int W, in
  * HWC uint8, x = clip((x + 1) / 2 * 255, 0, 255) with the reference's truncating cast.
  *   in [B,3,H,W] f32 -> out [B,H,W,3] u8 */
 int fusg_to_image(const float *in, uint8_t *out, int B, int H, int W, void *stream);
+/* to_image(..., from_LAB=True) (warp_learn/planes_utils.py:96-118; the ICN's output, trajectory_inference.py:182,391): the same
+ * float -> uint8 step, then cv2.cvtColor(COLOR_LAB2BGR) on uint8 -- OpenCV's integer pipeline, bit-exact on all 2^24 (L,a,b) triples.
+ *   in [B,3,H,W] f32 (Lab in [-1,1]) -> out [B,H,W,3] u8 BGR; lab_to_yf [512] u16 and inv_gamma [4096] u8 from
+ *   future_urban_scene_generation_b200/data/lab8.npz (scripts/make_lab_tables.py), in device memory. */
+int fusg_to_image_lab(const float *in, uint8_t *out, const uint16_t *lab_to_yf, const uint8_t *inv_gamma, int B, int H, int W, void *stream);
 /* ---- paste-back of completed crops into frames --------------------------------------
  * cv2.resize(src, dsize) with INTER_LINEAR on 8-bit, 3-channel HWC images, batched: item i reads src + src_off[i]
  * ([src_hw[2i], src_hw[2i+1], 3]) and writes dst + dst_off[i] ([dst_hw[2i], dst_hw[2i+1], 3]); offsets in bytes,

@@ -9,7 +9,7 @@ frames -- through every row of SURVEY.md section 8 in the reference's order (tra
   paste        to_image + fusg_paste_back into the 20 result frames, both generators   :393-407, :426-442
 
 Synthetic scene (synth.make_trajectory_case; elliptical sketch masks around the projected keypoints stand in for the Open3D
-renderer).  The ICN image is pasted without the 8-bit Lab->BGR step (not on the device yet).
+renderer).
 usage: python scripts/bench_clip.py [--vehicles 30] [--steps 20] [--out gpurun_out/clip.json]"""
 import argparse
 import json
@@ -141,7 +141,7 @@ def clip():
     fidx = [int(step_of_item[i]) for i in order]
     oi = torch.as_tensor(order, device=dev)
     masks_o = dst_masks[oi]
-    paste_back_batch(frames_icn, to_image_batch(icn_img)[oi].contiguous(), masks_o, infos_l, fidx)
+    paste_back_batch(frames_icn, to_image_batch(icn_img, from_LAB=True)[oi].contiguous(), masks_o, infos_l, fidx)
     paste_back_batch(frames_vun, to_image_batch(vun_img)[oi].contiguous(), masks_o, infos_l, fidx)
     ev["paste"][1].record()
     torch.cuda.synchronize()

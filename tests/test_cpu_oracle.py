@@ -220,6 +220,9 @@ def test_lab_and_icn_input_oracle_match_goldens():
     assert np.all(np.diff(z["exc_keys"].astype(np.int64)) > 0)                       # sorted, unique: the device binary-searches it
     known = np.array([[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [128, 128, 128]], np.uint8)
     assert FO.rgb2lab_u8(known).tolist() == [[0, 128, 128], [255, 128, 128], [136, 208, 195], [224, 42, 211], [82, 207, 20], [137, 128, 128]]
+    known_lab = np.array([[0, 128, 128], [255, 128, 128], [136, 208, 195], [50, 0, 255], [200, 255, 0], [17, 90, 160]], np.uint8)
+    assert FO.lab2rgb_u8(known_lab).tolist() == [[0, 0, 0], [255, 255, 255], [255, 2, 1], [0, 70, 0], [255, 47, 255], [0, 33, 0]]   # cv2 4.13 values
+    assert len(z["lab_to_yf"]) == 512 and len(z["inv_gamma"]) == 4096 and z["inv_gamma"][0] == 0 and z["inv_gamma"][4095] == 255
     gold = json.load(open(os.path.join(GOLD, "frame_golden.json")))["icn_inputs"]
     for c in gold[:5]:
         planes, normal, mask, central = synth.make_icn_pack_case(c["idx"], tuple(c["frame_hw"]))

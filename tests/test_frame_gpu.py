@@ -307,3 +307,26 @@ def test_stacked_tensor_inputs_equal_per_item_lists(cuda):
     a = paste_back_batch(torch.from_numpy(base.copy()).cuda(), crops, [it[1] for it in items], infos, fidx)
     b = paste_back_batch(torch.from_numpy(base.copy()).cuda(), crops, torch.from_numpy(np.stack([it[1] for it in items])).cuda(), infos, fidx)
     assert torch.equal(a, b)
+
+
+def test_to_image_from_lab_matches_oracle(cuda):
+    """to_image(x, from_LAB=True) on the device (fusg_to_image_lab: float -> uint8, OpenCV's 8-bit Lab -> BGR) vs the numpy oracle,
+    whose pipeline scripts/make_lab_tables.py verified against cv2 on all 2^24 (L, a, b) triples: a strided sweep of the Lab cube
+    fed through exact float encodings, random network-like outputs incl. values outside [-1, 1], and the per-image mirror."""
+    torch = cuda
+    from future_urban_scene_generation_b200.warp_learn.planes_utils import to_image_batch, to_image
+    sweep = np.stack(np.meshgrid(np.arange(0, 256, 3), np.arange(0, 256, 5), np.arange(0, 256, 5), indexing="ij"), -1).reshape(-1, 3)
+    n = 256 * 256
+    B = (len(sweep) + n - 1) // n
+    lab = np.concatenate([sweep, np.zeros((B * n - len(sweep), 3), sweep.dtype)]).reshape(B, 256, 256, 3)
+    x = np.transpose((lab.astype(np.float32) + 0.25) / 255 * 2 - 1, (0, 3, 1, 2)).copy()          # decodes back to `lab` after truncation
+    got = to_image_batch(torch.from_numpy(x).cuda(), from_LAB=True).cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b], FO.to_image_lab(x[b])), b
+        assert np.array_equal(got[b], FO.lab2rgb_u8(lab[b].astype(np.uint8))[..., ::-1])
+    rnd = np.random.default_rng(8).uniform(-1.3, 1.3, (3, 3, 128, 96)).astype(np.float32)
+    got = to_image_batch(torch.from_numpy(rnd).cuda(), from_LAB=True).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got[b], FO.to_image_lab(rnd[b]))
+    assert np.array_equal(to_image(torch.from_numpy(rnd[0]).cuda(), from_LAB=True), got[0])
+    assert np.array_equal(to_image(np.transpose(rnd[1], (1, 2, 0)), from_LAB=True), got[1])        # HWC ndarray form of the reference
