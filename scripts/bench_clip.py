@@ -33,6 +33,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--vehicles", type=int, default=30)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--chunk", type=int, default=100)
+ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--out", default=None)
 args = ap.parse_args()
 V, S, H, W = args.vehicles, args.steps, 1080, 1920
@@ -150,17 +151,21 @@ def clip():
 
 clip()                                                                  # warm-up (weight repack, allocator, table upload)
 torch.cuda.synchronize()
-n0 = _lib.kernel_launches()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-stages, res, f_icn, f_vun = clip()
-e1.record()
-torch.cuda.synchronize()
-total = e0.elapsed_time(e1)
+runs = []
+for _ in range(args.reps):                                              # host-side glue (CPU Sampler noise, Python) varies: report the best of a few
+    n0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stages, res, f_icn, f_vun = clip()
+    e1.record()
+    torch.cuda.synchronize()
+    runs.append((e0.elapsed_time(e1) - stages["sketches(synthetic)"], e0.elapsed_time(e1), stages, _lib.kernel_launches() - n0))
+runs.sort(key=lambda r: r[0])
+_, total, stages, n_launch = runs[0]
 path_ms = total - stages["sketches(synthetic)"]
 out = {"workload": f"BASELINE config 5: {V} vehicles x {S} future steps on {W}x{H} frames, {N} (vehicle, step) items, both generators, paste-back into {S} frames each",
        "items": N, "ms_total": total, "ms_path": path_ms, "items_per_s": N / path_ms * 1e3, "stages_ms": stages,
-       "gpu_launches": _lib.kernel_launches() - n0,
+       "gpu_launches": n_launch, "reps": args.reps, "ms_path_all_reps": [r[0] for r in runs],
        "items_with_out_of_frame_keypoints": int((res.plane_j[:, 0] == -2).sum().item()),
        "written_planes_per_item": float((res.plane_j >= 0).float().sum().item()) / N,
        "changed_pixels": {"icn_frames": int((f_icn != frames_dev).any(-1).sum().item()), "vunet_frames": int((f_vun != frames_dev).any(-1).sum().item())},
