@@ -612,13 +612,19 @@ __global__ void __launch_bounds__(128) k_plane_masks(const int32_t *__restrict__
     for (int w = threadIdx.x; w < words; w += blockDim.x) row[w] = ranges_word(lo, hi, rc, w);
 }
 
-__global__ void __launch_bounds__(256) k_warp_frame(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
-                                                    const int8_t *__restrict__ plane_j, const double *__restrict__ Minv,
-                                                    const uint32_t *__restrict__ masks, uint8_t *__restrict__ warped, int H, int W, int words) {
-    // grid (H, 5, B): one output row of output plane j
-    const int y = blockIdx.x, j = blockIdx.y, b = blockIdx.z;
+constexpr int WF_ROWS = 8;        // output rows per CTA of k_warp_frame: one per warp
+
+__global__ void __launch_bounds__(32 * WF_ROWS) k_warp_frame(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
+                                                            const int8_t *__restrict__ plane_j, const double *__restrict__ Minv,
+                                                            const uint32_t *__restrict__ masks, uint8_t *__restrict__ warped, int H, int W, int words,
+                                                            int row_smem) {
+    // grid (ceil(H / WF_ROWS), 5, B): WF_ROWS output rows of output plane j, one warp per row (a CTA per row meant 3.2 million CTAs
+    // for the 600-item 1080p clip).  Rows are assembled in shared memory and leave with 16-byte stores.
+    extern __shared__ __align__(16) uint8_t s_rows[];
+    const int j = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ double M[9];
-    __shared__ int s_i, s_lo, s_hi;
+    __shared__ int s_i, s_bbox[4];
     if (threadIdx.x == 0) {
         int i = -1;
         for (int k = 0; k < N_TEX; ++k) if (plane_j[b * N_TEX + k] == j) i = k;      // last writer wins
@@ -630,31 +636,50 @@ __global__ void __launch_bounds__(256) k_warp_frame(const uint8_t *__restrict__ 
                 const int vx = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2], vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
                 bbox[0] = min(bbox[0], vx); bbox[1] = max(bbox[1], vx); bbox[2] = min(bbox[2], vy); bbox[3] = max(bbox[3], vy);
             }
-            int xlo, xhi;
-            row_active_span(M, y, W, bbox, xlo, xhi);
-            s_lo = xlo; s_hi = xhi;
+            for (int k = 0; k < 4; ++k) s_bbox[k] = bbox[k];
         }
     }
     __syncthreads();
+    const int y = blockIdx.x * WF_ROWS + warp;
+    if (y >= H) return;
     uint8_t *orow = warped + ((((size_t)b * N_TEX + j) * H + y) * W) * 3;
     const int i = s_i;
-    if (i < 0 || s_lo > s_hi) {
-        for (int k = threadIdx.x; k < W * 3; k += blockDim.x) orow[k] = 0;
+    const int row_bytes = W * 3;
+    const bool vec = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);   // rows of 16-byte-multiple frames stay aligned
+    const int4 z4 = make_int4(0, 0, 0, 0);
+    int xlo = 1, xhi = 0;
+    if (i >= 0) {
+        if (lane == 0) { int bb[4] = {s_bbox[0], s_bbox[1], s_bbox[2], s_bbox[3]}; row_active_span(M, y, W, bb, xlo, xhi); }
+        xlo = __shfl_sync(0xffffffffu, xlo, 0);
+        xhi = __shfl_sync(0xffffffffu, xhi, 0);
+    }
+    if (i < 0 || xlo > xhi) {
+        if (vec) { int4 *o4 = reinterpret_cast<int4 *>(orow); for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = z4; }
+        else for (int k = lane; k < row_bytes; k += 32) orow[k] = 0;
         return;
     }
+    uint8_t *s_row = s_rows + (size_t)warp * row_smem;
     const uint8_t *simg = src + (size_t)b * H * W * 3;
     const uint32_t *mk = masks + ((size_t)b * N_TEX + i) * H * words;
     const int bw = warp_block_w(H, W);
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    for (int x = lane; x < W; x += 32) {
         uchar3 v = make_uchar3(0, 0, 0);
-        if (x >= s_lo && x <= s_hi) {
+        if (x >= xlo && x <= xhi) {
             const int bx = (x / bw) * bw;
             const RowBase rb = row_base(M, bx, y);
             int X, Y;
             src_coord(M, rb, x - bx, X, Y);
             v = bilinear_tap4<true>(simg, mk, words, H, W, X, Y);
         }
-        orow[3 * x] = v.x; orow[3 * x + 1] = v.y; orow[3 * x + 2] = v.z;
+        s_row[3 * x] = v.x; s_row[3 * x + 1] = v.y; s_row[3 * x + 2] = v.z;
+    }
+    __syncwarp();
+    if (vec) {
+        int4 *o4 = reinterpret_cast<int4 *>(orow);
+        const int4 *s4 = reinterpret_cast<const int4 *>(s_row);
+        for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = s4[k];
+    } else {
+        for (int k = lane; k < row_bytes; k += 32) orow[k] = s_row[k];
     }
 }
 
@@ -765,7 +790,15 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
         const int words = (W + 31) / 32;
         uint32_t *masks = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(workspace) + ((warp_ws_base(B) + 15) & ~(size_t)15));
         k_plane_masks<<<dim3(H, N_TEX, B), 128, 0, st>>>(src_kp, plane_j, masks, H, words);
-        k_warp_frame<<<dim3(H, N_TEX, B), 256, 0, st>>>(src, src_kp, plane_j, Minv, masks, warped, H, W, words);
+        const size_t row_smem = ((size_t)W * 3 + 15) & ~(size_t)15;
+        const size_t frame_smem = row_smem * WF_ROWS;
+        if (frame_smem > 200 * 1024) return FUSG_ERR_UNSUPPORTED;
+        static size_t frame_smem_set = 0;
+        if (frame_smem > 48 * 1024 && frame_smem > frame_smem_set) {
+            if (cudaFuncSetAttribute(k_warp_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frame_smem) != cudaSuccess) return fusg_check_launch();
+            frame_smem_set = frame_smem;
+        }
+        k_warp_frame<<<dim3((H + WF_ROWS - 1) / WF_ROWS, N_TEX, B), 32 * WF_ROWS, frame_smem, st>>>(src, src_kp, plane_j, Minv, masks, warped, H, W, words, (int)row_smem);
         fusg_count_launch(4);
     }
     return fusg_check_launch();
