@@ -399,9 +399,37 @@ def run_ours(args):
             "vunet_tflops_whole_forward": world * B * VUNET_FLOPS_PER_CROP / (ms_per_step * 1e-3) / 1e12,
             "cpu_baseline": cpu,
         }
+        if world == 1 and not args.no_icn:
+            line["icn_generator"] = icn_info(torch, synth, B, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def icn_info(torch, synth, B, dev):
+    """Informational, outside every timed region of the headline metric: the ICN generator G_Resnet (the consumer of
+    the warped planes in the reference's data flow) on the same batch size -- crops/s and FLOP-weighted tensor throughput."""
+    try:
+        from future_urban_scene_generation_b200.warp_learn.models import G_Resnet
+        torch.manual_seed(0)
+        g = G_Resnet(21).to(dev).eval()
+        xi = torch.from_numpy(synth.make_icn_inputs(0, min(B, 8), 256)).to(dev)
+        xi = xi.repeat((B + xi.shape[0] - 1) // xi.shape[0], 1, 1, 1)[:B].contiguous()
+        for _ in range(3):
+            g(xi)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g(xi)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        flops = 130124087296.0                       # per 256x256 crop, 18 convolutions (oracle/icn_oracle.py: flops_per_crop)
+        return {"crops_per_s": B / ms * 1e3, "ms_per_forward": ms, "crops": B, "tflops_whole_forward": B * flops / (ms * 1e-3) / 1e12,
+                "dtype": "fp16 operands, fp32 accumulate", "note": "not part of `value`; details in profiles/r1_icn_bench.json"}
+    except Exception as ex:                          # never let the informational block take the bench line down
+        return {"error": f"{type(ex).__name__}: {ex}"}
 
 
 def main():
@@ -412,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--crops-per-rank", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-icn", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that write to fd 1 on their own (NCCL prints its version there
     # whatever NCCL_DEBUG_FILE says) are pointed at stderr for the whole run, and print() gets the real stdout back
