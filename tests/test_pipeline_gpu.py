@@ -126,3 +126,38 @@ def test_pipeline_uint8_inputs_equal_float_inputs(cuda):
         outs.append(r)
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_config5_clip_script_runs_end_to_end(cuda):
+    """scripts/bench_clip.py at toy size: kinematics -> whole-frame fused warp -> get_icn_inputs -> ICN, VUNet, Lab->BGR, paste-back of
+    both generators -- every row of SURVEY.md section 8 chained on the device must keep composing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "bench_clip.py"), "--vehicles", "3", "--steps", "2", "--chunk", "4", "--reps", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["items"] == 6 and d["ms_path"] > 0
+    assert d["changed_pixels"]["icn_frames"] > 0 and d["changed_pixels"]["vunet_frames"] > 0
+    assert set(d["stages_ms"]) >= {"kinematics", "warp", "icn_inputs", "icn", "vunet", "paste"}
+
+
+def test_icn_generator_non_power_of_two_frames_use_the_direct_kernel(cuda):
+    """Frame sizes the tcgen05 tiling does not cover (not powers of two) are served by the CUDA-core kernel of the same library --
+    same program, same tolerance; nothing silently differs."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.warp_learn.models import G_Resnet
+    from oracle import icn_oracle as IO
+    sd = IO.make_state_dict(0)
+    g = G_Resnet(21)
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
+    x = torch.from_numpy(synth.make_icn_inputs(2, 1, 96)[:, :, :80, :])            # 80 x 96
+    with torch.no_grad():
+        want = IO.forward(sd, x)
+    got = g(x.cuda())
+    assert got.shape == want.shape and (got.cpu() - want).abs().max().item() <= 1e-2
