@@ -18,6 +18,7 @@
 // Compiled with -fmad=false (see warp_geom.cuh).
 #include <cuda_runtime.h>
 #include <climits>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include "../../include/fusg.h"
@@ -776,11 +777,31 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
                 return fusg_check_launch();
             hl_attr = true;
         }
-        // longest solves first: the 6-point list (at most 2 side planes per crop), then the 4-point list (at most 3)
+        // longest solves first: the 6-point list (at most 2 side planes per crop), then the 4-point list (at most 3).  The two lists are
+        // independent and both kernels are limited by shared memory per SM (3 x 72 KB / 5 x 40.5 KB CTAs), so the 4-point list runs on a
+        // forked stream and fills the SMs the 6-point list's last wave leaves idle.
+        static const int fork_lists = getenv("FUSG_WARP_NO_LIST_FORK") ? 0 : 1;
+        static cudaStream_t side = nullptr;
+        static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        if (fork_lists && !side) {
+            if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+                side = nullptr;
+                return fusg_check_launch();
+            }
+        }
+        cudaStream_t st4 = st;
+        if (fork_lists) {
+            if (fusg_record_cuda(cudaEventRecord(ev_fork, st)) != FUSG_OK || fusg_record_cuda(cudaStreamWaitEvent(side, ev_fork, 0)) != FUSG_OK) return FUSG_ERR_CUDA;
+            st4 = side;
+        }
         k_homography_list<<<(2 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES6 * HL_THREADS * 8, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
                                                                                                                    list6, list4, 0);
-        k_homography_list<<<(3 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES4 * HL_THREADS * 8, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
-                                                                                                                   list6, list4, 1);
+        k_homography_list<<<(3 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES4 * HL_THREADS * 8, st4>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
+                                                                                                                    list6, list4, 1);
+        if (fork_lists) {
+            if (fusg_record_cuda(cudaEventRecord(ev_join, side)) != FUSG_OK || fusg_record_cuda(cudaStreamWaitEvent(st, ev_join, 0)) != FUSG_OK) return FUSG_ERR_CUDA;
+        }
         fusg_count_launch(2);
     }
     if (!frame_path) {
