@@ -594,23 +594,28 @@ __global__ void __launch_bounds__(256) k_warp_perspective(const uint8_t *__restr
 // Frames larger than the shared-memory path (the reference runs the stage on whole 1280x720 frames,
 // GUI/app_interface.py:181): same arithmetic, source and polygon bit masks read from global memory / L2.
 // ============================================================================================
-__global__ void __launch_bounds__(128) k_plane_masks(const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
-                                                     uint32_t *__restrict__ masks, int H, int words) {
-    // grid (H, 5, B): bit mask of row y of SOURCE plane i (only for planes that are warped)
-    const int y = blockIdx.x, i = blockIdx.y, b = blockIdx.z;
+constexpr int PM_ROWS = 8;         // mask rows per CTA of k_plane_masks: one per warp
+
+__global__ void __launch_bounds__(32 * PM_ROWS) k_plane_masks(const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
+                                                             uint32_t *__restrict__ masks, int H, int words) {
+    // grid (ceil(H / PM_ROWS), 5, B): bit mask of PM_ROWS rows of SOURCE plane i (only for planes that are warped), a warp per row
+    const int i = blockIdx.y, b = blockIdx.z;
     if (plane_j[b * N_TEX + i] < 0) return;
-    __shared__ int lo[MAX_RANGES], hi[MAX_RANGES], rc;
-    if (threadIdx.x == 0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * PM_ROWS + warp;
+    if (y >= H) return;
+    __shared__ int s_lo[PM_ROWS][MAX_RANGES], s_hi[PM_ROWS][MAX_RANGES], s_rc[PM_ROWS];
+    if (lane == 0) {
         int px[6], py[6], l[MAX_RANGES], h[MAX_RANGES];
         const int n = c_plane_n[i];
         for (int k = 0; k < n; ++k) { px[k] = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2]; py[k] = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1]; }
         const int c = poly_row_ranges(px, py, n, y, l, h);
-        for (int k = 0; k < c; ++k) { lo[k] = l[k]; hi[k] = h[k]; }
-        rc = c;
+        for (int k = 0; k < c; ++k) { s_lo[warp][k] = l[k]; s_hi[warp][k] = h[k]; }
+        s_rc[warp] = c;
     }
-    __syncthreads();
+    __syncwarp();
     uint32_t *row = masks + (((size_t)b * N_TEX + i) * H + y) * words;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) row[w] = ranges_word(lo, hi, rc, w);
+    for (int w = lane; w < words; w += 32) row[w] = ranges_word(s_lo[warp], s_hi[warp], s_rc[warp], w);
 }
 
 constexpr int WF_ROWS = 8;        // output rows per CTA of k_warp_frame: one per warp
@@ -810,7 +815,7 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     } else {
         const int words = (W + 31) / 32;
         uint32_t *masks = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(workspace) + ((warp_ws_base(B) + 15) & ~(size_t)15));
-        k_plane_masks<<<dim3(H, N_TEX, B), 128, 0, st>>>(src_kp, plane_j, masks, H, words);
+        k_plane_masks<<<dim3((H + PM_ROWS - 1) / PM_ROWS, N_TEX, B), 32 * PM_ROWS, 0, st>>>(src_kp, plane_j, masks, H, words);
         const size_t row_smem = ((size_t)W * 3 + 15) & ~(size_t)15;
         const size_t frame_smem = row_smem * WF_ROWS;
         if (frame_smem > 200 * 1024) return FUSG_ERR_UNSUPPORTED;
