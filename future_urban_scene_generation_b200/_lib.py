@@ -55,7 +55,7 @@ def _load():
         "fusg_paste_back": ([vp] * 7 + [sz, i, i, i, i, i, i, vp], i),
         "fusg_u8_to_vunet_inputs": ([vp] * 5 + [i, i, vp], i),
         "fusg_mask_bbox": ([vp] * 4 + [i, i, vp], i),
-        "fusg_pack_icn_inputs": ([vp] * 8 + [i, vp, i, i, i, i, vp], i),
+        "fusg_pack_icn_inputs": ([vp] * 8 + [i, vp, vp, i, i, i, i, vp], i),
         "fusg_pack_vunet_inputs": ([vp] * 10 + [i, i, i, i, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():

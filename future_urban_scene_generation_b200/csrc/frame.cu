@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) k_u8_to_inputs(const uint8_t *__restrict_
 // OpenCV's uint8 Lab is the integer pipeline below PLUS a sorted list of 1671 colours where its interpolated table deviates
 // by one in a or b (scripts/make_lab_tables.py: verified against cv2 on all 2^24 colours).
 // ---------------------------------------------------------------------------------------------------------------
-struct LabTables { const uint16_t *gamma_tab, *cbrt_tab; const uint32_t *exc_keys; const uint16_t *exc_vals; int n_exc; };
+struct LabTables { const uint16_t *gamma_tab, *cbrt_tab; const uint32_t *exc_keys; const uint16_t *exc_vals; int n_exc; const uint32_t *exc_bitmap; };
 
 __device__ __forceinline__ void rgb2lab_u8(const LabTables &T, int r, int g, int b, int *lab) {
     const int R = __ldg(T.gamma_tab + r), G = __ldg(T.gamma_tab + g), B = __ldg(T.gamma_tab + b);
@@ -282,6 +282,8 @@ __device__ __forceinline__ void rgb2lab_u8(const LabTables &T, int r, int g, int
     lab[1] = min(max((500 * (fX - fY) + (128 << 15) + 16384) >> 15, 0), 255);
     lab[2] = min(max((200 * (fY - fZ) + (128 << 15) + 16384) >> 15, 0), 255);
     const uint32_t key = ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+    // one bit per colour (2 MB, L2 resident) says whether the colour is an exception at all: 1 in 10,000 pixels searches the list
+    if (T.exc_bitmap && !((__ldg(T.exc_bitmap + (key >> 5)) >> (key & 31u)) & 1u)) return;
     int lo = 0, hi = T.n_exc;                           // first index with exc_keys[i] >= key
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -503,12 +505,12 @@ extern "C" int fusg_step_keypoints(const double *kp3d, const int32_t *vehicle, c
 
 extern "C" int fusg_pack_icn_inputs(const uint8_t *planes, const uint8_t *normals, const uint8_t *central, const int32_t *bbox,
                                     const uint16_t *gamma_tab, const uint16_t *cbrt_tab, const uint32_t *exc_keys, const uint16_t *exc_vals, int n_exc,
-                                    float *out, int B, int Hf, int Wf, int res, void *stream) {
+                                    const uint32_t *exc_bitmap, float *out, int B, int Hf, int Wf, int res, void *stream) {
     if (!planes || !normals || !central || !bbox || !gamma_tab || !cbrt_tab || !out || B <= 0 || Hf <= 0 || Wf <= 0 || res <= 0 || n_exc < 0) return FUSG_ERR_ARG;
     if (n_exc > 0 && (!exc_keys || !exc_vals)) return FUSG_ERR_ARG;
     if (B > 65535) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    LabTables T{gamma_tab, cbrt_tab, exc_keys, exc_vals, n_exc};
+    LabTables T{gamma_tab, cbrt_tab, exc_keys, exc_vals, n_exc, exc_bitmap};
     k_pack_icn<<<dim3((res * res + 255) / 256, 7, B), 256, 0, st>>>(planes, normals, central, bbox, T, out, Hf, Wf, res);
     fusg_count_launch(1);
     return fusg_check_launch();

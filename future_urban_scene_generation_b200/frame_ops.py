@@ -284,10 +284,14 @@ def _lab_tables(torch, device):
     if key not in _LAB_DEV:
         import os
         z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lab8.npz"))
+        keys = z["exc_keys"].astype(np.int64)
+        bitmap = np.zeros(1 << 19, np.int64)                 # one bit per colour: is it in the exception list at all
+        np.bitwise_or.at(bitmap, keys >> 5, np.int64(1) << (keys & 31))
         _LAB_DEV[key] = (torch.from_numpy(z["gamma_tab"].astype(np.int32)).to(torch.uint16).to(device),
                          torch.from_numpy(z["cbrt_tab"].astype(np.int32)).to(torch.uint16).to(device),
                          torch.from_numpy(z["exc_keys"].astype(np.int64)).to(torch.uint32).to(device),
-                         torch.from_numpy(z["exc_vals"].astype(np.int32)).to(torch.uint16).to(device))
+                         torch.from_numpy(z["exc_vals"].astype(np.int32)).to(torch.uint16).to(device),
+                         torch.from_numpy(bitmap).to(torch.uint32).to(device))
     return _LAB_DEV[key]
 
 
@@ -344,10 +348,10 @@ def get_icn_inputs_batch(planes, sketch_normals, sketch_masks, central_crops, ic
     bb = bbox.cpu().numpy()                              # crop_info is host data in the reference too (a few ints per vehicle)
     if (bb[:, 2] < 0).any():
         raise ValueError("get_icn_inputs_batch: empty sketch mask (np.min of an empty array in the reference)")
-    g, c, ek, ev = _lab_tables(torch, dev)
+    g, c, ek, ev, bm = _lab_tables(torch, dev)
     out = torch.empty((B, 21, icn_h, icn_w), dtype=torch.float32, device=dev)
     _lib.check(L.fusg_pack_icn_inputs(_lib.ptr(pl), _lib.ptr(nm), _lib.ptr(ct), _lib.ptr(bbox), _lib.ptr(g), _lib.ptr(c), _lib.ptr(ek), _lib.ptr(ev),
-                                      int(ek.numel()), _lib.ptr(out), B, Hf, Wf, icn_h, _lib.stream_ptr(torch)), "fusg_pack_icn_inputs")
+                                      int(ek.numel()), _lib.ptr(bm), _lib.ptr(out), B, Hf, Wf, icn_h, _lib.stream_ptr(torch)), "fusg_pack_icn_inputs")
     out._keep = (pl, nm, ct, bbox)
     return out, [square_crop_info((Hf, Wf), bb[b]) for b in range(B)]
 

@@ -271,10 +271,11 @@ int fusg_pack_vunet_inputs(const uint8_t *frames, const int32_t *frame_idx, cons
  * with square_crop = utils/crop_utils.py:4-52, resize = cv2.resize(..., (res,res)), Lab = cv2.cvtColor(COLOR_RGB2LAB / COLOR_BGR2LAB) on
  * uint8, then ToTensor + Normalize(0.5, 0.5).  The Lab tables (gamma_tab [256] u16, cbrt_tab [3072] u16) and the sorted exception list
  * (exc_keys [n_exc] u32 = R<<16|G<<8|B, exc_vals [n_exc] u16 = a<<8|b) come from future_urban_scene_generation_b200/data/lab8.npz,
- * generated and verified against cv2 on all 2^24 colours by scripts/make_lab_tables.py; all in device memory. */
+ * generated and verified against cv2 on all 2^24 colours by scripts/make_lab_tables.py; exc_bitmap (may be NULL): [2^19] u32, bit
+ * (key & 31) of word (key >> 5) set iff key is in exc_keys -- lets 9,999 of 10,000 pixels skip the list search; all in device memory. */
 int fusg_pack_icn_inputs(const uint8_t *planes, const uint8_t *normals, const uint8_t *central, const int32_t *bbox,
                          const uint16_t *gamma_tab, const uint16_t *cbrt_tab, const uint32_t *exc_keys, const uint16_t *exc_vals, int n_exc,
-                         float *out, int B, int Hf, int Wf, int res, void *stream);
+                         const uint32_t *exc_bitmap, float *out, int B, int Hf, int Wf, int res, void *stream);
 /* The tail of the same assembly when the three 256x256 uint8 images already exist (trajectory_inference.py:221-225):
  *   x = cat(to_tensor(mask_bbox), to_tensor(normal_src[..., ::-1])), y = to_tensor(normal_dst[..., ::-1]);
  * inputs [B,res,res,3] u8 -> x [B,6,res,res] f32, y [B,3,res,res] f32.  Lets a host ship 9 bytes per pixel instead of 36. */
