@@ -24,7 +24,6 @@
 #include "../../include/fusg.h"
 #include "fusg_common.h"
 #include "warp_geom.cuh"
-#include "warp_geom_thread.cuh"
 
 namespace fusg {
 
@@ -201,9 +200,8 @@ __global__ void __launch_bounds__(HG_WARPS * 32) k_homography(const int32_t *__r
 }
 
 
-// Large batches: thread-per-solve (each solve is a long dependent fp64 chain; 32x more of them overlap
-// than with a warp per solve), fed from COMPACTED task lists so that every lane of a warp has a real solve
-// of the same kind: k_plane_gate applies the gating / remap of planes_utils.py:57-68 and appends the
+// Large batches: solves are fed from COMPACTED task lists so that no warp is spent on a skipped plane:
+// k_plane_gate applies the gating / remap of planes_utils.py:57-68 and appends the
 // surviving (crop, plane) tasks to a 6-point list (left/right, LM-refined) or a 4-point list; skipped
 // planes get their outputs written there.  Outputs are indexed by task id, so the (non-deterministic)
 // list order does not affect results.
@@ -232,37 +230,46 @@ __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ 
     }
 }
 
-constexpr int HL_THREADS = 32;                     // one warp per block: 3 blocks (6-point, 72 KB) or 5 blocks (4-point, 40.5 KB) per SM
-constexpr int HL_DOUBLES6 = 288, HL_DOUBLES4 = 162;   // scratch doubles per thread: LM arrays alias the Jacobi matrices
-
-// which = 0: the 6-point list (Jacobi + LM refinement), which = 1: the 4-point list (Jacobi only)
-__global__ void __launch_bounds__(HL_THREADS) k_homography_list(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
-                                                                int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
-                                                                const int *__restrict__ counters, const int *__restrict__ list6,
-                                                                const int *__restrict__ list4, int which) {
-    extern __shared__ double hl_scratch[];
-    const int count = counters[which];
-    const int idx = blockIdx.x * HL_THREADS + threadIdx.x;
-    if (idx >= count) return;
-    const int t = which == 0 ? list6[idx] : list4[idx];
+// One warp per surviving task, 6-point (LM-refined, ~10x longer) tasks first.
+__global__ void __launch_bounds__(HG_WARPS * 32) k_homography_list(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                                                  int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
+                                                                  const int *__restrict__ counters, const int *__restrict__ list6,
+                                                                  const int *__restrict__ list4) {
+    __shared__ HomogScratch scratch[HG_WARPS];
+    __shared__ int pts[HG_WARPS][24];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c6 = counters[0], c4 = counters[1];
+    const int idx = blockIdx.x * HG_WARPS + warp;
+    if (idx >= c6 + c4) return;
+    const int t = idx < c6 ? list6[idx] : list4[idx - c6];
     const int b = t / N_TEX, i = t % N_TEX, j = plane_j[t];
     const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
     const int n = c_plane_n[i];
-    int s[12], d[12];
-    for (int k = 0; k < n; ++k) {
-        s[2 * k] = sk[2 * c_plane_kp[i][k]]; s[2 * k + 1] = sk[2 * c_plane_kp[i][k] + 1];
-        d[2 * k] = dk[2 * c_plane_kp[j][k]]; d[2 * k + 1] = dk[2 * c_plane_kp[j][k] + 1];
+    if (lane < n) {
+        pts[warp][2 * lane] = sk[2 * c_plane_kp[i][lane]];
+        pts[warp][2 * lane + 1] = sk[2 * c_plane_kp[i][lane] + 1];
+        pts[warp][12 + 2 * lane] = dk[2 * c_plane_kp[j][lane]];
+        pts[warp][12 + 2 * lane + 1] = dk[2 * c_plane_kp[j][lane] + 1];
     }
+    __syncwarp();
     double Hm[9], Mi[9];
     // H21 is only ever used through its "is None" test, the same (symmetric) degeneracy test as H12's
-    if (!find_homography_thread(s, d, n, Hm, StridedArr<HL_THREADS>{hl_scratch + threadIdx.x})) {
-        plane_j[t] = -1;
+    const bool good = find_homography_warp(scratch[warp], lane, pts[warp], pts[warp] + 12, n, Hm);
+    if (!good) {
+#pragma unroll
         for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
     } else {
         invert3(Hm, Mi);
     }
-    for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
-    if (H12) for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
+    if (lane == 0) {
+        if (!good) plane_j[t] = -1;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
+        if (H12) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(HG_WARPS * 32) k_find_homography(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
@@ -776,38 +783,8 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
         int *list6 = counters + 4, *list4 = list6 + 2 * (size_t)B;
         if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
         k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
-        static bool hl_attr = false;
-        if (!hl_attr) {
-            if (cudaFuncSetAttribute(k_homography_list, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_DOUBLES6 * HL_THREADS * 8) != cudaSuccess)
-                return fusg_check_launch();
-            hl_attr = true;
-        }
-        // longest solves first: the 6-point list (at most 2 side planes per crop), then the 4-point list (at most 3).  The two lists are
-        // independent and both kernels are limited by shared memory per SM (3 x 72 KB / 5 x 40.5 KB CTAs), so the 4-point list runs on a
-        // forked stream and fills the SMs the 6-point list's last wave leaves idle.
-        static const int fork_lists = getenv("FUSG_WARP_NO_LIST_FORK") ? 0 : 1;
-        static cudaStream_t side = nullptr;
-        static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-        if (fork_lists && !side) {
-            if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
-                side = nullptr;
-                return fusg_check_launch();
-            }
-        }
-        cudaStream_t st4 = st;
-        if (fork_lists) {
-            if (fusg_record_cuda(cudaEventRecord(ev_fork, st)) != FUSG_OK || fusg_record_cuda(cudaStreamWaitEvent(side, ev_fork, 0)) != FUSG_OK) return FUSG_ERR_CUDA;
-            st4 = side;
-        }
-        k_homography_list<<<(2 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES6 * HL_THREADS * 8, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
-                                                                                                                   list6, list4, 0);
-        k_homography_list<<<(3 * B + HL_THREADS - 1) / HL_THREADS, HL_THREADS, HL_DOUBLES4 * HL_THREADS * 8, st4>>>(src_kp, dst_kp, plane_j, H12, Minv, counters,
-                                                                                                                    list6, list4, 1);
-        if (fork_lists) {
-            if (fusg_record_cuda(cudaEventRecord(ev_join, side)) != FUSG_OK || fusg_record_cuda(cudaStreamWaitEvent(st, ev_join, 0)) != FUSG_OK) return FUSG_ERR_CUDA;
-        }
-        fusg_count_launch(2);
+        k_homography_list<<<(N_TEX * B + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4);
+        fusg_count_launch(1);
     }
     if (!frame_path) {
         k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);

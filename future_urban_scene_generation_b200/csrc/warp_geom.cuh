@@ -155,15 +155,17 @@ __device__ __forceinline__ double plane_distance(const double *E, const double *
 //
 // The arithmetic is OpenCV's, element for element (normalised DLT -> 9x9 LtL -> cv::eigen's Jacobi
 // with its max-pivot bookkeeping -> de-normalisation -> LMSolver schedule for n > 4), so every
-// matrix entry sees the same fp64 operations in the same order as the scalar oracle; the warp only
+// matrix entry sees the same fp64 operations in the same order as the scalar oracle (whose n = 6 results are
+// bit-identical to cv2 4.13.0, scripts/check_lm_vs_cv2.py); the warp only
 // spreads *independent* entries over its lanes: the 45 LtL entries, the <= 27 element pairs of a
 // Jacobi rotation, the 17 pivot candidates (shuffle arg-max), the 36+8 normal-equation entries and
 // the per-point residual/Jacobian rows.  Matrices live in shared memory (dynamic indices).
 // ---------------------------------------------------------------------------------------------
 struct HomogScratch {
-    double A[81], V[81], W[9];          // Jacobi: matrix, eigenvectors (rows), eigenvalues
-    double J[96], N[64], r[12], v[8];   // LM: Jacobian 12x8, normal matrix, residual, J^T r
-    int indR[9], indC[9], perm[9], pad;
+    double A[81], V[81], W[9];            // Jacobi: matrix (destroyed), eigenvectors (rows), eigenvalues (sorted)
+    double J[108], N[81];                 // LM: Jacobian 12x9, normal matrix J^T J
+    double r[12], rd[12], v[9], d[9], q[9], td[9];   // residual, trial residual, J^T r, step, back-substitution / scratch
+    int indR[9], indC[9], perm[9], skip[9];
 };
 
 __device__ __forceinline__ double cv_hypot(double a, double b) {
@@ -271,47 +273,59 @@ __device__ __forceinline__ double dlt_ly(int idx, double X, double Y, double y) 
     switch (idx) { case 3: return X; case 4: return Y; case 5: return 1; case 6: return -y * X; case 7: return -y * Y; case 8: return -y; default: return 0; }
 }
 
-// x = A^-1 b, 8x8 SPD, square-root-free Cholesky; A is read from (shared) memory, everything else
-// stays in registers (all loops have constant bounds).  Same operation order as the oracle's ldl_solve.
-__device__ __forceinline__ void ldl_solve8(const double *A, const double *b, double *x) {
-    double L[64], Dg[8], y[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        double dj = A[j * 8 + j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) dj -= L[j * 8 + k] * L[j * 8 + k] * Dg[k];
-        Dg[j] = dj;
-        const double inv = dj > 0 ? 1. / dj : 0.;
-#pragma unroll
-        for (int i = j + 1; i < 8; ++i) {
-            double s = A[i * 8 + j];
-#pragma unroll
-            for (int k = 0; k < j; ++k) s -= L[i * 8 + k] * L[j * 8 + k] * Dg[k];
-            L[i * 8 + j] = s * inv;
+// cv::solve(A, b, x, DECOMP_EIG) for the symmetric 9x9 in sc.A (destroyed): Jacobi factors, then
+// SVBkSb with OpenCV's eigenvalue cut |w_i| <= 2 eps sum(w).  b: 9 doubles in shared memory; result in sc.d.
+// With `diag_only` the routine instead returns max_c |(A^-1)_cc| of cv::invert(A, DECOMP_EIG) (LMSolver's
+// lambda re-initialisation), seeded with DBL_EPSILON like the caller does.
+__device__ inline double eig_solve_warp(HomogScratch &sc, const int lane, const double *b, bool diag_only) {
+    constexpr int n = 9;
+    jacobi_eig_warp(sc, lane);
+    double threshold = 0;
+    for (int i = 0; i < n; ++i) threshold += sc.W[i];
+    threshold *= DBL_EPSILON * 2;
+    if (!diag_only) {
+        if (lane < n) {
+            const double wi = sc.W[lane];
+            const double *row = sc.V + n * sc.perm[lane];
+            const bool cut = fabs(wi) <= threshold;
+            double acc = 0;
+            for (int j = 0; j < n; ++j) acc += row[j] * b[j];
+            acc *= 1 / wi;
+            sc.q[lane] = acc;
+            sc.skip[lane] = cut;
         }
+        __syncwarp();
+        if (lane < n) {
+            double x = 0;
+            for (int i = 0; i < n; ++i)
+                if (!sc.skip[i]) x = x + sc.q[i] * sc.V[n * sc.perm[i] + lane];
+            sc.d[lane] = x;
+        }
+        __syncwarp();
+        return 0;
+    }
+    double mx = 0;
+    if (lane < n) {
+        double x = 0;
+        for (int i = 0; i < n; ++i) {
+            const double wi = sc.W[i];
+            if (fabs(wi) <= threshold) continue;
+            const double vic = sc.V[n * sc.perm[i] + lane];
+            const double sv = vic * (1 / wi);
+            x = x + sv * vic;
+        }
+        mx = fabs(x);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        double s = b[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) s -= L[i * 8 + k] * y[k];
-        y[i] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = Dg[i] > 0 ? y[i] / Dg[i] : 0.;
-#pragma unroll
-    for (int i = 7; i >= 0; --i) {
-        double s = y[i];
-#pragma unroll
-        for (int k = i + 1; k < 8; ++k) s -= L[k * 8 + i] * x[k];
-        x[i] = s;
-    }
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    return fmax(DBL_EPSILON, mx);
 }
 
-// residual (+ Jacobian rows) of correspondence `i` at parameters h (fundam.cpp HomographyRefineCallback)
+// residual (+ Jacobian rows) of one correspondence at parameters h -- fundam.cpp HomographyRefineCallback
+// as compiled into opencv-python 4.13.0: NINE parameters (h[8] in the denominator, 2n x 9 Jacobian).
 __device__ __forceinline__ void lm_point(float Mxf, float Myf, float mxf, float myf, const double *h, double *err, double *Jrows) {
     const double Mx = Mxf, My = Myf;
-    double ww = h[6] * Mx + h[7] * My + 1.;
+    double ww = h[6] * Mx + h[7] * My + h[8];
     ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
     const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
     const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
@@ -320,114 +334,115 @@ __device__ __forceinline__ void lm_point(float Mxf, float Myf, float mxf, float 
     if (Jrows) {
         Jrows[0] = Mx * ww; Jrows[1] = My * ww; Jrows[2] = ww;
         Jrows[3] = Jrows[4] = Jrows[5] = 0.;
-        Jrows[6] = -Mx * ww * xi; Jrows[7] = -My * ww * xi;
-        Jrows[8] = Jrows[9] = Jrows[10] = 0.;
-        Jrows[11] = Mx * ww; Jrows[12] = My * ww; Jrows[13] = ww;
-        Jrows[14] = -Mx * ww * yi; Jrows[15] = -My * ww * yi;
+        Jrows[6] = -Mx * ww * xi; Jrows[7] = -My * ww * xi; Jrows[8] = -ww * xi;
+        Jrows[9] = Jrows[10] = Jrows[11] = 0.;
+        Jrows[12] = Mx * ww; Jrows[13] = My * ww; Jrows[14] = ww;
+        Jrows[15] = -Mx * ww * yi; Jrows[16] = -My * ww * yi; Jrows[17] = -ww * yi;
     }
 }
 
-__device__ __forceinline__ double dot4_8(const double *a, const double *b) {
+// cv::Mat::dot (CV_64F, 9 elements) as the AVX2/FMA dispatch of the 4.13.0 wheel evaluates it:
+// per group of four t = fma(a0,b0, a1*b1); t = fma(a2,b2,t); t = fma(a3,b3,t); res += t; tail res = fma(a,b,res).
+__device__ __forceinline__ double cv_dot9(const double *a, const double *b) {
     double res = 0;
-    res += a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
-    res += a[4] * b[4] + a[5] * b[5] + a[6] * b[6] + a[7] * b[7];
-    return res;
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
+        double t = __fma_rn(a[i], b[i], a[i + 1] * b[i + 1]);
+        t = __fma_rn(a[i + 2], b[i + 2], t);
+        t = __fma_rn(a[i + 3], b[i + 3], t);
+        res += t;
+    }
+    return __fma_rn(a[8], b[8], res);
 }
 
-// LM refinement (LMSolver schedule, maxIters 10, eps FLT_EPSILON); h8 uniform across the warp.
-// Mf/mf: this lane's correspondence (lane < count).
-__device__ inline void lm_refine_warp(HomogScratch &sc, const int lane, const int count, float Mxf, float Myf, float mxf, float myf, double *h8) {
+// cv::gemm row . vector (GEMMSingleMul, one-column result): 4 interleaved accumulators, tail into s0
+__device__ __forceinline__ double gemm_rowdot(const double *a, int astride, const double *b, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = 0;
+    for (; k <= n - 4; k += 4) {
+        s0 += a[k * astride] * b[k];
+        s1 += a[(k + 1) * astride] * b[k + 1];
+        s2 += a[(k + 2) * astride] * b[k + 2];
+        s3 += a[(k + 3) * astride] * b[k + 3];
+    }
+    for (; k < n; ++k) s0 += a[k * astride] * b[k];
+    return ((s0 + s1) + s2) + s3;
+}
+
+// LM refinement (calib3d/levmarq.cpp LMSolverImpl::run, maxIters 10, epsx = epsf = FLT_EPSILON) of all nine
+// entries of H; h9 uniform across the warp.  Mf/mf: this lane's correspondence (lane < count).
+__device__ inline void lm_refine_warp(HomogScratch &sc, const int lane, const int count, float Mxf, float Myf, float mxf, float myf, double *h9) {
+    constexpr int lx = 9;
     const int rows = 2 * count;
     const double epsx = FLT_EPSILON, epsf = FLT_EPSILON;
-    double x[8], xd[8], d[8], D[8], temp_d[8], vv[8];
+    double x[lx], xd[lx], D[lx];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = h8[i];
+    for (int i = 0; i < lx; ++i) x[i] = h9[i];
     auto residual = [&](const double *h, double *rdst, bool jac) {
         __syncwarp();
-        if (lane < count) lm_point(Mxf, Myf, mxf, myf, h, rdst + 2 * lane, jac ? sc.J + 16 * lane : nullptr);
+        if (lane < count) lm_point(Mxf, Myf, mxf, myf, h, rdst + 2 * lane, jac ? sc.J + 2 * lx * lane : nullptr);
         __syncwarp();
     };
     auto sumsq = [&](const double *rv) { double S = 0; for (int i = 0; i < rows; ++i) S += rv[i] * rv[i]; return S; };
     auto normal_eq = [&]() {
-        // N = J^T J (sequential over rows), v = J^T r (4 interleaved accumulators) -- one entry per lane
-        for (int e = lane; e < 36 + 8; e += 32) {
-            if (e < 36) {
+        // N = J^T J (cv::mulTransposed, sequential over rows), v = J^T r (cv::gemm) -- one entry per lane
+        for (int e = lane; e < 45 + lx; e += 32) {
+            if (e < 45) {
                 int i = 0, rem = e;
-                while (rem >= 8 - i) { rem -= 8 - i; ++i; }
+                while (rem >= lx - i) { rem -= lx - i; ++i; }
                 const int j = i + rem;
-                double s = 0;
-                for (int k = 0; k < rows; ++k) s += sc.J[k * 8 + i] * sc.J[k * 8 + j];
-                sc.N[i * 8 + j] = s; sc.N[j * 8 + i] = s;
+                double acc = 0;
+                for (int k = 0; k < rows; ++k) acc += sc.J[k * lx + i] * sc.J[k * lx + j];
+                sc.N[i * lx + j] = acc; sc.N[j * lx + i] = acc;
             } else {
-                const int i = e - 36;
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                int k = 0;
-                for (; k <= rows - 4; k += 4) {
-                    s0 += sc.J[k * 8 + i] * sc.r[k];
-                    s1 += sc.J[(k + 1) * 8 + i] * sc.r[k + 1];
-                    s2 += sc.J[(k + 2) * 8 + i] * sc.r[k + 2];
-                    s3 += sc.J[(k + 3) * 8 + i] * sc.r[k + 3];
-                }
-                for (; k < rows; ++k) s0 += sc.J[k * 8 + i] * sc.r[k];
-                sc.v[i] = ((s0 + s1) + s2) + s3;
+                const int i = e - 45;
+                sc.v[i] = gemm_rowdot(sc.J + i, lx, sc.r, rows);
             }
         }
         __syncwarp();
     };
-    double *rd = sc.A;                       // the Jacobi matrix is dead by now: reuse as trial residual
     residual(x, sc.r, true);
     double S = sumsq(sc.r);
     normal_eq();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) D[i] = sc.N[i * 8 + i];
+    for (int i = 0; i < lx; ++i) D[i] = sc.N[i * lx + i];
     const double Rlo = 0.25, Rhi = 0.75;
     double lambda = 1, lc = 0.75;
     int iter = 0;
-    double *Ap = sc.V;                       // eigenvectors are dead too: damped normal matrix
     for (;;) {
         __syncwarp();
-        for (int e = lane; e < 64; e += 32) Ap[e] = sc.N[e] + ((e >> 3) == (e & 7) ? lambda * D[e & 7] : 0.0);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) vv[i] = sc.v[i];
-        ldl_solve8(Ap, vv, d);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xd[i] = x[i] - d[i];
-        residual(xd, rd, false);
-        const double Sd = sumsq(rd);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k += 4) {
-                s0 += sc.N[i * 8 + k] * d[k];
-                s1 += sc.N[i * 8 + k + 1] * d[k + 1];
-                s2 += sc.N[i * 8 + k + 2] * d[k + 2];
-                s3 += sc.N[i * 8 + k + 3] * d[k + 3];
-            }
-            temp_d[i] = -1. * (((s0 + s1) + s2) + s3) + 2. * vv[i];
+        for (int e = lane; e < lx * lx; e += 32) {
+            const int ri = e / lx, ci = e - ri * lx;
+            double a = sc.N[e];
+            if (ri == ci) a += lambda * D[ri];
+            sc.A[e] = a;
         }
-        const double dS = dot4_8(d, temp_d);
+        __syncwarp();
+        eig_solve_warp(sc, lane, sc.v, false);               // step in sc.d
+#pragma unroll
+        for (int i = 0; i < lx; ++i) xd[i] = x[i] - sc.d[i];
+        residual(xd, sc.rd, false);
+        const double Sd = sumsq(sc.rd);
+        // temp_d = -N d + 2 v  (cv::gemm(A, d, -1, v, 2))
+        if (lane < lx) sc.td[lane] = -1. * gemm_rowdot(sc.N + lane * lx, 1, sc.d, lx) + 2. * sc.v[lane];
+        __syncwarp();
+        const double dS = cv_dot9(sc.d, sc.td);
         const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+        double nd = 0;
+#pragma unroll
+        for (int i = 0; i < lx; ++i) nd = fmax(nd, fabs(sc.d[i]));
         if (R > Rhi) {
             lambda *= 0.5;
             if (lambda < lc) lambda = 0;
         } else if (R < Rlo) {
-            const double t = dot4_8(d, vv);
+            const double t = cv_dot9(sc.d, sc.v);
             double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
             nu = fmin(fmax(nu, 2.), 10.);
             if (lambda == 0) {
-                double maxval = DBL_EPSILON;
-                for (int c = 0; c < 8; ++c) {
-                    double e[8], col[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) e[q] = (q == c) ? 1. : 0.;
-                    ldl_solve8(sc.N, e, col);
-                    double cc = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) cc = (q == c) ? col[q] : cc;
-                    maxval = fmax(maxval, fabs(cc));
-                }
+                __syncwarp();
+                for (int e = lane; e < lx * lx; e += 32) sc.A[e] = sc.N[e];
+                __syncwarp();
+                const double maxval = eig_solve_warp(sc, lane, nullptr, true);
                 lambda = lc = 1. / maxval;
                 nu *= 0.5;
             }
@@ -436,19 +451,17 @@ __device__ inline void lm_refine_warp(HomogScratch &sc, const int lane, const in
         if (Sd < S) {
             S = Sd;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = xd[i];
+            for (int i = 0; i < lx; ++i) x[i] = xd[i];
             residual(x, sc.r, true);
             normal_eq();
         }
         iter++;
-        double nd = 0, nr = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) nd = fmax(nd, fabs(d[i]));
+        double nr = 0;
         for (int i = 0; i < rows; ++i) nr = fmax(nr, fabs(sc.r[i]));
         if (!(iter < 10 && nd >= epsx && nr >= epsf)) break;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h8[i] = x[i];
+    for (int i = 0; i < lx; ++i) h9[i] = x[i];
 }
 
 // Whole warp: s/d point to the 2*count int coordinates (uniform pointers).  Returns false where
@@ -512,7 +525,10 @@ __device__ inline bool find_homography_warp(HomogScratch &sc, const int lane, co
     if (count > 4) {
         const int li = lane < count ? lane : 0;
         lm_refine_warp(sc, lane, count, (float)s[2 * li], (float)s[2 * li + 1], (float)d[2 * li], (float)d[2 * li + 1], H);
-        H[8] = 1.;
+        // H.convertTo(H, H.type(), scaleFor(H(2,2)))
+        const double sc2 = fabs(H[8]) > DBL_EPSILON ? 1. / H[8] : 1.;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = H[i] * sc2;
     }
     return true;
 }

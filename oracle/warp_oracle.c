@@ -308,7 +308,7 @@ static void eig_backsubst(const double *W, const double *V, int n, const double 
 }
 
 void orc_solve_eig(const double *A, const double *b, double *x, int n) {
-    double a[64], w[8], v[64];
+    double a[81], w[9], v[81];
     memcpy(a, A, sizeof(double) * n * n);
     orc_jacobi(a, w, v, n);
     eig_backsubst(w, v, n, b, x);
@@ -316,7 +316,7 @@ void orc_solve_eig(const double *A, const double *b, double *x, int n) {
 
 /* cv::invert(A, Ainv, DECOMP_EIG) */
 void orc_invert_eig(const double *A, double *Ainv, int n) {
-    double a[64], w[8], v[64], e[8], col[8];
+    double a[81], w[9], v[81], e[9], col[9];
     memcpy(a, A, sizeof(double) * n * n);
     orc_jacobi(a, w, v, n);
     for (int c = 0; c < n; ++c) {
@@ -329,136 +329,107 @@ void orc_invert_eig(const double *A, double *Ainv, int n) {
 /* ========================================================================= */
 /* cv2.findHomography(src, dst) method 0 (calib3d/fundam.cpp)                 */
 /* returns 1 and fills H[9] (H[8] == 1), or 0 when OpenCV returns None.       */
+/*                                                                           */
+/* The refinement of n > 4 points is pinned against the installed             */
+/* opencv-python 4.13.0 binary (scripts/check_lm_vs_cv2.py):    */
+/* that build optimises ALL NINE entries of H (HomographyRefineCallback reads */
+/* h[8] in the denominator and emits a 2n x 9 Jacobian), so J^T J is singular */
+/* along the scale gauge and cv::solve(DECOMP_EIG)'s eigenvalue cut decides   */
+/* the step; H is rescaled by 1/H[8] afterwards.                              */
 /* ========================================================================= */
+#define LM_NP 9
 static void lm_compute(const float *M, const float *m, int count, const double *h, double *err, double *J) {
     for (int i = 0; i < count; ++i) {
         double Mx = M[2 * i], My = M[2 * i + 1];
-        double ww = h[6] * Mx + h[7] * My + 1.;
+        double ww = h[6] * Mx + h[7] * My + h[8];
         ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
         double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
         double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
         err[2 * i] = xi - m[2 * i];
         err[2 * i + 1] = yi - m[2 * i + 1];
         if (J) {
-            double *Jp = J + 16 * i;
+            double *Jp = J + 2 * LM_NP * i;
             Jp[0] = Mx * ww; Jp[1] = My * ww; Jp[2] = ww;
             Jp[3] = Jp[4] = Jp[5] = 0.;
-            Jp[6] = -Mx * ww * xi; Jp[7] = -My * ww * xi;
-            Jp[8] = Jp[9] = Jp[10] = 0.;
-            Jp[11] = Mx * ww; Jp[12] = My * ww; Jp[13] = ww;
-            Jp[14] = -Mx * ww * yi; Jp[15] = -My * ww * yi;
+            Jp[6] = -Mx * ww * xi; Jp[7] = -My * ww * xi; Jp[8] = -ww * xi;
+            Jp[9] = Jp[10] = Jp[11] = 0.;
+            Jp[12] = Mx * ww; Jp[13] = My * ww; Jp[14] = ww;
+            Jp[15] = -Mx * ww * yi; Jp[16] = -My * ww * yi; Jp[17] = -ww * yi;
         }
     }
+}
+
+/* cv::gemm row . vector (GEMMSingleMul, one-column result): 4 interleaved accumulators */
+static double gemm_rowdot(const double *a, int astride, const double *b, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = 0;
+    for (; k <= n - 4; k += 4) {
+        s0 += a[k * astride] * b[k];
+        s1 += a[(k + 1) * astride] * b[k + 1];
+        s2 += a[(k + 2) * astride] * b[k + 2];
+        s3 += a[(k + 3) * astride] * b[k + 3];
+    }
+    for (; k < n; ++k) s0 += a[k * astride] * b[k];
+    return ((s0 + s1) + s2) + s3;
 }
 
 static void jtj_jtr(const double *J, const double *r, int rows, double *A, double *v) {
     /* A = J^T J (cv::mulTransposed, sequential over rows); v = J^T r (cv::gemm GEMM_1_T) */
-    for (int i = 0; i < 8; ++i)
-        for (int j = i; j < 8; ++j) {
+    for (int i = 0; i < LM_NP; ++i)
+        for (int j = i; j < LM_NP; ++j) {
             double s = 0;
-            for (int k = 0; k < rows; ++k) s += J[k * 8 + i] * J[k * 8 + j];
-            A[i * 8 + j] = s; A[j * 8 + i] = s;
+            for (int k = 0; k < rows; ++k) s += J[k * LM_NP + i] * J[k * LM_NP + j];
+            A[i * LM_NP + j] = s; A[j * LM_NP + i] = s;
         }
-    for (int i = 0; i < 8; ++i) {
-        /* cv::gemm (GEMMSingleMul, vector result): 4 interleaved accumulators */
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        int k = 0;
-        for (; k <= rows - 4; k += 4) {
-            s0 += J[k * 8 + i] * r[k];
-            s1 += J[(k + 1) * 8 + i] * r[k + 1];
-            s2 += J[(k + 2) * 8 + i] * r[k + 2];
-            s3 += J[(k + 3) * 8 + i] * r[k + 3];
-        }
-        for (; k < rows; ++k) s0 += J[k * 8 + i] * r[k];
-        v[i] = ((s0 + s1) + s2) + s3;
-    }
+    for (int i = 0; i < LM_NP; ++i) v[i] = gemm_rowdot(J + i, LM_NP, r, rows);
 }
 
-/* cv::Mat::dot (dotProd_): groups of four products added to the running sum */
+/* cv::Mat::dot on CV_64F as the 4.13.0 wheel executes it on an FMA-capable CPU (the AVX2
+ * dispatch of dotProd_ is compiled with contraction): per group of four
+ * t = fma(a0,b0, a1*b1); t = fma(a2,b2,t); t = fma(a3,b3,t); res += t, tail res = fma(a,b,res). */
 static double cv_dot(const double *a, const double *b, int n) {
     double res = 0;
     int i = 0;
-    for (; i <= n - 4; i += 4)
-        res += a[i] * b[i] + a[i + 1] * b[i + 1] + a[i + 2] * b[i + 2] + a[i + 3] * b[i + 3];
-    for (; i < n; ++i) res += a[i] * b[i];
+    for (; i <= n - 4; i += 4) {
+        double t = fma(a[i], b[i], a[i + 1] * b[i + 1]);
+        t = fma(a[i + 2], b[i + 2], t);
+        t = fma(a[i + 3], b[i + 3], t);
+        res += t;
+    }
+    for (; i < n; ++i) res = fma(a[i], b[i], res);
     return res;
 }
 
 static double norm_l2sqr(const double *r, int n) { double s = 0; for (int i = 0; i < n; ++i) s += r[i] * r[i]; return s; }
 static double norm_inf(const double *r, int n) { double s = 0; for (int i = 0; i < n; ++i) { double a = fabs(r[i]); if (a > s) s = a; } return s; }
 
-/* Linear solver used inside the LM refinement.
- *   0: OpenCV's own choice, cv::solve(DECOMP_EIG) (Jacobi eigen-decomposition + back substitution)
- *   1: LDL^T (square-root-free Cholesky) -- the variant the CUDA path implements; ~50x fewer
- *      dependent fp64 operations.  Both are backward stable; against cv2 4.13 the two variants
- *      land equally far from cv2's own result (tests/test_oracle_vs_cv2.py), because OpenCV's LM
- *      stops on a step-size test, not at the optimum.
- */
-int orc_lm_variant = 1;
+/* LM trace hook for scripts/check_lm_vs_cv2.py: number of outer iterations of the last call */
+int orc_lm_last_iters = 0;
+int orc_lm_iters(void) { return orc_lm_last_iters; }
 
-void orc_set_lm_variant(int v) { orc_lm_variant = v; }
-
-/* x = A^-1 b for symmetric positive definite A (n<=8) by LDL^T, row-major, fixed operation order.
- * A non-positive pivot (rank-deficient normal matrix) zeroes that component, mirroring the
- * eigenvalue cut of the EIG solve. */
-static void ldl_solve(const double *A, const double *b, double *x, int n) {
-    double L[64], Dg[8], y[8];
-    for (int j = 0; j < n; ++j) {
-        double dj = A[j * 8 + j];
-        for (int k = 0; k < j; ++k) dj -= L[j * 8 + k] * L[j * 8 + k] * Dg[k];
-        Dg[j] = dj;
-        double inv = dj > 0 ? 1. / dj : 0.;
-        for (int i = j + 1; i < n; ++i) {
-            double s = A[i * 8 + j];
-            for (int k = 0; k < j; ++k) s -= L[i * 8 + k] * L[j * 8 + k] * Dg[k];
-            L[i * 8 + j] = s * inv;
-        }
-    }
-    for (int i = 0; i < n; ++i) {
-        double s = b[i];
-        for (int k = 0; k < i; ++k) s -= L[i * 8 + k] * y[k];
-        y[i] = s;
-    }
-    for (int i = 0; i < n; ++i) y[i] = Dg[i] > 0 ? y[i] / Dg[i] : 0.;
-    for (int i = n - 1; i >= 0; --i) {
-        double s = y[i];
-        for (int k = i + 1; k < n; ++k) s -= L[k * 8 + i] * x[k];
-        x[i] = s;
-    }
-}
-
-static void lm_refine(const float *M, const float *m, int count, double *h8) {
-    /* calib3d/levmarq.cpp LMSolverImpl::run, maxIters = 10, eps = FLT_EPSILON */
-    const int lx = 8, rows = 2 * count;
+static void lm_refine(const float *M, const float *m, int count, double *h9) {
+    /* calib3d/levmarq.cpp LMSolverImpl::run, maxIters = 10, epsx = epsf = FLT_EPSILON */
+    const int lx = LM_NP, rows = 2 * count;
     const int maxIters = 10;
     const double epsx = FLT_EPSILON, epsf = FLT_EPSILON;
-    double x[8], xd[8], r[32], rd[32], J[32 * 8], A[64], Ap[64], v[8], d[8], D[8], temp_d[8];
-    memcpy(x, h8, sizeof(x));
+    double x[LM_NP], xd[LM_NP], r[32], rd[32], J[32 * LM_NP], A[LM_NP * LM_NP], Ap[LM_NP * LM_NP], v[LM_NP], d[LM_NP], D[LM_NP], temp_d[LM_NP];
+    memcpy(x, h9, sizeof(x));
     lm_compute(M, m, count, x, r, J);
     double S = norm_l2sqr(r, rows);
     jtj_jtr(J, r, rows, A, v);
-    for (int i = 0; i < lx; ++i) D[i] = A[i * 8 + i];
+    for (int i = 0; i < lx; ++i) D[i] = A[i * lx + i];
     const double Rlo = 0.25, Rhi = 0.75;
     double lambda = 1, lc = 0.75;
     int iter = 0;
     for (;;) {
         memcpy(Ap, A, sizeof(A));
-        for (int i = 0; i < lx; ++i) Ap[i * 8 + i] += lambda * D[i];
-        if (orc_lm_variant == 0) orc_solve_eig(Ap, v, d, lx); else ldl_solve(Ap, v, d, lx);
+        for (int i = 0; i < lx; ++i) Ap[i * lx + i] += lambda * D[i];
+        orc_solve_eig(Ap, v, d, lx);
         for (int i = 0; i < lx; ++i) xd[i] = x[i] - d[i];
         lm_compute(M, m, count, xd, rd, NULL);
         double Sd = norm_l2sqr(rd, rows);
-        /* temp_d = -A d + 2 v */
-        for (int i = 0; i < lx; ++i) {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int k = 0; k < lx; k += 4) {
-                s0 += A[i * 8 + k] * d[k];
-                s1 += A[i * 8 + k + 1] * d[k + 1];
-                s2 += A[i * 8 + k + 2] * d[k + 2];
-                s3 += A[i * 8 + k + 3] * d[k + 3];
-            }
-            temp_d[i] = -1. * (((s0 + s1) + s2) + s3) + 2. * v[i];
-        }
+        /* temp_d = -A d + 2 v  (cv::gemm(A, d, -1, v, 2)) */
+        for (int i = 0; i < lx; ++i) temp_d[i] = -1. * gemm_rowdot(A + i * lx, 1, d, lx) + 2. * v[i];
         double dS = cv_dot(d, temp_d, lx);
         double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
         if (R > Rhi) {
@@ -470,17 +441,8 @@ static void lm_refine(const float *M, const float *m, int count, double *h8) {
             nu = fmin(fmax(nu, 2.), 10.);
             if (lambda == 0) {
                 double maxval = DBL_EPSILON;
-                if (orc_lm_variant == 0) {
-                    orc_invert_eig(A, Ap, lx);
-                    for (int i = 0; i < lx; ++i) maxval = fmax(maxval, fabs(Ap[i * 8 + i]));
-                } else {
-                    for (int c = 0; c < lx; ++c) {
-                        double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, col[8];
-                        e[c] = 1.;
-                        ldl_solve(A, e, col, lx);
-                        maxval = fmax(maxval, fabs(col[c]));
-                    }
-                }
+                orc_invert_eig(A, Ap, lx);
+                for (int i = 0; i < lx; ++i) maxval = fmax(maxval, fabs(Ap[i * lx + i]));
                 lambda = lc = 1. / maxval;
                 nu *= 0.5;
             }
@@ -496,7 +458,8 @@ static void lm_refine(const float *M, const float *m, int count, double *h8) {
         int proceed = iter < maxIters && norm_inf(d, lx) >= epsx && norm_inf(r, rows) >= epsf;
         if (!proceed) break;
     }
-    memcpy(h8, x, sizeof(x));
+    orc_lm_last_iters = iter;
+    memcpy(h9, x, sizeof(x));
 }
 
 int orc_find_homography(const int32_t *src, const int32_t *dst, int count, double *H, int refine) {
@@ -548,7 +511,9 @@ int orc_find_homography(const int32_t *src, const int32_t *dst, int count, doubl
     for (int i = 0; i < 9; ++i) H[i] = H1[i] * sc;
     if (count > 4 && refine) {
         lm_refine(M, m, count, H);
-        H[8] = 1.;   /* LM touches only the 8 free parameters */
+        /* H.convertTo(H, H.type(), scaleFor(H(2,2))) */
+        double sc2 = fabs(H[8]) > DBL_EPSILON ? 1. / H[8] : 1.;
+        for (int i = 0; i < 9; ++i) H[i] = H[i] * sc2;
     }
     return 1;
 }

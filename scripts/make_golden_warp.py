@@ -1,10 +1,11 @@
 """Runs the imported reference (cv2 + numpy, /root/reference) on seeded synthetic crops and commits
 what the oracle must reproduce: tests/golden/warp_golden.json
 
-  per crop: visibility dicts of both poses, get_planes sha1 per plane, plane vertices,
-            warp_unwarp_planes()[0] sha1 per plane, and -- because OpenCV's LM refinement of the
-            6-point side planes cannot be reproduced bit for bit -- whether the oracle's
-            plane was identical to the reference's when this file was generated.
+  per crop (160 detailed cases): visibility dicts of both poses, get_planes sha1 per plane, plane
+            vertices, warp_unwarp_planes()[0] sha1 per plane;
+  bulk (seeds 1000..2999): one sha1 per crop over (visibility of both poses, warped planes) of the
+            REFERENCE's outputs -- the oracle and the CUDA path must reproduce every one of them.
+The generator asserts that the oracle is bit-identical to the reference on every plane it writes.
 Only runs where /root/reference exists (the build container)."""
 import hashlib
 import json
@@ -47,10 +48,9 @@ for idx in range(N):
     assert [bool(vs[k]) for k in O.PLANE_NAMES] == [bool(v) for v in vis[0]], idx
     assert [bool(vd[k]) for k in O.PLANE_NAMES] == [bool(v) for v in vis[1]], idx
     assert np.array_equal(sp, O.get_planes(img, p["src_kp"])), idx
-    equal = [bool(np.array_equal(wr[j], wo[j])) for j in range(5)]
+    assert np.array_equal(wr, wo), idx
     written = [bool(wr[j].any()) for j in range(5)]
     n_planes += sum(written)
-    n_equal += sum(e for e, w in zip(equal, written) if w)
     cases.append({
         "idx": idx,
         "vis_src": [int(bool(vs[k])) for k in O.PLANE_NAMES], "vis_dst": [int(bool(vd[k])) for k in O.PLANE_NAMES],
@@ -58,9 +58,33 @@ for idx in range(N):
         "planes_sha1": [sha(sp[j]) for j in range(5)],
         "warped_sha1": [sha(wr[j]) for j in range(5)],
         "warped_nonzero": written,
-        "oracle_identical": equal,
         "plane_j": [int(v) for v in pj],
     })
-gold = {"cv2_version": cv2.__version__, "n": N, "hw": [H, W], "written_planes": n_planes, "oracle_identical_planes": n_equal, "cases": cases}
+
+def ref_crop(idx):
+    p = synth.make_pose_pair(idx)
+    img = synth.make_crop(idx)
+    kp3d = {k: p["kp3d"][i] for i, k in enumerate(synth.KP_NAMES)}
+    vs = compute_visibility(p["E_src"], p["K"], kp3d, H, W)
+    vd = compute_visibility(p["E_dst"], p["K"], kp3d, H, W)
+    ks = {k: p["kp2d_src"][i] for i, k in enumerate(synth.KP_NAMES)}
+    kd = {k: p["kp2d_dst"][i] for i, k in enumerate(synth.KP_NAMES)}
+    sp, skp, sv = get_planes(img, ks, 'car', vs)
+    dp, dkp, dv = get_planes(img, kd, 'car', vd)
+    wr, _ = warp_unwarp_planes(sp, skp, dkp, sv, dv, 'car', pascal_texture_planes)
+    vis = np.array([[int(bool(v[k])) for k in O.PLANE_NAMES] for v in (vs, vd)], np.uint8)
+    return vis, wr
+
+
+BULK0, BULKN = 1000, 2000
+bulk = []
+bulk_planes = 0
+for idx in range(BULK0, BULK0 + BULKN):
+    vis, wr = ref_crop(idx)
+    bulk_planes += sum(bool(wr[j].any()) for j in range(5))
+    bulk.append(hashlib.sha1(vis.tobytes() + np.ascontiguousarray(wr).tobytes()).hexdigest()[:16])
+
+gold = {"cv2_version": cv2.__version__, "n": N, "hw": [H, W], "written_planes": n_planes, "cases": cases,
+        "bulk_first": BULK0, "bulk_sha1_16": bulk, "bulk_written_planes": bulk_planes}
 json.dump(gold, open(os.path.join(ROOT, "tests", "golden", "warp_golden.json"), "w"))
-print(f"{N} crops: {n_planes} written planes, oracle identical on {n_equal} ({100.0 * n_equal / n_planes:.1f}%)")
+print(f"{N} crops: {n_planes} written planes, all identical to the oracle; bulk {BULKN} crops, {bulk_planes} written planes")

@@ -34,6 +34,29 @@ def test_fused_matches_oracle(cuda, hw):
     assert (pj >= 0).sum() >= B // 2     # the batch really exercises warped planes
 
 
+def test_bulk_reference_goldens(cuda):
+    """2000 crops (seeds 1000..2999, 4268 written planes): visibility of both poses and every warped plane of the
+    CUDA path hash to what the imported reference (cv2 4.13.0) produced in the build container
+    (scripts/make_golden_warp.py) -- bit-exact, no tolerance, including the LM-refined side planes."""
+    import hashlib
+    import json
+    import os
+    from future_urban_scene_generation_b200.warp_learn import warp_batch
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "warp_golden.json")))
+    first, want = gold["bulk_first"], gold["bulk_sha1_16"]
+    bad = []
+    CH = 500
+    for c0 in range(0, len(want), CH):
+        batch = synth.make_warp_batch(first + c0, CH)
+        res = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"])
+        vis, warped = res.vis.cpu().numpy(), res.warped.cpu().numpy()
+        for i in range(CH):
+            got = hashlib.sha1(np.ascontiguousarray(vis[i, :2]).tobytes() + np.ascontiguousarray(warped[i]).tobytes()).hexdigest()[:16]
+            if got != want[c0 + i]:
+                bad.append(first + c0 + i)
+    assert not bad, f"{len(bad)} of {len(want)} crops differ from the reference: {bad[:10]}"
+
+
 def test_visibility_areas_match_oracle(cuda):
     from oracle import warp_oracle as O
     from future_urban_scene_generation_b200.warp_learn.online_visibility import compute_visibility_batch
@@ -159,8 +182,8 @@ def test_large_batch_properties(cuda):
 
 
 def test_large_batch_solver_path_matches_small_batch(cuda):
-    """Above 8192 (crop, plane) tasks the homographies come from the compacted thread-per-solve kernels
-    instead of the warp-cooperative one; both must give the same bits (and the oracle's, by transitivity)."""
+    """Above 8192 (crop, plane) tasks the homographies are solved from the compacted task lists instead of one warp
+    per (crop, plane); both launches must give the same bits (and the oracle's, by transitivity)."""
     from future_urban_scene_generation_b200.warp_learn import warp_batch
     torch = cuda
     U, R = 96, 24                                   # 96 unique crops tiled to 2304 (> 8192 / 5)
