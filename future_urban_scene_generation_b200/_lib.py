@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfusg.so")
 
+POLY_COORD_MAX = 1 << 20      # csrc/warp_geom.cuh
 ERRORS = {-1: "FUSG_ERR_ARG", -2: "FUSG_ERR_UNSUPPORTED", -3: "FUSG_ERR_CUDA", -4: "FUSG_ERR_WORKSPACE"}
 
 

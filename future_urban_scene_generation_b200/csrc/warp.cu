@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
     if (lane < N_KP) {
         double u, v;
         project_point(Kp, Ep, Xp + 3 * lane, &u, &v);
-        // int(): truncation toward zero; far-out values are clamped (rejected as out-of-frame below anyway)
+        // int(): truncation toward zero; far-out values are clamped (and refused below: POLY_COORD_MAX)
         u = fmin(fmax(u, -1.0e9), 1.0e9);
         v = fmin(fmax(v, -1.0e9), 1.0e9);
         sm.vx[lane] = (int)u;
@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
         sm.dist[lane - N_KP] = plane_distance(Ep, Xp, lane - N_KP);
     }
     __syncwarp();
+    // Vertices outside the frame are fine (cv2.fillPoly clips, poly_row_ranges follows it); only absurd
+    // magnitudes (a keypoint on the camera plane) are refused.
     bool oob = false;
-    if (lane < N_KP) oob = sm.vx[lane] < 0 || sm.vx[lane] >= W || sm.vy[lane] < 0 || sm.vy[lane] >= H;
+    if (lane < N_KP) oob = abs(sm.vx[lane]) > POLY_COORD_MAX || abs(sm.vy[lane]) > POLY_COORD_MAX;
     oob = __any_sync(0xffffffffu, oob);
     int cnt_abs[N_VIS], cnt_occ[N_VIS];
 #pragma unroll
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
             bx0 = min(bx0, sm.vx[k]); bx1 = max(bx1, sm.vx[k]);
             by0 = min(by0, sm.vy[k]); by1 = max(by1, sm.vy[k]);
         }
+        bx0 = max(bx0, 0); bx1 = min(bx1, W - 1);
+        by0 = max(by0, 0); by1 = min(by1, H - 1);
         const int w0 = bx0 >> 5, w1 = bx1 >> 5;
         for (int y = by0 + lane; y <= by1; y += 32) {
             int lo[N_VIS][MAX_RANGES], hi[N_VIS][MAX_RANGES], rc[N_VIS];
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
                 int px[6], py[6];
                 const int n = c_plane_n[p];
                 for (int k = 0; k < n; ++k) { px[k] = sm.vx[c_plane_kp[p][k]]; py[k] = sm.vy[c_plane_kp[p][k]]; }
-                rc[p] = poly_row_ranges(px, py, n, y, lo[p], hi[p]);
+                rc[p] = poly_row_ranges(px, py, n, y, H, W, lo[p], hi[p]);
             }
             for (int w = w0; w <= w1; ++w) {
                 unsigned bits[N_VIS];
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
     if (lane == 0) {
 #pragma unroll
         for (int p = 0; p < N_VIS; ++p) {
-            vis[N_VIS * g + p] = oob ? 0xff : ((double)cnt_occ[p] > 0.9 * (double)cnt_abs[p] ? 1 : 0);   // 0xff: out-of-frame marker
+            vis[N_VIS * g + p] = oob ? 0xff : ((double)cnt_occ[p] > 0.9 * (double)cnt_abs[p] ? 1 : 0);   // 0xff: refused (see above)
             if (areas) { areas[2 * N_VIS * g + 2 * p] = oob ? -1 : cnt_abs[p]; areas[2 * N_VIS * g + 2 * p + 1] = oob ? -1 : cnt_occ[p]; }
         }
     }
@@ -153,10 +157,10 @@ __global__ void __launch_bounds__(HG_WARPS * 32) k_homography(const int32_t *__r
     const int b = t / N_TEX, i = t % N_TEX;
     const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
     const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
-    bool bad = sv[0] == 0xff || dv[0] == 0xff;            // projected keypoint out of frame
+    bool bad = sv[0] == 0xff || dv[0] == 0xff;            // refused by k_visibility
     if (lane < N_KP) {
-        const bool oob = sk[2 * lane] < 0 || sk[2 * lane] >= W || sk[2 * lane + 1] < 0 || sk[2 * lane + 1] >= H ||
-                         dk[2 * lane] < 0 || dk[2 * lane] >= W || dk[2 * lane + 1] < 0 || dk[2 * lane + 1] >= H;
+        const bool oob = abs(sk[2 * lane]) > POLY_COORD_MAX || abs(sk[2 * lane + 1]) > POLY_COORD_MAX ||
+                         abs(dk[2 * lane]) > POLY_COORD_MAX || abs(dk[2 * lane + 1]) > POLY_COORD_MAX;
         bad = bad || oob;
     }
     bad = __any_sync(0xffffffffu, bad);
@@ -215,10 +219,8 @@ __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ 
     const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
     bool bad = sv[0] == 0xff || dv[0] == 0xff;
     const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
-    for (int k = 0; k < N_KP && !bad; ++k) {
-        if (sk[2 * k] < 0 || sk[2 * k] >= W || sk[2 * k + 1] < 0 || sk[2 * k + 1] >= H) bad = true;
-        if (dk[2 * k] < 0 || dk[2 * k] >= W || dk[2 * k + 1] < 0 || dk[2 * k + 1] >= H) bad = true;
-    }
+    for (int k = 0; k < 2 * N_KP && !bad; ++k)
+        if (abs(sk[k]) > POLY_COORD_MAX || abs(dk[k]) > POLY_COORD_MAX) bad = true;
     const int j = bad ? -2 : plane_target(i, sv, dv);
     plane_j[t] = (int8_t)j;
     if (j >= 0) {
@@ -502,7 +504,7 @@ k_warp(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, cons
             int px[6], py[6], lo[MAX_RANGES], hi[MAX_RANGES];
             const int n = hd->polyn;
             for (int k = 0; k < n; ++k) { px[k] = hd->polyx[k]; py[k] = hd->polyy[k]; }
-            const int rc = poly_row_ranges(px, py, n, y, lo, hi);
+            const int rc = poly_row_ranges(px, py, n, y, H, W, lo, hi);
             for (int w = 0; w < MASK_WORDS; ++w) s_mask[y * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
             int xlo, xhi;
             row_active_span(M, y, W, hd->bbox, xlo, xhi);
@@ -544,8 +546,8 @@ k_warp(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, cons
     }
 }
 
-// crops with out-of-frame keypoints (plane_j == -2): k_warp already zero-filled them because no
-// plane has a writer; nothing else to do.
+// refused crops (plane_j == -2, vertex magnitude beyond POLY_COORD_MAX): k_warp already zero-filled them
+// because no plane has a writer; the Python host raises on them (warp_learn/batch.py).
 
 // ============================================================================================
 // Stand-alone kernels for the per-function drop-ins
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(256) k_get_planes(const uint8_t *__restrict__ 
         const int n = c_plane_n[p];
         for (int k = 0; k < n; ++k) { px[k] = kp[(b * N_KP + c_plane_kp[p][k]) * 2]; py[k] = kp[(b * N_KP + c_plane_kp[p][k]) * 2 + 1]; }
         int l[MAX_RANGES], h[MAX_RANGES];
-        const int c = poly_row_ranges(px, py, n, y, l, h);
+        const int c = poly_row_ranges(px, py, n, y, H, W, l, h);
         for (int k = 0; k < c; ++k) { lo[k] = l[k]; hi[k] = h[k]; }
         rc = c;
     }
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(256) k_warp_perspective(const uint8_t *__restr
 constexpr int PM_ROWS = 8;         // mask rows per CTA of k_plane_masks: one per warp
 
 __global__ void __launch_bounds__(32 * PM_ROWS) k_plane_masks(const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
-                                                             uint32_t *__restrict__ masks, int H, int words) {
+                                                             uint32_t *__restrict__ masks, int H, int W, int words) {
     // grid (ceil(H / PM_ROWS), 5, B): bit mask of PM_ROWS rows of SOURCE plane i (only for planes that are warped), a warp per row
     const int i = blockIdx.y, b = blockIdx.z;
     if (plane_j[b * N_TEX + i] < 0) return;
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(32 * PM_ROWS) k_plane_masks(const int32_t *__r
         int px[6], py[6], l[MAX_RANGES], h[MAX_RANGES];
         const int n = c_plane_n[i];
         for (int k = 0; k < n; ++k) { px[k] = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2]; py[k] = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1]; }
-        const int c = poly_row_ranges(px, py, n, y, l, h);
+        const int c = poly_row_ranges(px, py, n, y, H, W, l, h);
         for (int k = 0; k < c; ++k) { s_lo[warp][k] = l[k]; s_hi[warp][k] = h[k]; }
         s_rc[warp] = c;
     }
@@ -792,7 +794,7 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     } else {
         const int words = (W + 31) / 32;
         uint32_t *masks = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(workspace) + ((warp_ws_base(B) + 15) & ~(size_t)15));
-        k_plane_masks<<<dim3((H + PM_ROWS - 1) / PM_ROWS, N_TEX, B), 32 * PM_ROWS, 0, st>>>(src_kp, plane_j, masks, H, words);
+        k_plane_masks<<<dim3((H + PM_ROWS - 1) / PM_ROWS, N_TEX, B), 32 * PM_ROWS, 0, st>>>(src_kp, plane_j, masks, H, W, words);
         const size_t row_smem = ((size_t)W * 3 + 15) & ~(size_t)15;
         const size_t frame_smem = row_smem * WF_ROWS;
         if (frame_smem > 200 * 1024) return FUSG_ERR_UNSUPPORTED;

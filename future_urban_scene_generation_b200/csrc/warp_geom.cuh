@@ -29,12 +29,65 @@ __device__ __constant__ int c_plane_kp[N_VIS][6] = {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Scanline coverage of cv2.fillPoly for one in-frame polygon: the pixels of row y that are set
-// are the union of the returned closed ranges [lo[k], hi[k]].  Outline = 8-connected Bresenham
-// traced left-to-right (closed form per row), interior = even-odd spans between 16.16
-// fixed-point edge crossings, [ceil(xa), floor(xb)].
+// OpenCV's clipLine (imgproc/drawing.cpp): integer Cohen-Sutherland variant whose intersections are
+// computed in fp64 and truncated.  Returns true when a visible segment remains; like the original
+// it may leave the endpoints PARTIALLY clipped when it returns false, and CollectPolyEdges then
+// uses them as they are.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int poly_row_ranges(const int *px, const int *py, int n, int y, int *lo, int *hi) {
+__device__ __forceinline__ bool clip_line(long long width, long long height, long long &x1, long long &y1, long long &x2, long long &y2) {
+    const long long right = width - 1, bottom = height - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// Polygon vertices beyond this magnitude are refused (plane_j = -2): the 16.16 edge arithmetic below stays
+// inside int64 for |coordinate| <= 2^20, and cv2 itself only takes int32 vertices.
+constexpr int POLY_COORD_MAX = 1 << 20;
+
+// ---------------------------------------------------------------------------------------------
+// Scanline coverage of cv2.fillPoly (single contour, 8-connected, shift 0) on an H x W canvas: the
+// pixels of row y (0 <= y < H) that are set are the union of the returned closed ranges
+// [lo[k], hi[k]] intersected with [0, W).  Vertices may lie outside the canvas.
+//   outline  = Line() of every edge: clipLine first, then an 8-connected Bresenham traced
+//              left-to-right FROM THE CLIPPED END POINTS (closed form per row);
+//   interior = even-odd spans [ceil(xa), floor(xb)] between 16.16 fixed-point edge crossings, where
+//              an edge with an out-of-canvas end point takes its x (always) and y (unless the
+//              clipped segment is horizontal) from the clipped end points and is extrapolated
+//              back to its original top row (CollectPolyEdges / FillEdgeCollection).
+// Pinned against cv2 4.13.0 on 26,000 random in- and out-of-frame polygons through the oracle
+// restatement (tests/test_cpu_oracle.py), which this function follows operation for operation.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int poly_row_ranges(const int *px, const int *py, int n, int y, int H, int W, int *lo, int *hi) {
     int cnt = 0;
     long long xs[6];
     int na = 0;
@@ -42,34 +95,45 @@ __device__ __forceinline__ int poly_row_ranges(const int *px, const int *py, int
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const int bx = px[i], by = py[i];
-        // ---- outline run of edge a->b in row y
-        const int ymin = ay < by ? ay : by, ymax = ay < by ? by : ay;
-        if (y >= ymin && y <= ymax) {
-            int sx = ax, sy = ay, ex = bx, ey = by;
-            if (bx < ax) { sx = bx; sy = by; ex = ax; ey = ay; }
-            const int ddx = ex - sx;
-            const int dys = ey - sy;
-            const int ddy = dys < 0 ? -dys : dys;
-            const int cy = y > sy ? y - sy : sy - y;
-            int l, h;
-            if (ddy > ddx) {                    // y-major: one pixel per row
-                l = h = sx + (2 * ddx * cy + ddy - 1) / (2 * ddy);
-            } else if (ddy == 0) {              // horizontal (or a single point)
-                l = sx; h = ex;
-            } else {                            // x-major: a run of pixels per row
-                const int il = cy == 0 ? 0 : (2 * ddx * cy - ddx + 1 + 2 * ddy - 1) / (2 * ddy);
-                const int ih = cy == ddy ? ddx : (2 * ddx * (cy + 1) - ddx + 1 + 2 * ddy - 1) / (2 * ddy) - 1;
-                l = sx + il; h = sx + ih;
+        long long t0x = ax, t0y = ay, t1x = bx, t1y = by;
+        const bool outside = (unsigned)ax >= (unsigned)W || (unsigned)bx >= (unsigned)W || (unsigned)ay >= (unsigned)H || (unsigned)by >= (unsigned)H;
+        bool drawn = true;
+        if (outside) drawn = clip_line(W, H, t0x, t0y, t1x, t1y);
+        // ---- outline run of the (clipped) segment t0->t1 in row y
+        if (drawn) {
+            int sx = (int)t0x, sy = (int)t0y, ex = (int)t1x, ey = (int)t1y;
+            if (ex < sx) { const int tx = sx, ty = sy; sx = ex; sy = ey; ex = tx; ey = ty; }
+            const int ymin = sy < ey ? sy : ey, ymax = sy < ey ? ey : sy;
+            if (y >= ymin && y <= ymax) {
+                const int ddx = ex - sx;
+                const int dys = ey - sy;
+                const int ddy = dys < 0 ? -dys : dys;
+                const int cy = y > sy ? y - sy : sy - y;
+                int l, h;
+                if (ddy > ddx) {                    // y-major: one pixel per row
+                    l = h = sx + (2 * ddx * cy + ddy - 1) / (2 * ddy);
+                } else if (ddy == 0) {              // horizontal (or a single point)
+                    l = sx; h = ex;
+                } else {                            // x-major: a run of pixels per row
+                    const int il = cy == 0 ? 0 : (2 * ddx * cy - ddx + 1 + 2 * ddy - 1) / (2 * ddy);
+                    const int ih = cy == ddy ? ddx : (2 * ddx * (cy + 1) - ddx + 1 + 2 * ddy - 1) / (2 * ddy) - 1;
+                    l = sx + il; h = sx + ih;
+                }
+                lo[cnt] = l; hi[cnt] = h; ++cnt;
             }
-            lo[cnt] = l; hi[cnt] = h; ++cnt;
         }
         // ---- interior crossing (half-open in y, 16.16 fixed point, C truncating division)
         if (ay != by) {
-            int xt = ax, yt = ay, xb = bx, yb = by;
-            if (by < ay) { xt = bx; yt = by; xb = ax; yb = ay; }
+            const int yt = ay < by ? ay : by, yb = ay < by ? by : ay;
             if (y >= yt && y < yb) {
-                const long long dxf = ((long long)(xb - xt) * 65536LL) / (long long)(yb - yt);
-                xs[na++] = (long long)xt * 65536LL + (long long)(y - yt) * dxf;
+                long long c0x = (long long)ax * 65536LL, c0y = ay, c1x = (long long)bx * 65536LL, c1y = by;
+                if (outside) {
+                    if (t0y != t1y) { c0y = t0y; c1y = t1y; }
+                    c0x = t0x * 65536LL; c1x = t1x * 65536LL;
+                }
+                const long long dxf = (c1x - c0x) / (c1y - c0y);
+                const long long x0 = ay < by ? c0x + ((long long)ay - c0y) * dxf : c1x + ((long long)by - c1y) * dxf;
+                xs[na++] = x0 + (long long)(y - yt) * dxf;
             }
         }
         ax = bx; ay = by;
@@ -82,8 +146,12 @@ __device__ __forceinline__ int poly_row_ranges(const int *px, const int *py, int
         xs[k + 1] = v;
     }
     for (int k = 0; k + 1 < na; k += 2) {
-        const int l = (int)((xs[k] + 65535LL) >> 16), h = (int)(xs[k + 1] >> 16);
-        if (l <= h) { lo[cnt] = l; hi[cnt] = h; ++cnt; }
+        long long l = (xs[k] + 65535LL) >> 16, h = xs[k + 1] >> 16;
+        if (l < W && h >= 0) {
+            if (l < 0) l = 0;
+            if (h >= W) h = W - 1;
+            if (l <= h) { lo[cnt] = (int)l; hi[cnt] = (int)h; ++cnt; }
+        }
     }
     return cnt;
 }

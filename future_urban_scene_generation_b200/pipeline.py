@@ -230,6 +230,10 @@ class NovelViewPipeline:
         `warped` (B,5,256,256,3) u8 planes, `plane_j`, `vis`.  Valid until `depth` more batches are submitted."""
         slot = self.slots[ticket % self.depth]
         slot.done.synchronize()
+        pj = slot.out.get("plane_j")
+        if pj is not None and bool((pj == -2).any()):                # never hand back silently-black planes
+            from .warp_learn.batch import RefusedCrops
+            raise RefusedCrops(torch.nonzero((pj == -2).any(dim=1)).flatten().tolist())
         return slot.out
 
     def wait(self, ticket: int):

@@ -61,14 +61,16 @@ def project(K: np.ndarray, E: np.ndarray, X: np.ndarray) -> np.ndarray:
     return p.T[:, :2]
 
 
-def make_pose_pair(idx: int, h: int = 256, w: int = 256, max_tries: int = 200):
-    """Source/destination poses for crop `idx` with every projected keypoint inside the frame.
+def make_pose_pair(idx: int, h: int = 256, w: int = 256, max_tries: int = 200, out_of_frame: bool = False):
+    """Source/destination poses for crop `idx` with every projected keypoint inside the frame, or -- with
+    `out_of_frame` -- a vehicle leaving the frame (trajectory_inference.py:374-379): the look-at point is shifted so
+    that the car straddles a border, and at least one keypoint of either pose must project outside.
 
     Returns dict(K, E_src, E_dst, kp3d, kp2d_src, kp2d_dst, src_kp, dst_kp) where kp2d_* are the
     normalised (12,2) arrays the reference passes to get_planes and *_kp their int32 truncation
     (planes_utils.py:22-27).
     """
-    rng = np.random.default_rng(1234 + idx)
+    rng = np.random.default_rng((1234 if not out_of_frame else 91_234) + idx)
     K = intrinsic(h, w)
     kp3d = cad_keypoints(idx % 10)
     for _ in range(max_tries):
@@ -76,15 +78,20 @@ def make_pose_pair(idx: int, h: int = 256, w: int = 256, max_tries: int = 200):
         el = rng.uniform(5, 40)
         E_src = look_at_extrinsic(az, el, rng.uniform(8, 11))
         E_dst = look_at_extrinsic(az + rng.uniform(-20, 20), el, rng.uniform(8, 11))
+        if out_of_frame:
+            # slide the principal point: the car drifts towards / across a border of the frame
+            K = intrinsic(h, w)
+            K[0, 2] += rng.uniform(-0.6, 0.6) * w
+            K[1, 2] += rng.uniform(-0.6, 0.6) * h
         p_src, p_dst = project(K, E_src, kp3d), project(K, E_dst, kp3d)
-        ok = True
+        inside = True
         for p in (p_src, p_dst):
             if p[:, 0].min() < 0 or p[:, 0].max() > w - 1 or p[:, 1].min() < 0 or p[:, 1].max() > h - 1:
-                ok = False
-        if ok:
+                inside = False
+        if inside != out_of_frame:
             break
     else:
-        raise RuntimeError("no in-frame pose found")
+        raise RuntimeError("no suitable pose found")
     out = dict(K=K, E_src=E_src, E_dst=E_dst, kp3d=kp3d)
     for name, p in (("src", p_src), ("dst", p_dst)):
         norm = p / np.array([w, h], np.float64)
@@ -101,9 +108,9 @@ def make_crop(idx: int, h: int = 256, w: int = 256) -> np.ndarray:
     return np.random.default_rng(77_000 + idx).integers(0, 256, (h, w, 3), dtype=np.uint8)
 
 
-def make_warp_batch(start: int, count: int, h: int = 256, w: int = 256, crops: bool = True):
+def make_warp_batch(start: int, count: int, h: int = 256, w: int = 256, crops: bool = True, out_of_frame: bool = False):
     """Stacked arrays for crops [start, start+count): the layout the C ABI takes (include/fusg.h)."""
-    poses = [make_pose_pair(start + i, h, w) for i in range(count)]
+    poses = [make_pose_pair(start + i, h, w, out_of_frame=out_of_frame) for i in range(count)]
     batch = dict(
         K=np.stack([p["K"] for p in poses]),
         E_src=np.stack([p["E_src"][:3] for p in poses]),

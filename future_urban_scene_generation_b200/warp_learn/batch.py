@@ -14,7 +14,7 @@ from .. import _lib
 class WarpResult:
     warped: "torch.Tensor"    # (B,5,H,W,3) uint8, device
     vis: "torch.Tensor"       # (B,2,7) uint8: [src|dst] x (left,right,roof,front,back,front_bt,back_bt)
-    plane_j: "torch.Tensor"   # (B,5) int8: target plane of source plane i, -1 skipped, -2 keypoint out of frame
+    plane_j: "torch.Tensor"   # (B,5) int8: target plane of source plane i, -1 skipped, -2 refused (a vertex beyond 2^20 px)
     H12: "torch.Tensor"       # (B,5,3,3) float64 (zeros where skipped)
 
 
@@ -28,12 +28,34 @@ def _dev(torch, a, dtype, shape, device):
     return t.contiguous()
 
 
-def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None, kp3d_dst=None) -> WarpResult:
+class RefusedCrops(ValueError):
+    """Raised when the kernels refused crops (plane_j == -2): a plane vertex or projected keypoint lies beyond
+    2^20 pixels, where neither cv2's int32 polygon rasteriser nor the 16.16 edge arithmetic is defined."""
+
+    def __init__(self, indices):
+        super().__init__(f"fused warp refused {len(indices)} crop(s) (vertex magnitude > 2^20 px): {indices[:8]}")
+        self.indices = indices
+
+
+def check_refused(result: "WarpResult"):
+    """Synchronises and raises RefusedCrops if any crop was refused.  The reference would warp or raise inside cv2 for
+    such inputs; silently returning black planes is the one thing that must not happen."""
+    torch = _lib.require_cuda()
+    bad = torch.nonzero((result.plane_j == -2).any(dim=1)).flatten()
+    if bad.numel():
+        raise RefusedCrops(bad.cpu().tolist())
+    return result
+
+
+def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None, kp3d_dst=None, check=False) -> WarpResult:
     """src (B,H,W,3) u8; src_kp/dst_kp (B,12,2) i32 plane vertices (_KP_NAMES order, already
     truncated as in planes_utils.py:22-27); K (B,3,3) or (3,3); E_* (B,3,4) or (B,4,4); kp3d (B,12,3).
     numpy arrays or torch tensors on host or device.  Asynchronous on the current CUDA stream.
     kp3d_dst (B,12,3), optional: the destination pose's own keypoints (trajectory loop: same camera, moved keypoints,
-    trajectory_inference.py:359-379 -- see kinematics.step_keypoints_batch); default: kp3d for both poses."""
+    trajectory_inference.py:359-379 -- see kinematics.step_keypoints_batch); default: kp3d for both poses.
+    Keypoints outside the frame are handled like cv2 does (clipped polygons).  check=True synchronises and raises
+    RefusedCrops when a crop came back refused (plane_j == -2); asynchronous callers use check_refused(result)
+    once the stream is done (NovelViewPipeline.result does)."""
     torch = _lib.require_cuda()
     device = torch.device(device if device is not None else "cuda")
     src = _dev(torch, src, torch.uint8, src.shape, device)
@@ -77,4 +99,4 @@ def warp_batch(src, src_kp, dst_kp, K, E_src, E_dst, kp3d, device=None, out=None
     _lib.check(rc, "fusg_warp_fused")
     # keep inputs/workspace alive until the stream has consumed them
     out._keep = (src, skp, dkp, Kt, Es, Ed, X, Xd, ws)
-    return out
+    return check_refused(out) if check else out

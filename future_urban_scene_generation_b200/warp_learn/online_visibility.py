@@ -41,7 +41,7 @@ def _extrinsic34(extrinsic):
 
 def compute_visibility_batch(extrinsics, intrinsics, kpoints_3d, h, w, return_aux=False):
     """B poses at once: extrinsics (B,3,4) f64, intrinsics (B,3,3), kpoints_3d (B,12,3) in
-    _KP_NAMES order -> (B,7) uint8 on the device (0xff rows mark out-of-frame projections)."""
+    _KP_NAMES order -> (B,7) uint8 on the device (0xff rows: a projection beyond 2^20 pixels, refused)."""
     torch = _lib.require_cuda()
     E = torch.as_tensor(np.ascontiguousarray(extrinsics, np.float64)).cuda()
     K = torch.as_tensor(np.ascontiguousarray(intrinsics, np.float64)).cuda()
@@ -66,7 +66,6 @@ def compute_visibility(extrinsic, intrinsic, kpoints_3d, h, w):
     vis, pts, _ = compute_visibility_batch(E, K[None], X, h, w, return_aux=True)
     vis = vis.cpu().numpy()[0]
     if vis[0] == 0xff:
-        raise NotImplementedError(
-            "compute_visibility: a projected keypoint lies outside the frame "
-            f"({pts.cpu().numpy()[0].tolist()}); cv2.fillPoly's clipped-polygon regime is not covered by the CUDA path")
+        raise ValueError("compute_visibility: a keypoint projects beyond 2^20 pixels "
+                         f"({pts.cpu().numpy()[0].tolist()}); is it on the camera plane?")
     return {n: bool(v) for n, v in zip(_VIS_NAMES, vis)}

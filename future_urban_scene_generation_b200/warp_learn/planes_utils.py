@@ -28,8 +28,10 @@ def get_planes(image: np.ndarray, src_kpoint_dict, pascal_class: str, planes_vis
     for n, arr in zip(names, kpoints_planes):
         for k, v in zip(pascal_texture_planes[pascal_class][n], arr):
             kp12[_KP_NAMES.index(k)] = v
-    if (kp12[:, 0].min() < 0 or kp12[:, 0].max() >= w or kp12[:, 1].min() < 0 or kp12[:, 1].max() >= h):
-        raise NotImplementedError("get_planes: keypoint outside the frame (clipped fillPoly regime not covered)")
+    # keypoints outside the frame are served (cv2.fillPoly's clipped-edge rules are reproduced on the device);
+    # the 16.16 fixed-point edge arithmetic is guaranteed up to |coordinate| <= 2^20 (csrc/warp_geom.cuh)
+    if np.abs(kp12).max() > _lib.POLY_COORD_MAX:
+        raise ValueError("get_planes: keypoint magnitude beyond 2^20 pixels")
     img = torch.as_tensor(np.ascontiguousarray(image, np.uint8)).cuda()
     kp = torch.as_tensor(kp12).cuda()
     planes = torch.empty((5, h, w, 3), dtype=torch.uint8, device="cuda")

@@ -155,10 +155,8 @@ void orc_fill_poly(uint8_t *mask, int H, int W, const int32_t *pts, int n, uint8
         if ((uint64_t)t0x >= (uint64_t)W || (uint64_t)t1x >= (uint64_t)W ||
             (uint64_t)t0y >= (uint64_t)H || (uint64_t)t1y >= (uint64_t)H) {
             clip_line(W, H, &t0x, &t0y, &t1x, &t1y);
-            if (t0y != t1y) {
-                c0y = t0y; c1y = t1y;
-                c0x = t0x << XY_SHIFT; c1x = t1x << XY_SHIFT;
-            }
+            if (t0y != t1y) { c0y = t0y; c1y = t1y; }
+            c0x = t0x << XY_SHIFT; c1x = t1x << XY_SHIFT;
         }
         if (p0y != p1y) {
             PolyEdge e;

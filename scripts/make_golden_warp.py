@@ -61,9 +61,9 @@ for idx in range(N):
         "plane_j": [int(v) for v in pj],
     })
 
-def ref_crop(idx):
-    p = synth.make_pose_pair(idx)
-    img = synth.make_crop(idx)
+def ref_crop(idx, H=H, W=W, out_of_frame=False):
+    p = synth.make_pose_pair(idx, H, W, out_of_frame=out_of_frame)
+    img = synth.make_crop(idx, H, W)
     kp3d = {k: p["kp3d"][i] for i, k in enumerate(synth.KP_NAMES)}
     vs = compute_visibility(p["E_src"], p["K"], kp3d, H, W)
     vd = compute_visibility(p["E_dst"], p["K"], kp3d, H, W)
@@ -73,18 +73,33 @@ def ref_crop(idx):
     dp, dkp, dv = get_planes(img, kd, 'car', vd)
     wr, _ = warp_unwarp_planes(sp, skp, dkp, sv, dv, 'car', pascal_texture_planes)
     vis = np.array([[int(bool(v[k])) for k in O.PLANE_NAMES] for v in (vs, vd)], np.uint8)
+    wo, vo, pj, _ = O.warp_fused(img, p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
+    assert np.array_equal(vis, vo[:2]) and np.array_equal(wr, wo) and np.array_equal(sp, O.get_planes(img, p["src_kp"])), (idx, H, W)
     return vis, wr
 
 
+def bulk_set(first, n, H=H, W=W, out_of_frame=False):
+    shas, planes = [], 0
+    for idx in range(first, first + n):
+        vis, wr = ref_crop(idx, H, W, out_of_frame)
+        planes += sum(bool(wr[j].any()) for j in range(5))
+        shas.append(hashlib.sha1(vis.tobytes() + np.ascontiguousarray(wr).tobytes()).hexdigest()[:16])
+    return shas, planes
+
+
+import warnings
+warnings.simplefilter("ignore")          # normalize_kpoints warns about keypoints > 1.0 in the out-of-frame sets
 BULK0, BULKN = 1000, 2000
-bulk = []
-bulk_planes = 0
-for idx in range(BULK0, BULK0 + BULKN):
-    vis, wr = ref_crop(idx)
-    bulk_planes += sum(bool(wr[j].any()) for j in range(5))
-    bulk.append(hashlib.sha1(vis.tobytes() + np.ascontiguousarray(wr).tobytes()).hexdigest()[:16])
+bulk, bulk_planes = bulk_set(BULK0, BULKN)
+# vehicles leaving the frame (clipped-polygon regime of cv2.fillPoly): 2000 crops at 256 x 256, 60 at the reference's
+# own 1280 x 720 working resolution (GUI/app_interface.py:181)
+oob, oob_planes = bulk_set(0, 2000, out_of_frame=True)
+oob720, oob720_planes = bulk_set(0, 60, 720, 1280, out_of_frame=True)
 
 gold = {"cv2_version": cv2.__version__, "n": N, "hw": [H, W], "written_planes": n_planes, "cases": cases,
-        "bulk_first": BULK0, "bulk_sha1_16": bulk, "bulk_written_planes": bulk_planes}
+        "bulk_first": BULK0, "bulk_sha1_16": bulk, "bulk_written_planes": bulk_planes,
+        "oob_sha1_16": oob, "oob_written_planes": oob_planes,
+        "oob720_sha1_16": oob720, "oob720_written_planes": oob720_planes}
 json.dump(gold, open(os.path.join(ROOT, "tests", "golden", "warp_golden.json"), "w"))
-print(f"{N} crops: {n_planes} written planes, all identical to the oracle; bulk {BULKN} crops, {bulk_planes} written planes")
+print(f"{N} crops: {n_planes} written planes, all identical to the oracle; bulk {BULKN} crops, {bulk_planes} written planes; "
+      f"out-of-frame 2000 crops / {oob_planes} planes at 256x256, 60 crops / {oob720_planes} planes at 1280x720")

@@ -124,6 +124,33 @@ def test_oracle_reproduces_reference_goldens():
         assert [_sha(warped[j]) for j in range(5)] == case["warped_sha1"], idx
 
 
+def test_fillpoly_matches_cv2_out_of_frame():
+    """cv2.fillPoly's clipped-edge regime: vertices outside the canvas (outline drawn from the clipLine'd end points;
+    interior edges take x -- always -- and y -- unless horizontal -- from the clipped segment)."""
+    rng = np.random.default_rng(12)
+    for t in range(4000):
+        H, W = [(256, 256), (96, 160), (720, 1280), (64, 64)][t % 4]
+        n = 4 if t % 2 else 6
+        spread = [0.2, 0.6, 2.0, 8.0][(t // 4) % 4]
+        c = np.array([rng.integers(-W // 4, W + W // 4), rng.integers(-H // 4, H + H // 4)])
+        pts = (c + rng.normal(0, spread * max(H, W) / 4, (n, 2))).astype(np.int32)
+        ref = cv2.fillPoly(np.zeros((H, W), np.uint8), [pts], 1)
+        got = O.fill_poly(np.zeros((H, W), np.uint8), pts, 1)
+        assert np.array_equal(ref, got), ((H, W), pts.tolist())
+
+
+def test_oracle_reproduces_reference_out_of_frame_goldens():
+    """Vehicles leaving the frame: the reference's outputs (hashes committed by scripts/make_golden_warp.py) at 256 x 256
+    and at its own 1280 x 720 working resolution."""
+    gold = json.load(open(os.path.join(GOLD, "warp_golden.json")))
+    for key, (H, W), step in (("oob_sha1_16", (256, 256), 8), ("oob720_sha1_16", (720, 1280), 6)):
+        for idx in range(0, len(gold[key]), step):
+            p = synth.make_pose_pair(idx, H, W, out_of_frame=True)
+            warped, vis, pj, _ = O.warp_fused(synth.make_crop(idx, H, W), p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
+            got = hashlib.sha1(np.ascontiguousarray(vis[:2], np.uint8).tobytes() + np.ascontiguousarray(warped).tobytes()).hexdigest()[:16]
+            assert got == gold[key][idx], (key, idx)
+
+
 def test_oracle_reproduces_reference_bulk_goldens():
     """2000 further crops (seeds 1000..2999, 4268 written planes): sha1 over (visibility x2, warped planes) of the
     reference's outputs -- no tolerance, no exceptions."""

@@ -57,6 +57,33 @@ def test_bulk_reference_goldens(cuda):
     assert not bad, f"{len(bad)} of {len(want)} crops differ from the reference: {bad[:10]}"
 
 
+@pytest.mark.parametrize("key,hw,chunk", [("oob_sha1_16", (256, 256), 500), ("oob720_sha1_16", (720, 1280), 12)])
+def test_out_of_frame_reference_goldens(cuda, key, hw, chunk):
+    """Vehicles leaving the frame (cv2.fillPoly's clipped-polygon regime, online_visibility.py:78-102 and
+    planes_utils.py:25-31): every crop is warped, none refused, and the bytes equal the imported reference's."""
+    import hashlib
+    import json
+    import os
+    from future_urban_scene_generation_b200.warp_learn import warp_batch
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "warp_golden.json")))
+    want = gold[key]
+    h, w = hw
+    bad, n_out = [], 0
+    for c0 in range(0, len(want), chunk):
+        n = min(chunk, len(want) - c0)
+        batch = synth.make_warp_batch(c0, n, h, w, out_of_frame=True)
+        n_out += int(((batch["src_kp"] < 0) | (batch["src_kp"] >= [w, h]) | (batch["dst_kp"] < 0) | (batch["dst_kp"] >= [w, h])).any(axis=(1, 2)).sum())
+        res = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"], check=True)
+        vis, warped = res.vis.cpu().numpy(), res.warped.cpu().numpy()
+        assert not (res.plane_j == -2).any().item()
+        for i in range(n):
+            got = hashlib.sha1(np.ascontiguousarray(vis[i, :2]).tobytes() + np.ascontiguousarray(warped[i]).tobytes()).hexdigest()[:16]
+            if got != want[c0 + i]:
+                bad.append(c0 + i)
+    assert n_out >= 0.9 * len(want)            # the set really is out of frame
+    assert not bad, f"{len(bad)} of {len(want)} crops differ from the reference: {bad[:10]}"
+
+
 def test_visibility_areas_match_oracle(cuda):
     from oracle import warp_oracle as O
     from future_urban_scene_generation_b200.warp_learn.online_visibility import compute_visibility_batch
@@ -81,9 +108,8 @@ def test_compute_visibility_dropin(cuda):
     got = compute_visibility(p["E_src"], p["K"], kp3d, 256, 256)
     assert list(got.keys()) == O.PLANE_NAMES
     assert got == O.compute_visibility(p["E_src"], p["K"], kp3d, 256, 256)
-    # out-of-frame projections are refused loudly, never silently different
-    with pytest.raises(NotImplementedError):
-        compute_visibility(p["E_src"], p["K"], kp3d, 64, 64)
+    # out-of-frame projections follow cv2's clipped polygons
+    assert compute_visibility(p["E_src"], p["K"], kp3d, 64, 64) == O.compute_visibility(p["E_src"], p["K"], kp3d, 64, 64)
 
 
 def test_get_planes_dropin(cuda):
@@ -150,14 +176,32 @@ def test_warp_perspective_and_unwarp_dropin(cuda):
         assert np.array_equal(u_got, u_ref)
 
 
-def test_out_of_frame_keypoints_are_flagged(cuda):
-    from future_urban_scene_generation_b200.warp_learn import warp_batch
+def test_absurd_keypoints_are_refused_loudly(cuda):
+    """Vertices beyond 2^20 px (a keypoint on the camera plane) are outside cv2's int32 rasteriser and the 16.16 edge
+    arithmetic: the crop comes back refused (plane_j == -2, zero planes) and the host raises -- never silent."""
+    from future_urban_scene_generation_b200.warp_learn import warp_batch, check_refused, RefusedCrops
     batch = synth.make_warp_batch(0, 4)
-    batch["src_kp"][2, 3, 0] = 300          # outside a 256-wide frame
+    batch["src_kp"][2, 3, 0] = (1 << 20) + 5
     res = warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"])
     pj = res.plane_j.cpu().numpy()
     assert (pj[2] == -2).all() and (pj[[0, 1, 3]] != -2).all()
     assert not res.warped[2].any().item()
+    with pytest.raises(RefusedCrops) as ei:
+        check_refused(res)
+    assert ei.value.indices == [2]
+    with pytest.raises(RefusedCrops):
+        warp_batch(batch["src"], batch["src_kp"], batch["dst_kp"], batch["K"], batch["E_src"], batch["E_dst"], batch["kp3d"], check=True)
+
+
+def test_get_planes_dropin_out_of_frame(cuda):
+    from oracle import warp_oracle as O
+    from future_urban_scene_generation_b200.warp_learn.planes_utils import get_planes
+    for idx, (h, w) in enumerate([(256, 256), (90, 130), (720, 1280)] * 3):
+        p = synth.make_pose_pair(idx, h, w, out_of_frame=True)
+        img = synth.make_crop(idx, h, w)
+        kd = {k: p["kp2d_src"][i] for i, k in enumerate(synth.KP_NAMES)}
+        planes, kps, v = get_planes(img, kd, 'car', {n: True for n in O.PLANE_NAMES})
+        assert np.array_equal(planes, O.get_planes(img, p["src_kp"]))
 
 
 def test_large_batch_properties(cuda):
