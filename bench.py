@@ -8,9 +8,10 @@ the dominant kernel, next to the reference algorithm's CPU path timed on this bo
   python bench.py --impl reference ...                           CPU arm: the oracle port of the reference path
 
 One "step" = one pass of the hot path over one batch of synthetic crops (BASELINE config 2: 64 crops
-per GPU): fusg_warp_fused on the batch, Vunet_fix_res.forward on the batch, to_image, and -- when
-N > 1 -- the NCCL all-gather of the completed uint8 crops (the only collective; crops are sharded
-contiguously by rank, weak scaling).  Prints ONE JSON line on rank 0.
+per GPU; at 8 GPUs BASELINE config 4: 4096 crops = 512 per rank in 8 micro-batches of 64):
+fusg_warp_fused, Vunet_fix_res.forward, to_image, and -- when N > 1 -- ONE NCCL all-gather of the
+step's completed uint8 crops (the only collective; crops are sharded contiguously by rank, weak
+scaling).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import collections
@@ -87,17 +88,58 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (test infrastructure used as the timed baseline)
 # ------------------------------------------------------------------------------------------------
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _import_reference():
+    """The reference's own modules, when its tree is reachable (the build container has /root/reference; the GPU box
+    does not -- reference sources are never copied into this repo).  Returns None when it is not importable."""
+    for root in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(root, "warp_learn")) and os.path.isdir(os.path.join(root, "vunet")):
+            os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
+            if root not in sys.path:
+                sys.path.append(root)
+            try:
+                import warnings
+                warnings.simplefilter("ignore")
+                from warp_learn.online_visibility import compute_visibility, pascal_texture_planes
+                from warp_learn.planes_utils import get_planes, warp_unwarp_planes
+                from vunet.models import Vunet_fix_res
+                return {"root": root, "compute_visibility": compute_visibility, "pascal_texture_planes": pascal_texture_planes,
+                        "get_planes": get_planes, "warp_unwarp_planes": warp_unwarp_planes, "Vunet_fix_res": Vunet_fix_res}
+            except Exception:
+                return None
+    return None
+
+
 def cpu_reference_run(steps, warmup, crops_per_step=1):
-    """Times the reference algorithm's CPU path: oracle/warp_oracle.c (scalar C, 1 thread) for
-    visibility x2 + homographies + masked warp, and oracle/vunet_oracle.py (torch fp32, all host
-    threads) for the VUNet forward -- BASELINE config 1 (batch 1, --device cpu)."""
+    """Times the reference's CPU path on BASELINE config 1 (batch 1, --device cpu), all host threads.
+    kind "reference": the reference's own modules (compute_visibility x2 + get_planes x2 + warp_unwarp_planes through
+    cv2, Vunet_fix_res.forward through torch) when its tree is importable; kind "port" otherwise: oracle/warp_oracle.c
+    (scalar C, 1 thread) + oracle/vunet_oracle.py (torch fp32, all host threads)."""
     import numpy as np
     import torch
     from future_urban_scene_generation_b200 import synth
-    from oracle import warp_oracle as WO, vunet_oracle as VO
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = VO.make_state_dict(0)
+    ref = _import_reference()
+    if ref is not None:
+        from argparse import Namespace
+        import cv2
+        torch.manual_seed(0)
+        net = ref["Vunet_fix_res"](Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).eval()
+        kind, cv_threads = "reference", cv2.getNumThreads()
+    else:
+        from oracle import warp_oracle as WO, vunet_oracle as VO
+        sd = VO.make_state_dict(0)
+        kind, cv_threads = "port", None
     t_warp, t_vunet = [], []
     for s in range(warmup + steps):
         tw = tv = 0.0
@@ -108,10 +150,23 @@ def cpu_reference_run(steps, warmup, crops_per_step=1):
             x, y = synth.make_vunet_inputs(idx, 1)
             x, y = torch.from_numpy(x), torch.from_numpy(y)
             t0 = time.perf_counter()
-            WO.warp_fused(img, p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
+            if ref is not None:
+                kp3d = {k: p["kp3d"][i] for i, k in enumerate(synth.KP_NAMES)}
+                ks = {k: p["kp2d_src"][i] for i, k in enumerate(synth.KP_NAMES)}
+                kd = {k: p["kp2d_dst"][i] for i, k in enumerate(synth.KP_NAMES)}
+                vs = ref["compute_visibility"](p["E_src"], p["K"], kp3d, 256, 256)
+                vd = ref["compute_visibility"](p["E_dst"], p["K"], kp3d, 256, 256)
+                sp, skp, sv = ref["get_planes"](img, ks, 'car', vs)
+                dp, dkp, dv = ref["get_planes"](img, kd, 'car', vd)
+                ref["warp_unwarp_planes"](sp, skp, dkp, sv, dv, 'car', ref["pascal_texture_planes"])
+            else:
+                WO.warp_fused(img, p["src_kp"], p["dst_kp"], p["K"], p["E_src"], p["E_dst"], p["kp3d"])
             t1 = time.perf_counter()
             with torch.no_grad():
-                VO.forward(sd, y, x)
+                if ref is not None:
+                    net(y, x)
+                else:
+                    VO.forward(sd, y, x)
             t2 = time.perf_counter()
             tw += t1 - t0
             tv += t2 - t1
@@ -120,9 +175,14 @@ def cpu_reference_run(steps, warmup, crops_per_step=1):
             t_vunet.append(tv)
     total = sum(t_warp) + sum(t_vunet)
     n = steps * crops_per_step
-    return {"value": n / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} crops, batch 1 (BASELINE config 1): C oracle warp {1e3 * sum(t_warp) / n:.1f} ms/crop (1 thread) + "
-                      f"torch fp32 VUNet oracle {sum(t_vunet) / n:.3f} s/crop ({torch.get_num_threads()} threads)",
+    if ref is not None:
+        how = (f"the reference's own modules ({ref['root']}): cv2 warp half {1e3 * sum(t_warp) / n:.1f} ms/crop (cv2 threads {cv_threads}) + "
+               f"Vunet_fix_res.forward fp32 {sum(t_vunet) / n:.3f} s/crop (torch threads {torch.get_num_threads()})")
+    else:
+        how = (f"C oracle warp {1e3 * sum(t_warp) / n:.1f} ms/crop (1 thread) + torch fp32 VUNet oracle {sum(t_vunet) / n:.3f} s/crop "
+               f"({torch.get_num_threads()} threads); reference tree not present on this box")
+    return {"value": n / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} crops, batch 1 (BASELINE config 1): {how}; os.cpu_count()={cores}, CPU {_cpu_model()}",
             "ms_per_step": 1e3 * total / steps}
 
 
@@ -143,6 +203,45 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa(torch, rank, world):
+    """Binds this rank's threads (main, noise prefetch, torch intra-op) to its share of the CPUs of the NUMA node its
+    GPU hangs off, BEFORE any pinned staging buffer is allocated (first touch puts the pages on that node).  Without this
+    eight ranks each start os.cpu_count() intra-op threads for the Sampler noise and trample each other."""
+    def gpu_node(i):
+        try:
+            pr = torch.cuda.get_device_properties(i)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            return int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        except Exception:
+            return -1
+
+    def cpulist(node):
+        try:
+            txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            out = []
+            for part in txt.split(","):
+                lo, _, hi = part.partition("-")
+                out.extend(range(int(lo), int(hi or lo) + 1))
+            return out
+        except Exception:
+            return []
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        nodes = [gpu_node(i) for i in range(world)]
+        mine = nodes[rank]
+        pool = [c for c in cpulist(mine) if c in allowed] if mine >= 0 else []
+        peers = [r for r in range(world) if nodes[r] == mine] if pool else list(range(world))
+        if not pool:
+            pool = allowed
+        k = peers.index(rank)
+        share = pool[k * len(pool) // len(peers):(k + 1) * len(pool) // len(peers)] or pool
+        os.sched_setaffinity(0, share)
+        torch.set_num_threads(max(1, min(len(share), 8)))
+        return {"numa_node": mine, "cpus": len(share), "torch_threads": torch.get_num_threads()}
+    except Exception as exc:                                  # affinity is an optimisation, never a reason to fail
+        return {"numa_node": None, "error": str(exc)[:80]}
+
+
 def run_ours(args):
     from argparse import Namespace
     import numpy as np
@@ -150,7 +249,6 @@ def run_ours(args):
     import torch.distributed as dist
     from future_urban_scene_generation_b200 import synth, _lib
     from future_urban_scene_generation_b200.warp_learn import warp_batch
-    from future_urban_scene_generation_b200.warp_learn.planes_utils import to_image_batch
     from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
     from future_urban_scene_generation_b200.parallel import shard_range, gather_crops
 
@@ -161,11 +259,19 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = pin_to_gpu_numa(torch, local_rank, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version/info lines must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
-    B = args.crops_per_rank
+    # BASELINE config 2: 64 crops per GPU per step; config 4 (8 GPUs): 4096 crops per step = 512 per rank, processed as
+    # 8 micro-batches of 64 (the same kernels, graphs and per-GPU work per crop as every other N -> weak scaling holds)
+    # with ONE all-gather of the 805 MB of completed crops per step.
+    B = args.micro_batch
+    CPR = args.crops_per_rank if args.crops_per_rank else (512 if world == 8 else 64)
+    if CPR % B:
+        raise SystemExit("--crops-per-rank must be a multiple of --micro-batch")
+    M = CPR // B
     peaks = _peaks()
 
     # ---- model: random-init weights of the reference architecture (checkpoints are not available offline)
@@ -173,21 +279,26 @@ def run_ours(args):
     model = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).to(dev).eval()
     eng = model.engine()
 
-    # ---- synthetic inputs for this rank's contiguous shard of crops (SURVEY.md §8d generators)
-    first, last = shard_range(world * B, rank, world)
-    assert last - first == B
-    wb = synth.make_warp_batch(first, B)
-    xs, ys = synth.make_vunet_inputs(first, B)
-    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
-    host["x"] = torch.from_numpy(xs).pin_memory()
-    host["y"] = torch.from_numpy(ys).pin_memory()
-    devin = {k: v.to(dev) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    # ---- synthetic inputs for this rank's contiguous shard of crops (SURVEY.md §8d generators), one dict per micro-batch
+    first, last = shard_range(world * CPR, rank, world)
+    assert last - first == CPR
+
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host_u8, host_f32 = [], []
+    for mb in range(M):
+        f0 = first + mb * B
+        wb = {k: pinned(v) for k, v in synth.make_warp_batch(f0, B).items()}
+        mk, nsrc, ndst = synth.make_vunet_inputs_u8(f0, B)
+        # the form the reference holds before to_tensor (trajectory_inference.py:215-220): three uint8 images per crop
+        host_u8.append(dict(wb, x_mask_u8=pinned(mk), x_normal_u8=pinned(nsrc), y_normal_u8=pinned(ndst)))
+        if M == 1:
+            xs, ys = synth.make_vunet_inputs(f0, B)
+            host_f32.append(dict(wb, x=pinned(xs), y=pinned(ys)))
+    h2d_bytes_u8 = M * sum(v.numel() * v.element_size() for v in host_u8[0].values())
 
     from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
-    # The public batched API: NovelViewPipeline (CUDA-graph replay of the ~125 launches of a step, two
-    # steps in flight).  N > 1 adds the NCCL all-gather of the completed crops (eager launches then).
-    pipe = NovelViewPipeline(model, depth=2, gather_fn=(lambda c: gather_crops(c, world * B)) if world > 1 else None)
+    gather = (lambda c: gather_crops(c, world * CPR)) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -201,108 +312,98 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    def run_steps(n, resident, pipe=pipe, host=host):
-        # keep depth-1 steps in flight behind the one being submitted; every step's outputs are read on the host
+    def run_steps(pipe, n, resident, host):
+        """n steps of M micro-batches.  depth-1 submits stay in flight behind the one being issued; in the end-to-end
+        form every micro-batch's outputs are read on the host."""
         pending, last = collections.deque(), None
         for _ in range(n):
-            last = pipe.submit(host, resident=resident)
-            pending.append(last)
-            if len(pending) >= pipe.depth and not resident:
-                pipe.result(pending.popleft())         # an earlier step's outputs are on the host
+            for mb in range(M):
+                last = pipe.submit(host[mb], resident=resident)
+                pending.append(last)
+                if len(pending) >= pipe.depth and not resident:
+                    pipe.result(pending.popleft())         # an earlier micro-batch's outputs are on the host
         if resident:
             pipe.wait(last)
         else:
             while pending:
                 pipe.result(pending.popleft())
+        if gather is not None:
+            pipe.wait_gather()                             # the last step's all-gather belongs to the timed region
         return last
 
-    # warm-up: builds the slots (eager pass + graph capture), fills inputs and noise on the device
-    torch.manual_seed(1)
-    last_ticket = run_steps(max(3, args.warmup), resident=False)
-    d2h_bytes = pipe.d2h_bytes(last_ticket)
-    launches_per_step = pipe.launches_per_step()
+    def timed(pipe, n, resident, host, first_stream, last_stream_of):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(first_stream)
+        last_t = run_steps(pipe, n, resident, host)
+        e1.record(last_stream_of(last_t))
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        # several streams are in flight: bracket with device events and cross-check with the host clock
+        ms = reduce_max(max(e0.elapsed_time(e1), wall if (n * M >= 20 or not resident) else 0.0))
+        barrier()
+        return ms
 
     # ---- device-resident loop: inputs and noise already in HBM, graph replays only ----------------
+    # The public batched API: NovelViewPipeline (CUDA-graph replay of the launches of a micro-batch, two in flight).
+    pipe = NovelViewPipeline(model, depth=2, gather_fn=gather, micro_batches_per_step=M)
+    torch.manual_seed(1)
+    warm = max(3, args.warmup)
+    last_ticket = run_steps(pipe, max(warm, (3 + M - 1) // M), resident=False, host=host_u8)
+    launches_per_mb = pipe.launches_per_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(pipe.slots[pipe.n % pipe.depth].stream)                     # the stream of the first timed step
-    last_t = run_steps(args.steps, resident=True)
-    e1.record(pipe.slots[last_t % pipe.depth].stream)                     # ... and of the last one
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    # two compute streams are in flight: bracket with device events and cross-check with the host clock
-    ms_total = reduce_max(max(e0.elapsed_time(e1), wall_ms if args.steps >= 20 else 0.0))
-    barrier()
+    ms_total = timed(pipe, args.steps, True, host_u8, pipe.slots[pipe.n % pipe.depth].stream, lambda t: pipe.slots[t % pipe.depth].stream)
     clocks = sampler.stop() if rank == 0 else None
-    launches = launches_per_step * args.steps
+    launches = launches_per_mb * M * args.steps
     ms_per_step = ms_total / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    value = world * CPR / (ms_per_step * 1e-3)
+    del pipe
 
-    # ---- end-to-end loop: every step copies its own pinned inputs H2D, draws the Sampler noise on the
-    # CPU generator (reference semantics), and lands its own results in host memory, inside the timed region
-    # (one compute stream shared by the two slots: with host copies in the loop, graphs that overlap only
-    # partially slow each other down -- measured 11.8 vs 14.2 ms/step, scripts/e2e_probe.py)
-    pipe_e2e = NovelViewPipeline(model, depth=3, shared_stream=True,
-                                 gather_fn=(lambda c: gather_crops(c, world * B)) if world > 1 else None)
-    run_steps(5, resident=False, pipe=pipe_e2e)
+    # ---- end-to-end loop (the headline): every micro-batch copies its own pinned uint8 inputs H2D, draws the Sampler
+    # noise on the CPU generator (reference semantics), and lands its completed crops + flags in host memory, inside
+    # the timed region.  One compute stream shared by the slots: with host copies in the loop, graphs that overlap only
+    # partially slow each other down (measured 11.8 vs 14.2 ms/step, scripts/e2e_probe.py).
     e2e_steps = max(4, args.steps)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(pipe_e2e.copy_stream)
-    run_steps(e2e_steps, resident=False, pipe=pipe_e2e)
-    e1.record(pipe_e2e.out_stream)
-    torch.cuda.synchronize()
-    e2e_wall = (time.perf_counter() - t0) * 1e3
-    e2e_ms = reduce_max(max(e0.elapsed_time(e1), e2e_wall))
-    barrier()
-    e2e_value = world * B / (e2e_ms / e2e_steps * 1e-3)
-    del pipe_e2e
 
-    # ---- the same loop with the VUNet inputs shipped as the three uint8 images the reference holds before to_tensor
-    # (trajectory_inference.py:215-220; to_tensor / flip / concat run on the device): 9 instead of 36 bytes per pixel
-    mk, nsrc, ndst = synth.make_vunet_inputs_u8(first, B)
-    host_u8 = {k: v for k, v in host.items() if k not in ("x", "y")}
-    host_u8.update(x_mask_u8=torch.from_numpy(mk).pin_memory(), x_normal_u8=torch.from_numpy(nsrc).pin_memory(),
-                   y_normal_u8=torch.from_numpy(ndst).pin_memory())
-    h2d_bytes_u8 = sum(v.numel() * v.element_size() for v in host_u8.values())
-    pipe_u8 = NovelViewPipeline(model, depth=3, shared_stream=True,
-                                gather_fn=(lambda c: gather_crops(c, world * B)) if world > 1 else None)
-    run_steps(5, resident=False, pipe=pipe_u8, host=host_u8)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(pipe_u8.copy_stream)
-    run_steps(e2e_steps, resident=False, pipe=pipe_u8, host=host_u8)
-    e1.record(pipe_u8.out_stream)
-    torch.cuda.synchronize()
-    u8_wall = (time.perf_counter() - t0) * 1e3
-    u8_ms = reduce_max(max(e0.elapsed_time(e1), u8_wall))
-    barrier()
-    e2e_u8_value = world * B / (u8_ms / e2e_steps * 1e-3)
-    del pipe_u8
+    def e2e_run(host, **kw):
+        pp = NovelViewPipeline(model, depth=3, shared_stream=True, gather_fn=gather, micro_batches_per_step=M, **kw)
+        lt = run_steps(pp, max(2, (5 + M - 1) // M), resident=False, host=host)
+        d2h = M * pp.d2h_bytes(lt)
+        ms = timed(pp, e2e_steps, False, host, pp.copy_stream, lambda t: pp.out_stream)
+        return world * CPR / (ms / e2e_steps * 1e-3), ms / e2e_steps, d2h
+    e2e_value, e2e_ms_step, d2h_bytes = e2e_run(host_u8)
+    extra = {}
+    if M == 1 and not args.headline_only:
+        # the same loop with the warped planes also copied back to the host (round-1 contract) ...
+        v, ms, d2h = e2e_run(host_u8, return_warped=True)
+        extra["e2e_u8_with_planes"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes_u8, "d2h_bytes_per_step": d2h, "ms_per_step": ms,
+                                       "note": "as e2e, plus the (B,5,256,256,3) warped planes D2H (the reference never reads them on the host)"}
+        # ... and with the VUNet inputs shipped as fp32 NCHW tensors (36 instead of 9 bytes per pixel)
+        v, ms, d2h = e2e_run(host_f32, return_warped=True)
+        extra["e2e_fp32"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_f32[0].values()),
+                             "d2h_bytes_per_step": d2h, "ms_per_step": ms,
+                             "note": "round-1 headline form: x / y_tilde as fp32 NCHW host tensors, warped planes copied back"}
 
     # ---- per-launch roofline pass (CUDA events around every conv launch, on the launching stream)
-    devin = {k: v.to(dev) for k, v in host.items()}
-    noise_bank = {}
-
-    def staged_noise(b, c, h, w):
-        key = (b, c, h, w, staged_noise.i)
-        staged_noise.i += 1
-        if key not in noise_bank:
-            noise_bank[key] = torch.randn((b, h, w, c), device=dev)
-        return noise_bank[key]
-    staged_noise.i = 0
-    eng.noise_provider = staged_noise
-    roof = None
-    warp_roof = None
+    roof = warp_roof = None
     if rank == 0:
-        eng.profile = []
+        xs, ys = synth.make_vunet_inputs(first, B)
+        devin = {k: v.to(dev) for k, v in host_u8[0].items()}
+        devin["x"], devin["y"] = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+        noise_bank = {}
+
+        def staged_noise(b, c, h, w):
+            key = (b, c, h, w, staged_noise.i)
+            staged_noise.i += 1
+            if key not in noise_bank:
+                noise_bank[key] = torch.randn((b, h, w, c), device=dev)
+            return noise_bank[key]
         staged_noise.i = 0
+        eng.noise_provider = staged_noise
+        eng.profile = []
         model.fork_branches = False            # per-launch timing: one stream, no kernel overlaps another
         for _ in range(2):
             staged_noise.i = 0
@@ -314,6 +415,7 @@ def run_ours(args):
         model.fork_branches = True
         recs = eng.profile
         eng.profile = None
+        eng.noise_provider = None
         agg = {}
         for path, impl, flops, e0, e1 in recs:
             a = agg.setdefault(impl, [0.0, 0.0, 0])
@@ -324,41 +426,48 @@ def run_ours(args):
         achieved = tc[0] / tc[1] / 1e12
         peak = peaks["bf16_tflops_sustained"]
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic_summary.json")
-        if os.path.exists(tpath) and B == 64:
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
+        for name in ("r2_conv_traffic_summary.json", "r1_conv_traffic_summary.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath) and B == 64:
+                tj = json.load(open(tpath))
+                traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
+                break
         roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu; B=64)", "traffic_source": traffic_src, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_per_step": tc[2] // 2, "avg_launch_ms": 1e3 * tc[1] / max(1, tc[2]),
                 "algorithmic_flops_per_step": tc[0] / 2, "share_of_vunet_time": tc[1] / max(1e-9, sum(a[1] for a in agg.values()))}
-        # fused warp kernel alone (BASELINE config 3 shape, HBM bound)
+        # fused warp path alone (HBM bound) at this micro-batch ...
+        wk = ("src", "src_kp", "dst_kp", "K", "E_src", "E_dst", "kp3d")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            warp_batch(devin["src"], devin["src_kp"], devin["dst_kp"], devin["K"], devin["E_src"], devin["E_dst"], devin["kp3d"], device=dev)
+            warp_batch(*(devin[k] for k in wk), device=dev)
         reps = 20
         e0.record()
         for _ in range(reps):
-            warp_batch(devin["src"], devin["src_kp"], devin["dst_kp"], devin["K"], devin["E_src"], devin["E_dst"], devin["kp3d"], device=dev)
+            warp_batch(*(devin[k] for k in wk), device=dev)
         e1.record()
         torch.cuda.synchronize()
         wsec = e0.elapsed_time(e1) * 1e-3 / reps
         wgbs = B * WARP_BYTES_PER_CROP / wsec / 1e9
-        warp_roof = {"bound": "hbm", "kernel": "fusg_warp_fused (k_visibility+k_homography+k_warp)", "achieved": wgbs, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": wgbs / peaks["hbm_gbs"], "crops": B, "ms": wsec * 1e3,
+        wtraffic = None
+        wt = os.path.join(ROOT, "profiles", "r2_warp_traffic_summary.json")
+        if os.path.exists(wt):
+            wtraffic = json.load(open(wt))
+        warp_roof = {"bound": "hbm", "kernel": "fusg_warp_fused", "achieved": wgbs, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": wgbs / peaks["hbm_gbs"], "crops": B, "ms": wsec * 1e3, "traffic": wtraffic,
                      "note": f"{B} crops only ({B * WARP_BYTES_PER_CROP / 1e6:.0f} MB < L2, latency-bound); see large_batch"}
-        # the same call at an HBM-sized batch: this rank's crops tiled to 4096 (4.8 GB of algorithmic traffic, the
-        # compacted thread-per-solve homography path); BASELINE config 3 proper (16k crops) is scripts/bench_warp.py
+        # ... and at an HBM-sized batch: this rank's crops tiled to 4096 (4.8 GB of algorithmic traffic);
+        # BASELINE config 3 proper (16k crops) is scripts/bench_warp.py
         try:
             BL = 4096
             rep = (BL + B - 1) // B
-            big = {k: devin[k].repeat((rep,) + (1,) * (devin[k].dim() - 1))[:BL].contiguous() for k in ("src", "src_kp", "dst_kp", "K", "E_src", "E_dst", "kp3d")}
+            big = {k: devin[k].repeat((rep,) + (1,) * (devin[k].dim() - 1))[:BL].contiguous() for k in wk}
             for _ in range(2):
-                rb = warp_batch(big["src"], big["src_kp"], big["dst_kp"], big["K"], big["E_src"], big["E_dst"], big["kp3d"], device=dev)
+                rb = warp_batch(*(big[k] for k in wk), device=dev)
             torch.cuda.synchronize()
             e0.record()
             for _ in range(3):
-                rb = warp_batch(big["src"], big["src_kp"], big["dst_kp"], big["K"], big["E_src"], big["E_dst"], big["kp3d"], device=dev)
+                rb = warp_batch(*(big[k] for k in wk), device=dev)
             e1.record()
             torch.cuda.synchronize()
             bsec = e0.elapsed_time(e1) * 1e-3 / 3
@@ -366,40 +475,49 @@ def run_ours(args):
             warp_roof["large_batch"] = {"crops": BL, "ms": bsec * 1e3, "achieved": bgbs, "unit": "GB/s", "frac": bgbs / peaks["hbm_gbs"]}
             del big, rb
             torch.cuda.empty_cache()
-        except RuntimeError as exc:                       # e.g. not enough free memory next to the pipelines: report, do not fail the bench
+        except RuntimeError as exc:                       # e.g. not enough free memory: report, do not fail the bench
             warp_roof["large_batch"] = {"skipped": str(exc)[:120]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))          # the CPU arm gets every host core
+        except Exception:
+            pass
         cpu = cpu_reference_run(steps=8, warmup=1)
         cpu.pop("ms_per_step", None)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{B} synthetic 256x256 vehicle crops per GPU per step: fused planar warp (5 CAD planes) + VUNet bf16 forward "
-                                   f"(BASELINE config 2), random-init weights" + (", NCCL all-gather of completed uint8 crops" if world > 1 else ""),
-                       "crops_per_gpu": B, "global_crops_per_step": world * B, "parallelism": f"crop-sharded dp{world}",
-                       "l2": "per-step activations (>5 GB) exceed the 126 MB L2; no explicit flush",
-                       "launch": "one CUDA-graph replay per step (gpu_launches counts the kernels inside the graphs)" + (" + eager NCCL all-gather" if world > 1 else "")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "note": "NovelViewPipeline.submit/result: pinned host inputs -> H2D, Sampler noise drawn on the CPU generator (reference "
-                            "semantics), CUDA-graph replay, completed crops + warped planes + flags D2H; 3 slots (2 steps in flight behind the one being submitted), all inside the timed region"},
-            "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes_u8, "d2h_bytes_per_step": d2h_bytes,
-                       "ms_per_step": u8_ms / e2e_steps, "steps": e2e_steps,
-                       "note": "same loop, VUNet inputs shipped as the three uint8 images the reference holds before to_tensor "
-                               "(trajectory_inference.py:215-220); to_tensor / channel flip / concat on the device (fusg_u8_to_vunet_inputs)"},
+            "config": {"workload": f"{CPR} synthetic 256x256 vehicle crops per GPU per step" + (f" in {M} micro-batches of {B}" if M > 1 else "") +
+                                   ": fused planar warp (5 CAD planes) + VUNet bf16 forward, random-init weights (BASELINE config " +
+                                   ("4: 4096 crops per step, 512 per rank" if world * CPR == 4096 else "2") + ")" +
+                                   (", one NCCL all-gather of the completed uint8 crops per step" if world > 1 else ""),
+                       "crops_per_gpu": CPR, "micro_batch": B, "global_crops_per_step": world * CPR, "parallelism": f"crop-sharded dp{world}",
+                       "gathered_bytes_per_step": world * CPR * 256 * 256 * 3 if world > 1 else 0,
+                       "l2": "per-micro-batch activations (>5 GB) exceed the 126 MB L2; no explicit flush",
+                       "launch": "one CUDA-graph replay per micro-batch (gpu_launches counts the kernels inside the graphs)" +
+                                 (" + one NCCL all-gather per step on its own stream, overlapping the next step" if world > 1 else ""),
+                       "host_affinity": affinity},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes_u8, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms_step, "steps": e2e_steps,
+                    "note": "NovelViewPipeline.submit/result: pinned host inputs in the form the reference holds them before to_tensor "
+                            "(uint8 crop + three uint8 sketch images, trajectory_inference.py:215-220) -> H2D, to_tensor/flip/concat on the "
+                            "device, Sampler noise drawn on the CPU generator (reference semantics), CUDA-graph replay, completed uint8 crops "
+                            "+ plane_j + visibility flags D2H; 3 slots in flight, all inside the timed region.  The warped planes stay in HBM "
+                            "(they feed get_icn_inputs on the device); e2e_u8_with_planes / e2e_fp32 time the round-1 forms"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
             "roofline_warp": warp_roof,
-            "vunet_tflops_whole_forward": world * B * VUNET_FLOPS_PER_CROP / (ms_per_step * 1e-3) / 1e12,
+            "vunet_tflops_whole_forward": world * CPR * VUNET_FLOPS_PER_CROP / (ms_per_step * 1e-3) / 1e12,
             "cpu_baseline": cpu,
         }
-        if world == 1 and not args.no_icn:
+        line.update(extra)
+        if world == 1 and not args.no_icn and not args.headline_only:
             line["icn_generator"] = icn_info(torch, synth, B, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -438,7 +556,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--crops-per-rank", type=int, default=64)
+    ap.add_argument("--crops-per-rank", type=int, default=0, help="crops per GPU per step (default: 512 at 8 GPUs = BASELINE config 4, else 64)")
+    ap.add_argument("--micro-batch", type=int, default=64, help="crops per graph replay (BASELINE config 2 batch)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the informational extra keys (e2e_fp32, ICN)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-icn", action="store_true")
     args = ap.parse_args()

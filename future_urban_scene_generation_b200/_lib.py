@@ -39,6 +39,7 @@ def _load():
         "fusg_warp_perspective": ([vp] * 3 + [i, i, i, vp], i),
         "fusg_conv2d": ([vp, vp], i),
         "fusg_conv2d_select": ([vp], i),
+        "fusg_conv2d_last_plan": ([vp], None),
         "fusg_sizeof_conv_desc": ([], sz),
         "fusg_fold_weightnorm": ([vp, vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_fold_weightnorm_paired": ([vp, vp, vp, vp, vp, i, i, i, i, i, i, vp], i),
@@ -80,6 +81,13 @@ def check(rc, what):
     if rc != 0:
         msg = lib().fusg_last_error().decode() if rc == -3 else ""
         raise FusgError(f"{what} failed: {ERRORS.get(rc, rc)} {msg}")
+
+
+def conv_last_plan():
+    """dict(msub, pair, halo, ksplit, stages, group, w_resident, fast_epi) of this thread's last tcgen05 conv launch."""
+    buf = (C.c_int32 * 8)()
+    lib().fusg_conv2d_last_plan(buf)
+    return dict(zip(("msub", "pair", "halo", "ksplit", "stages", "group", "w_resident", "fast_epi"), list(buf)))
 
 
 def kernel_launches():

@@ -242,6 +242,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -250,6 +251,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
+        if (!done) fusg_spin_guard(t0);
     }
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -347,6 +349,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {
 // wait on a barrier of this CTA that a PEER CTA arrives on (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -355,6 +358,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
             : "=r"(done)
             : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
+        if (!done) fusg_spin_guard(t0);
     }
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
@@ -1253,6 +1257,13 @@ static bool tc_supported(const fusg_conv_desc &d, int Ho, int Wo) {
     return get_encode() != nullptr;
 }
 
+// tiling plan of this host thread's last tcgen05 launch (fusg_conv2d_last_plan)
+static thread_local int32_t g_last_plan[8];
+
+extern "C" void fusg_conv2d_last_plan(int32_t *plan8) {
+    for (int i = 0; i < 8; ++i) plan8[i] = g_last_plan[i];
+}
+
 static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
@@ -1260,13 +1271,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.Ho = Ho; p.Wo = Wo;
     p.block_n = d.cout_pad < 128 ? d.cout_pad : 128;
     p.n_tiles = d.cout_pad / p.block_n;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = fusg_num_sms();
     // 256-row CTA tiles (two 128-row MMA sub-tiles sharing each weight k-block) once there is enough work for
     // at least ~4 tiles per SM; halves the weight traffic per output pixel
     static const int msub_max = getenv("FUSG_MSUB1") ? 1 : 2;
@@ -1430,12 +1435,13 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     const size_t pipe_b = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (p.halo ? (size_t)p.stages * d.ksize * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
     const size_t smem = pipe_a + pipe_b +
                         1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
-        if (cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return fusg_check_launch();
-        attr_set = true;
-    }
+    if (fusg_once_per_device(0, 0, [] {
+            cudaError_t e = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return e != cudaSuccess ? e : cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        }) != cudaSuccess)
+        return fusg_check_launch();
+    g_last_plan[0] = p.msub; g_last_plan[1] = p.pair; g_last_plan[2] = p.halo; g_last_plan[3] = p.ksplit;
+    g_last_plan[4] = p.stages; g_last_plan[5] = p.group; g_last_plan[6] = p.w_resident; g_last_plan[7] = p.fast_epi;
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
     static const int pdl_on = getenv("FUSG_NO_PDL") ? 0 : 1;
     p.pdl = pdl_on;

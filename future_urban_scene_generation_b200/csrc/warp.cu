@@ -374,6 +374,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -382,6 +383,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phas
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
+        if (!done) fusg_spin_guard(t0);
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
@@ -770,13 +772,9 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     if (workspace_bytes < fusg_warp_workspace_bytes_hw(B, H, W)) return FUSG_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     double *Minv = reinterpret_cast<double *>(workspace);
-    static bool attr_set = false;
     const size_t smem = H <= MAX_HW && W <= MAX_HW ? warp_smem_bytes(H, W) : 0;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW, MAX_HW)) != cudaSuccess)
-            return fusg_check_launch();
-        attr_set = true;
-    }
+    if (fusg_once_per_device(1, 0, [] { return cudaFuncSetAttribute(k_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW, MAX_HW)); }) != cudaSuccess)
+        return fusg_check_launch();
     k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, kp3d_dst, vis, nullptr, nullptr, 2 * B, H, W);
     // small batches: latency matters -> one warp per solve; large batches: throughput -> one thread per solve
     if (B * N_TEX <= 8192) k_homography<<<(B * N_TEX + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
@@ -798,11 +796,9 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
         const size_t row_smem = ((size_t)W * 3 + 15) & ~(size_t)15;
         const size_t frame_smem = row_smem * WF_ROWS;
         if (frame_smem > 200 * 1024) return FUSG_ERR_UNSUPPORTED;
-        static size_t frame_smem_set = 0;
-        if (frame_smem > 48 * 1024 && frame_smem > frame_smem_set) {
-            if (cudaFuncSetAttribute(k_warp_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frame_smem) != cudaSuccess) return fusg_check_launch();
-            frame_smem_set = frame_smem;
-        }
+        if (frame_smem > 48 * 1024 &&
+            fusg_once_per_device(2, frame_smem, [frame_smem] { return cudaFuncSetAttribute(k_warp_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frame_smem); }) != cudaSuccess)
+            return fusg_check_launch();
         k_warp_frame<<<dim3((H + WF_ROWS - 1) / WF_ROWS, N_TEX, B), 32 * WF_ROWS, frame_smem, st>>>(src, src_kp, plane_j, Minv, masks, warped, H, W, words, (int)row_smem);
         fusg_count_launch(4);
     }

@@ -41,13 +41,21 @@ class _Slot:
                                  # full-grid layers of the next batch in flight
         self.prefetch = None     # (thread, state_before, result holder) of a background noise draw into noise_stage
         self.crops_all = None    # multi-GPU: the all-gathered completed crops of the last step, on the device
+        self.wkey = None         # the engine's folded-weight key the graph was captured against
 
 
 class NovelViewPipeline:
     WARP_KEYS = ("src", "src_kp", "dst_kp", "K", "E_src", "E_dst", "kp3d")
 
     def __init__(self, model, depth: int = 2, gather_fn=None, use_graph: bool = True, shared_stream: bool = False,
-                 prefetch_noise: bool = True):
+                 prefetch_noise: bool = True, return_warped: bool = False, micro_batches_per_step: int = 1):
+        """return_warped: also copy the (B,5,256,256,3) warped planes back to the host (63 of 75 MB per 64 crops).  The
+        reference never reads the planes on the host for their own sake -- they feed get_icn_inputs
+        (trajectory_inference.py:175-182), which runs on the device here -- so the default keeps them in HBM
+        (`device_outputs(ticket)["warped"]`).
+        micro_batches_per_step: a step of the data-parallel job is M consecutive submits (BASELINE config 4: 512 crops per
+        rank = 8 micro-batches of 64); the completed crops of a step are collected in one device buffer and `gather_fn`
+        runs ONCE per step on it, on its own stream, overlapping the next step's kernels."""
         _lib.require_cuda()
         self.model = model
         self.dev = next(model.parameters()).device
@@ -55,6 +63,12 @@ class NovelViewPipeline:
         self.gather_fn = gather_fn        # optional device-side collective on the completed crops (parallel.gather_crops)
         self.use_graph = use_graph        # the collective (if any) is issued eagerly after the graph replay
         self.prefetch_noise = prefetch_noise
+        self.return_warped = return_warped
+        self.mps = max(1, int(micro_batches_per_step))
+        self.step_bufs = None             # two (M*B,256,256,3) u8 device buffers: the step being filled / being gathered
+        self.comm_stream = torch.cuda.Stream(self.dev)
+        self.gather_done = [None, None]   # event per step buffer: its all-gather has finished reading it
+        self.crops_all = None             # the last all-gathered step, on the device (global crop order)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.out_stream = torch.cuda.Stream(self.dev)
         self.side_stream = torch.cuda.Stream(self.dev)
@@ -112,6 +126,7 @@ class NovelViewPipeline:
             with torch.cuda.graph(slot.graph, stream=slot.stream):
                 slot.dev_out = self._compute(slot.inp)
         slot.launches = _lib.kernel_launches() - n0
+        slot.wkey = eng._wkey
         eng.noise_provider = prev
 
     def _draw_noise(self, slot: _Slot, generator=None):
@@ -166,7 +181,12 @@ class NovelViewPipeline:
         resident=True skips the host copies (inputs / noise already in the slot; outputs stay on the device)."""
         ticket = self.n
         slot = self.slots[ticket % self.depth]
-        fresh = slot.inp is None or any(tuple(slot.inp[k].shape) != tuple(v.shape) for k, v in batch.items())
+        eng = self.model.engine()
+        eng.prepare_weights()                 # no-op unless the parameters changed (load_state_dict, .to, in-place update)
+        # a captured graph bakes in the device pointers of the folded weights: re-capture after a reload instead of
+        # replaying over freed memory
+        fresh = slot.inp is None or slot.wkey != eng._wkey or set(slot.inp) != set(batch) or \
+            any(tuple(slot.inp[k].shape) != tuple(v.shape) for k, v in batch.items())
         if not resident and not fresh:
             self._take_noise(slot)                                    # host RNG work overlaps the batches still in flight
         if slot.done is not None:
@@ -178,7 +198,6 @@ class NovelViewPipeline:
             self._prepare_slot(slot, batch)
             if not resident:
                 self._take_noise(slot)
-        eng = self.model.engine()
         if not resident:
             with torch.cuda.stream(self.copy_stream):
                 for k, v in batch.items():
@@ -198,14 +217,14 @@ class NovelViewPipeline:
                 slot.dev_out = self._compute(slot.inp)
                 eng.noise_provider = prev
             dev_out = dict(slot.dev_out)
-            gathered = None
             if self.gather_fn is not None:
                 # the exchange step: every rank gets all completed crops ON THE DEVICE (for a device-side paste-back,
                 # frame_ops.paste_back_batch); the host copy below stays this rank's own shard
-                gathered = self.gather_fn(dev_out["crops"])
-                slot.crops_all = gathered
+                self._collect_and_gather(slot, dev_out["crops"], ticket)
             computed = torch.cuda.Event()
             computed.record(slot.stream)
+        if not self.return_warped:
+            dev_out.pop("warped", None)
         if resident:
             slot.done = computed
             self.n += 1
@@ -225,9 +244,50 @@ class NovelViewPipeline:
             self._start_prefetch(nxt)                                 # the next step's noise, off the submit path
         return ticket
 
+    def _collect_and_gather(self, slot: _Slot, crops, ticket: int):
+        """Runs on slot.stream.  Micro-batch `ticket % M` of the current step lands in the step buffer; the last one of
+        a step triggers the all-gather of the whole step on comm_stream."""
+        M, B = self.mps, crops.shape[0]
+        if self.step_bufs is None or self.step_bufs[0].shape[0] != M * B:
+            self.step_bufs = [torch.empty((M * B,) + tuple(crops.shape[1:]), dtype=crops.dtype, device=self.dev) for _ in range(2)]
+            self.gather_done = [None, None]
+        step, mb = divmod(ticket, M)
+        which = step % 2
+        buf = self.step_bufs[which]
+        if self.gather_done[which] is not None:
+            slot.stream.wait_event(self.gather_done[which])          # the gather that last read this buffer (two steps ago) is done
+        if M == 1:
+            src = crops
+        else:
+            buf[mb * B:(mb + 1) * B].copy_(crops, non_blocking=True)
+            src = buf
+        if mb == M - 1:
+            filled = torch.cuda.Event()
+            filled.record(slot.stream)
+            if M > 1:
+                # other micro-batches of this step may have run on other slot streams
+                for other in self.slots:
+                    if other is not slot and other.stream is not slot.stream and other.done is not None:
+                        self.comm_stream.wait_stream(other.stream)
+            self.comm_stream.wait_event(filled)
+            with torch.cuda.stream(self.comm_stream):
+                self.crops_all = self.gather_fn(src)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+            src.record_stream(self.comm_stream)
+            self.gather_done[which] = done
+            slot.crops_all = self.crops_all
+
+    def wait_gather(self):
+        """Blocks until the last issued all-gather has completed; returns the gathered crops (device)."""
+        for ev in self.gather_done:
+            if ev is not None:
+                ev.synchronize()
+        return self.crops_all
+
     def result(self, ticket: int) -> dict:
-        """Host (pinned) outputs of a submitted batch: `crops` (B,256,256,3) u8 completed views,
-        `warped` (B,5,256,256,3) u8 planes, `plane_j`, `vis`.  Valid until `depth` more batches are submitted."""
+        """Host (pinned) outputs of a submitted batch: `crops` (B,256,256,3) u8 completed views, `plane_j`, `vis`
+        (+ `warped` (B,5,256,256,3) u8 planes with return_warped=True).  Valid until `depth` more batches are submitted."""
         slot = self.slots[ticket % self.depth]
         slot.done.synchronize()
         pj = slot.out.get("plane_j")

@@ -10,6 +10,28 @@
  * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless its name
  * ends in _host; `stream` is a cudaStream_t passed as void*; calls are asynchronous on that
  * stream, never allocate, never synchronise; the return value is 0 or a negative FUSG_ERR_*.
+ *
+ * Devices and threads: a call works on the CURRENT device of the calling thread (cudaSetDevice), whose
+ * memory the pointers must belong to; `stream` must be a stream of that device.  One process may drive
+ * several devices, and several host threads may call concurrently: kernel attributes and SM counts are
+ * cached per device under a mutex, nothing else is shared.  fusg_last_error / fusg_kernel_launches are
+ * process-wide diagnostics.
+ *
+ * Faults: device-side mbarrier waits are bounded (~4 s); a TMA-descriptor or pipeline bug aborts the
+ * kernel with a device assertion (the next call returns FUSG_ERR_CUDA, fusg_last_error names it) instead
+ * of hanging the GPU.
+ *
+ * Environment switches (read once per process; DEBUG / A-B measurement only, never needed for correctness,
+ * every setting gives results within the same tolerances):
+ *   FUSG_MSUB1=1            conv: 128-row CTA tiles only (no 256-row tiles)
+ *   FUSG_NO_HALO=1          conv: no sliding-window A tiles for wide 3x3/5x5/7x7 layers
+ *   FUSG_HALO_NMAX=<n>      conv: widest N tile that may use the sliding window (default 128)
+ *   FUSG_HALO_KEEP_STAGED=1 conv: keep the staged epilogue instead of a third pipeline stage on 5x5/7x7
+ *   FUSG_NO_PAIR2=1         conv: no cta_group::2 CTA pairs
+ *   FUSG_KSPLIT_MAX=<n>     conv: largest split-K cluster (default 8); FUSG_KSPLIT_MIN_KB=<n> smallest K (in
+ *                           k-blocks) that is split (default 36)
+ *   FUSG_EPI_DIRECT=1       conv: no warp-staged epilogue
+ *   FUSG_NO_PDL=1           conv: no programmatic dependent launch
  */
 #ifndef FUSG_H_
 #define FUSG_H_
@@ -202,6 +224,11 @@ int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
 size_t fusg_sizeof_conv_desc(void);
 /* Which kernel FUSG_IMPL_AUTO resolves to for this descriptor (FUSG_IMPL_TCGEN05 or FUSG_IMPL_DIRECT). */
 int fusg_conv2d_select(const fusg_conv_desc *desc);
+/* Diagnostics: the tiling plan of the calling thread's last tcgen05 launch --
+ * plan8 = {msub (128-row sub-tiles per CTA tile), pair (cta_group::2), halo (sliding-window A tiles), ksplit (split-K
+ * cluster size), stages, group (k-blocks per barrier round trip), w_resident, fast_epi}.  Tests use it to assert that
+ * a case really exercises the variant it is named after. */
+void fusg_conv2d_last_plan(int32_t *plan8_host);
 
 /* weight_norm fold (vunet/layers.py:29-31): w = g * v / ||v||, repacked from [cout][cin][k][k]
  * fp32 to [cout_pad][k*k][cin_pad] in `dtype` (zero padded).  Run once per load_state_dict. */

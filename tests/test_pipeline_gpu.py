@@ -21,7 +21,7 @@ def test_pipeline_matches_eager_and_oracle(cuda):
     m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True))
     m.load_state_dict(sd, strict=True)
     m = m.cuda().eval()
-    pipe = NovelViewPipeline(m, depth=2)
+    pipe = NovelViewPipeline(m, depth=2, return_warped=True)
     batches = []
     for s in range(4):
         wb = synth.make_warp_batch(10 * s, B)
@@ -62,6 +62,57 @@ def test_pipeline_matches_eager_and_oracle(cuda):
     w0 = WO.warp_fused(host["src"][0].numpy(), host["src_kp"][0].numpy(), host["dst_kp"][0].numpy(), host["K"][0].numpy(),
                        host["E_src"][0].numpy(), host["E_dst"][0].numpy(), host["kp3d"][0].numpy())[0]
     assert np.array_equal(outs[0]["warped"][0].numpy(), w0)
+
+
+def test_warped_planes_stay_on_device_by_default(cuda):
+    """Default outputs on the host: completed crops + flags; the planes stay in HBM (device_outputs) for get_icn_inputs."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from future_urban_scene_generation_b200.warp_learn import warp_batch
+    B = 2
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True)).cuda().eval()
+    wb = synth.make_warp_batch(3, B)
+    mk, ns, nd = synth.make_vunet_inputs_u8(3, B)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
+    host.update(x_mask_u8=torch.from_numpy(mk).pin_memory(), x_normal_u8=torch.from_numpy(ns).pin_memory(), y_normal_u8=torch.from_numpy(nd).pin_memory())
+    pipe = NovelViewPipeline(m, depth=2)
+    t = pipe.submit(host)
+    out = pipe.result(t)
+    assert set(out) == {"crops", "plane_j", "vis"}
+    res = warp_batch(host["src"], host["src_kp"], host["dst_kp"], host["K"], host["E_src"], host["E_dst"], host["kp3d"])
+    assert torch.equal(pipe.device_outputs(t)["warped"], res.warped)
+
+
+def test_reloading_weights_after_capture_recaptures_the_graph(cuda):
+    """A captured graph bakes in the pointers of the folded weights; load_state_dict after the first submit must lead to
+    a re-capture (outputs of the NEW weights), not a replay over freed memory."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from future_urban_scene_generation_b200.warp_learn.planes_utils import to_image_batch
+    from oracle import vunet_oracle as VO
+    B = 2
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True))
+    m.load_state_dict(VO.make_state_dict(0), strict=True)
+    m = m.cuda().eval()
+    wb = synth.make_warp_batch(5, B)
+    xs, ys = synth.make_vunet_inputs(5, B)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
+    host["x"], host["y"] = torch.from_numpy(xs).pin_memory(), torch.from_numpy(ys).pin_memory()
+    pipe = NovelViewPipeline(m, depth=2)
+    torch.manual_seed(3)
+    first = [pipe.result(pipe.submit(host))["crops"].clone() for _ in range(3)]
+    m.load_state_dict(VO.make_state_dict(1), strict=True)             # second checkpoint, same module
+    torch.manual_seed(3)
+    second = [pipe.result(pipe.submit(host))["crops"].clone() for _ in range(3)]
+    torch.manual_seed(3)
+    eager = [to_image_batch(m(host["y"].cuda(), host["x"].cuda())[0]).cpu() for _ in range(3)]
+    for a, b, c in zip(first, second, eager):
+        assert torch.equal(b, c)
+        assert not torch.equal(a, b)
 
 
 def test_noise_prefetch_keeps_generator_semantics(cuda):
@@ -161,3 +212,79 @@ def test_icn_generator_non_power_of_two_frames_use_the_direct_kernel(cuda):
         want = IO.forward(sd, x)
     got = g(x.cuda())
     assert got.shape == want.shape and (got.cpu() - want).abs().max().item() <= 1e-2
+
+
+def test_bench_step_parity_b64(cuda):
+    """Exactly bench.py's step (BASELINE config 2: 64 crops, uint8 inputs, graph replay): completed crops against the
+    fp32 torch oracle of the VUNet forward with the same CPU noise (bar: 1e-2 on [-1,1] = 1.3 grey levels -> <= 2 after
+    the truncating uint8 conversion), warped planes / flags bit-exact against the C oracle of the warp half."""
+    torch = cuda
+    from future_urban_scene_generation_b200 import synth
+    from future_urban_scene_generation_b200.pipeline import NovelViewPipeline
+    from future_urban_scene_generation_b200.vunet.models import Vunet_fix_res
+    from future_urban_scene_generation_b200.warp_learn.planes_utils import to_image
+    from oracle import vunet_oracle as VO, warp_oracle as WO
+    B = 64
+    sd = VO.make_state_dict(0)
+    m = Vunet_fix_res(Namespace(up_mode='subpixel', w_norm=True, drop_prob=0.2, vunet_256=True))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    wb = synth.make_warp_batch(0, B)
+    xs, ys = synth.make_vunet_inputs(0, B)
+    mk, ns, nd = synth.make_vunet_inputs_u8(0, B)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in wb.items()}
+    host.update(x_mask_u8=torch.from_numpy(mk).pin_memory(), x_normal_u8=torch.from_numpy(ns).pin_memory(), y_normal_u8=torch.from_numpy(nd).pin_memory())
+    pipe = NovelViewPipeline(m, depth=2, return_warped=True)
+    pipe.result(pipe.submit(host))                       # eager pass + capture
+    pipe.result(pipe.submit(host))
+    torch.manual_seed(21)
+    out = {k: v.clone() for k, v in pipe.result(pipe.submit(host)).items()}       # a graph REPLAY, like the bench's timed steps
+    torch.manual_seed(21)
+    with torch.no_grad():
+        ref = VO.forward(sd, torch.from_numpy(ys), torch.from_numpy(xs))[0]
+    ref_u8 = np.stack([to_image(ref[i], from_LAB=False) for i in range(B)])
+    diff = np.abs(out["crops"].numpy().astype(int) - ref_u8.astype(int))
+    assert diff.max() <= 2, diff.max()
+    assert (diff > 1).mean() < 1e-3
+    for i in range(B):
+        w, vis, pj, _ = WO.warp_fused(wb["src"][i], wb["src_kp"][i], wb["dst_kp"][i], wb["K"][i], wb["E_src"][i], wb["E_dst"][i], wb["kp3d"][i])
+        assert np.array_equal(out["warped"][i].numpy(), w), i
+        assert np.array_equal(out["plane_j"][i].numpy(), pj) and np.array_equal(out["vis"][i].numpy(), vis[:2])
+
+
+def _nccl_worker(rank, world, port, n_total, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from future_urban_scene_generation_b200.parallel import shard_range, gather_crops
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = torch.Generator().manual_seed(5)
+        full = torch.randint(0, 256, (n_total, 64, 64, 3), dtype=torch.uint8, generator=g)
+        b, e = shard_range(n_total, rank, world)
+        out = gather_crops(full[b:e].cuda(), n_total)
+        torch.cuda.synchronize()
+        q.put((rank, bool(torch.equal(out.cpu(), full))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_gather_crops_nccl_world_2(cuda, n_total):
+    """gather_crops over NCCL on two GPUs: global crop order, even and ragged shards.  Skips on a one-GPU box."""
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + n_total
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    got = sorted(q.get(timeout=10) for _ in range(2))
+    assert got == [(0, True), (1, True)]

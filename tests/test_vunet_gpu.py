@@ -144,12 +144,29 @@ CONV_CASES = [
     ("final_3ch", 1, (32,), 3, 3, 1, 64, False, False, 0),
     ("big_tile_256", 1, (128,), 128, 3, 1, 256, True, False, 0),
     ("msub2_wide", 4, (128,), 128, 3, 1, 256, True, False, 0),        # enough tiles for 256-row CTA tiles
-    ("msub2_down", 8, (128,), 128, 3, 2, 256, False, False, 0),
+    ("msub2_down", 10, (128,), 128, 3, 2, 256, False, False, 0),     # 640 256-row tiles >= 4 x 148: stride 2 WITH msub = 2
+    ("msub2_down_64", 40, (128,), 128, 3, 2, 128, False, False, 0),  # the 128^2 -> 64^2 down-sampler at bench-like tile counts
+    ("pair_w256", 3, (128,), 128, 3, 1, 256, True, False, 0),        # cta_group::2 pairs, two tile columns
+    ("pair_w128", 10, (128,), 128, 3, 1, 128, True, False, 0),       # cta_group::2 pairs on a one-tile-column frame (W = N = 128)
     ("msub2_cat32", 4, (32, 32), 32, 3, 1, 256, True, False, 0),
     ("halo_cat64", 4, (64, 64), 64, 3, 1, 256, True, False, 0),       # sliding-window A tiles, streamed weights
     ("halo_res64", 4, (64,), 64, 3, 1, 256, True, False, 0),          # sliding-window A tiles, resident weights
     ("halo_w128", 16, (64,), 64, 3, 1, 128, True, False, 0),          # one tile column (image row == sub-tile)
 ]
+
+
+# the kernel variant a case is named after must really be the one that ran (fusg_conv2d_last_plan)
+EXPECTED_PLAN = {
+    "msub2_wide": {"msub": 2, "halo": 1, "pair": 1},
+    "msub2_down": {"msub": 2, "halo": 0, "pair": 0},
+    "msub2_down_64": {"msub": 2, "halo": 0},
+    "pair_w256": {"msub": 2, "pair": 1},
+    "pair_w128": {"msub": 2, "pair": 1},
+    "halo_cat64": {"halo": 1},
+    "halo_res64": {"halo": 1, "w_resident": 1},
+    "halo_w128": {"halo": 1},
+    "ar_res_1024": {"msub": 1},
+}
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
@@ -185,6 +202,11 @@ def test_conv_kernels(cuda, case):
     scale = max(1.0, y_b.abs().max().item())
     for impl in (2, 1):
         ob = _run_conv(torch, xs, w, bias, stride, impl, "bf16", res, noise, mode, blk, want)
+        if impl == 1 and name in EXPECTED_PLAN:
+            from future_urban_scene_generation_b200 import _lib
+            plan = _lib.conv_last_plan()
+            for key, val in EXPECTED_PLAN[name].items():
+                assert plan[key] == val, (name, plan)
         err = (ob["rawf32"].double() - y_b).abs().max().item()
         assert err < 2e-3 * scale, (name, impl, "f32 out", err)      # only fp32 accumulation order differs
         if "raw" in ob:
