@@ -40,6 +40,7 @@ def _load():
         "fusg_conv2d": ([vp, vp], i),
         "fusg_conv2d_select": ([vp], i),
         "fusg_conv2d_last_plan": ([vp], None),
+        "fusg_conv2d_set_sm_reserve": ([i], i),
         "fusg_sizeof_conv_desc": ([], sz),
         "fusg_fold_weightnorm": ([vp, vp, vp, i, i, i, i, i, i, vp], i),
         "fusg_fold_weightnorm_paired": ([vp, vp, vp, vp, vp, i, i, i, i, i, i, vp], i),

@@ -240,9 +240,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
 }
+// the barriers of a CTA live in one 1024-byte aligned block: [full | empty | tfull[2] | tempty[2] | w_bar | tmem_slot[6]];
+// tmem_slot[4] doubles as the CTA's wait-failure counter
+constexpr unsigned TC_WAIT_COUNTER_OFF = 312;        // (2 * TC_MAX_STAGES + 5) * 8 + 16, checked below
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
-    unsigned long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -251,7 +253,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done) fusg_spin_guard(t0);
+        if (!done) fusg_wait_failed<100000u>((s_addr(bar) & ~1023u) + TC_WAIT_COUNTER_OFF);
     }
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -349,7 +351,6 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {
 // wait on a barrier of this CTA that a PEER CTA arrives on (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
-    unsigned long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -358,7 +359,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
             : "=r"(done)
             : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done) fusg_spin_guard(t0);
+        if (!done) fusg_wait_failed<100000u>((s_addr(bar) & ~1023u) + TC_WAIT_COUNTER_OFF);
     }
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
@@ -515,6 +516,7 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_HALO_ROWS_MAX = TC_BLOCK_M + 6;                   // pixels of one halo A buffer: 128 + ksize - 1, ksize <= 7
 constexpr int TC_HALO_BYTES = ((TC_HALO_ROWS_MAX * 128 + 1023) / 1024) * 1024;   // 128-byte rows (kc = 64), 1024-aligned
 constexpr int TC_MAX_STAGES = 16;
+static_assert(TC_WAIT_COUNTER_OFF == (2 * TC_MAX_STAGES + 5) * 8 + 16, "wait-failure counter must sit in tmem_slot[4]");
 
 struct alignas(64) ConvTcParams {
     CUtensorMap tmA0, tmA1, tmW;
@@ -714,6 +716,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
         mbar_init(w_bar, 1);
+        tmem_slot[4] = 0;                      // wait-failure counter (fusg_wait_failed), at bars + TC_WAIT_COUNTER_OFF
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1257,6 +1260,15 @@ static bool tc_supported(const fusg_conv_desc &d, int Ho, int Wo) {
     return get_encode() != nullptr;
 }
 
+// SMs the persistent conv grids leave free for kernels of other streams (fusg_conv2d_set_sm_reserve)
+static int g_sm_reserve = getenv("FUSG_SM_RESERVE") ? atoi(getenv("FUSG_SM_RESERVE")) : 0;
+
+extern "C" int fusg_conv2d_set_sm_reserve(int n) {
+    const int prev = g_sm_reserve;
+    if (n >= 0) g_sm_reserve = n;
+    return prev;
+}
+
 // tiling plan of this host thread's last tcgen05 launch (fusg_conv2d_last_plan)
 static thread_local int32_t g_last_plan[8];
 
@@ -1445,7 +1457,11 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
     static const int pdl_on = getenv("FUSG_NO_PDL") ? 0 : 1;
     p.pdl = pdl_on;
-    int grid = p.ksplit > 1 ? total_tiles * p.ksplit /* one cluster per tile */ : (total_tiles < num_sms ? total_tiles : num_sms);
+    // persistent CTAs own a STATIC share of the tiles, and one CTA fills an SM: if a co-tenant (the solver warps of the warp
+    // stage that runs next to the VUNet in a pipeline step) holds even one SM, the CTA meant for it starts only when another
+    // CTA has finished its whole share -- the layer takes twice as long.  g_sm_reserve SMs are therefore left to co-tenants.
+    const int usable = num_sms - g_sm_reserve > 8 ? num_sms - g_sm_reserve : num_sms;
+    int grid = p.ksplit > 1 ? total_tiles * p.ksplit /* one cluster per tile */ : (total_tiles < usable ? total_tiles : usable);
     if (p.pair) grid &= ~1;                                                  // whole CTA pairs
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

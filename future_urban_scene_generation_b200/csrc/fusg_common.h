@@ -17,16 +17,18 @@ int fusg_num_sms();                            // multiprocessor count of the cu
 // A slot that carries a size (dynamic shared memory limit) is re-run when `size` exceeds what was set before.
 #include <functional>
 cudaError_t fusg_once_per_device(int slot, size_t size, const std::function<cudaError_t()> &fn);
-
 #ifdef __CUDACC__
-// Bounded spin for mbarrier waits: a wait that has not completed after ~4 s of wall time (a descriptor / pipeline bug --
-// healthy waits take microseconds) aborts the kernel with a device-side assertion instead of hanging the GPU; the
-// next library call then returns FUSG_ERR_CUDA and fusg_last_error() names cudaErrorAssert.
-extern "C" __device__ void __assertfail(const char *message, const char *file, unsigned line, const char *function, size_t charSize);
-__device__ __forceinline__ void fusg_spin_guard(unsigned long long &t0) {
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000ull) __assertfail("fusg: mbarrier wait timed out (TMA descriptor / pipeline bug)", __FILE__, __LINE__, "mbar_wait", 1);
+// Bounded mbarrier waits without a live register in the hot kernels (k_conv_tc sits exactly at its register cap) and without
+// static shared memory (it also sits at the shared-memory cap): every try_wait that comes back empty-handed -- with the
+// 10 ms suspend hint the tensor-core kernels use, or after ~1 us of polling in the gather kernel -- bumps one CTA-wide
+// 32-bit counter whose shared-memory address the caller derives from the barrier's own address; a healthy pipeline never
+// comes near the limit, a TMA-descriptor / pipeline bug reaches it within seconds and makes the kernel trap instead of
+// hanging the GPU (the next library call returns FUSG_ERR_CUDA and fusg_last_error() names the launch failure).
+// Kernels zero the counter before their first wait.
+template <unsigned LIMIT>
+__device__ __forceinline__ void fusg_wait_failed(unsigned counter_smem_addr) {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(counter_smem_addr) : "memory");
+    if (old > LIMIT) __trap();      // (a trap, not an assert: no call, hence no ABI stack frame in the hot kernels)
 }
 #endif

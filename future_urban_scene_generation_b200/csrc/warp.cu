@@ -24,6 +24,7 @@
 #include "../../include/fusg.h"
 #include "fusg_common.h"
 #include "warp_geom.cuh"
+#include "warp_solver.cuh"
 
 namespace fusg {
 
@@ -141,74 +142,15 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
 }
 
 // ============================================================================================
-// k_homography: one warp per (crop, source plane)
+// Homographies: k_plane_gate applies the gating / symmetry remap of planes_utils.py:57-68 and appends the
+// surviving (crop, plane) tasks to a 6-point list (left / right, LM-refined: ~10 Jacobi runs) or a 4-point
+// list (one Jacobi run); skipped planes get their outputs written there.  k_solve then runs the thread-per-
+// point-set solver of warp_solver.cuh over the lists, `lanes` tasks per warp (1 for small batches: the
+// latency of one solve; 32 for large ones: throughput), 6-point and 4-point tasks in separate warps so that the
+// lanes of a warp run jobs of the same length.  Outputs are indexed by task id, so the (non-deterministic)
+// list order does not affect results.
 // workspace layout per crop: Minv[5][9] f64 (inverse maps indexed by SOURCE plane i)
 // ============================================================================================
-constexpr int HG_WARPS = 4;
-
-__global__ void __launch_bounds__(HG_WARPS * 32) k_homography(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
-                                                             const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j,
-                                                             double *__restrict__ H12, double *__restrict__ Minv, int B, int H, int W) {
-    __shared__ HomogScratch scratch[HG_WARPS];
-    __shared__ int pts[HG_WARPS][24];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * HG_WARPS + warp;
-    if (t >= B * N_TEX) return;
-    const int b = t / N_TEX, i = t % N_TEX;
-    const uint8_t *sv = vis + 2 * N_VIS * b, *dv = sv + N_VIS;
-    const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
-    bool bad = sv[0] == 0xff || dv[0] == 0xff;            // refused by k_visibility
-    if (lane < N_KP) {
-        const bool oob = abs(sk[2 * lane]) > POLY_COORD_MAX || abs(sk[2 * lane + 1]) > POLY_COORD_MAX ||
-                         abs(dk[2 * lane]) > POLY_COORD_MAX || abs(dk[2 * lane + 1]) > POLY_COORD_MAX;
-        bad = bad || oob;
-    }
-    bad = __any_sync(0xffffffffu, bad);
-    double Hm[9], Mi[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
-    int j;
-    if (bad) {
-        j = -2;
-    } else {
-        j = plane_target(i, sv, dv);
-        if (j >= 0) {
-            const int n = c_plane_n[i];
-            if (lane < n) {
-                pts[warp][2 * lane] = sk[2 * c_plane_kp[i][lane]];
-                pts[warp][2 * lane + 1] = sk[2 * c_plane_kp[i][lane] + 1];
-                pts[warp][12 + 2 * lane] = dk[2 * c_plane_kp[j][lane]];
-                pts[warp][12 + 2 * lane + 1] = dk[2 * c_plane_kp[j][lane] + 1];
-            }
-            __syncwarp();
-            // H21 is only ever used through its "is None" test, which is the same degeneracy
-            // test as H12's (symmetric in src/dst) -- planes_utils.py:72-74
-            if (!find_homography_warp(scratch[warp], lane, pts[warp], pts[warp] + 12, n, Hm)) {
-                j = -1;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) Hm[k] = 0;
-            } else {
-                invert3(Hm, Mi);
-            }
-        }
-    }
-    if (lane == 0) {
-        plane_j[t] = (int8_t)j;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
-        if (H12) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
-        }
-    }
-}
-
-
-// Large batches: solves are fed from COMPACTED task lists so that no warp is spent on a skipped plane:
-// k_plane_gate applies the gating / remap of planes_utils.py:57-68 and appends the
-// surviving (crop, plane) tasks to a 6-point list (left/right, LM-refined) or a 4-point list; skipped
-// planes get their outputs written there.  Outputs are indexed by task id, so the (non-deterministic)
-// list order does not affect results.
 __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
                                                     const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j, double *__restrict__ H12,
                                                     double *__restrict__ Minv, int *__restrict__ counters, int *__restrict__ list6,
@@ -232,64 +174,78 @@ __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ 
     }
 }
 
-// One warp per surviving task, 6-point (LM-refined, ~10x longer) tasks first.
-__global__ void __launch_bounds__(HG_WARPS * 32) k_homography_list(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
-                                                                  int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
-                                                                  const int *__restrict__ counters, const int *__restrict__ list6,
-                                                                  const int *__restrict__ list4) {
-    __shared__ HomogScratch scratch[HG_WARPS];
-    __shared__ int pts[HG_WARPS][24];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c6 = counters[0], c4 = counters[1];
-    const int idx = blockIdx.x * HG_WARPS + warp;
-    if (idx >= c6 + c4) return;
-    const int t = idx < c6 ? list6[idx] : list4[idx - c6];
-    const int b = t / N_TEX, i = t % N_TEX, j = plane_j[t];
-    const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
-    const int n = c_plane_n[i];
-    if (lane < n) {
-        pts[warp][2 * lane] = sk[2 * c_plane_kp[i][lane]];
-        pts[warp][2 * lane + 1] = sk[2 * c_plane_kp[i][lane] + 1];
-        pts[warp][12 + 2 * lane] = dk[2 * c_plane_kp[j][lane]];
-        pts[warp][12 + 2 * lane + 1] = dk[2 * c_plane_kp[j][lane] + 1];
-    }
-    __syncwarp();
-    double Hm[9], Mi[9];
-    // H21 is only ever used through its "is None" test, the same (symmetric) degeneracy test as H12's
-    const bool good = find_homography_warp(scratch[warp], lane, pts[warp], pts[warp] + 12, n, Hm);
-    if (!good) {
+// grid = blocks6 + blocks4 one-warp blocks; block b < blocks6 serves 6-point tasks [b*lanes, (b+1)*lanes)
+__global__ void __launch_bounds__(32) k_solve(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
+                                              int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
+                                              const int *__restrict__ counters, const int *__restrict__ list6,
+                                              const int *__restrict__ list4, int blocks6, int lanes) {
+    extern __shared__ double solver_smem[];
+    const int lane = threadIdx.x;
+    const bool six = (int)blockIdx.x < blocks6;
+    const int blk = six ? blockIdx.x : blockIdx.x - blocks6;
+    const int count = six ? counters[0] : counters[1];
+    if (blk * lanes >= count) return;                       // whole warp without work
+    const int idx = blk * lanes + lane;
+    const bool has = lane < lanes && idx < count;
+    PointSet ps;
+    ps.count = 0;
+    int t = 0;
+    if (has) {
+        t = six ? list6[idx] : list4[idx];
+        const int b = t / N_TEX, i = t % N_TEX, j = plane_j[t];
+        const int32_t *sk = src_kp + 2 * N_KP * b, *dk = dst_kp + 2 * N_KP * b;
+        ps.count = c_plane_n[i];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
-    } else {
-        invert3(Hm, Mi);
-    }
-    if (lane == 0) {
-        if (!good) plane_j[t] = -1;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
-        if (H12) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) H12[9 * t + k] = Hm[k];
+        for (int k = 0; k < 6; ++k) {
+            if (k < ps.count) {
+                ps.Mx[k] = (float)sk[2 * c_plane_kp[i][k]]; ps.My[k] = (float)sk[2 * c_plane_kp[i][k] + 1];
+                ps.mx[k] = (float)dk[2 * c_plane_kp[j][k]]; ps.my[k] = (float)dk[2 * c_plane_kp[j][k] + 1];
+            }
         }
+    }
+    double Hm[9], Mi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hm[k] = Mi[k] = 0;
+    // H21 is only ever used through its "is None" test, the same (symmetric) degeneracy test as H12's -- planes_utils.py:72-74
+    const bool good = sv_find_homography(LaneMem{solver_smem + lane}, ps, Hm);
+    if (!has) return;
+    if (good) invert3(Hm, Mi);
+    else plane_j[t] = -1;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Minv[9 * t + k] = Mi[k];
+    if (H12) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H12[9 * t + k] = good ? Hm[k] : 0.0;
     }
 }
 
-__global__ void __launch_bounds__(HG_WARPS * 32) k_find_homography(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
-                                                                  double *__restrict__ H, uint8_t *__restrict__ ok, int N) {
-    __shared__ HomogScratch scratch[HG_WARPS];
-    __shared__ int pts[HG_WARPS][24];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * HG_WARPS + warp;
-    if (t >= N) return;
-    if (lane < 2 * n) { pts[warp][lane] = src[2 * n * t + lane]; pts[warp][12 + lane] = dst[2 * n * t + lane]; }
-    __syncwarp();
-    double Hm[9];
-    const bool good = find_homography_warp(scratch[warp], lane, pts[warp], pts[warp] + 12, n, Hm);
-    if (lane == 0) {
+// cv2.findHomography drop-in on N explicit point sets of n points each
+__global__ void __launch_bounds__(32) k_find_homography(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
+                                                        double *__restrict__ H, uint8_t *__restrict__ ok, int N, int lanes) {
+    extern __shared__ double solver_smem[];
+    const int lane = threadIdx.x;
+    const int t = blockIdx.x * lanes + lane;
+    const bool has = lane < lanes && t < N;
+    PointSet ps;
+    ps.count = 0;
+    if (has) {
+        ps.count = n;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) H[9 * t + k] = good ? Hm[k] : 0.0;
-        ok[t] = good ? 1 : 0;
+        for (int k = 0; k < 6; ++k) {
+            if (k < n) {
+                ps.Mx[k] = (float)src[(t * n + k) * 2]; ps.My[k] = (float)src[(t * n + k) * 2 + 1];
+                ps.mx[k] = (float)dst[(t * n + k) * 2]; ps.my[k] = (float)dst[(t * n + k) * 2 + 1];
+            }
+        }
     }
+    double Hm[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hm[k] = 0;
+    const bool good = sv_find_homography(LaneMem{solver_smem + lane}, ps, Hm);
+    if (!has) return;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[9 * t + k] = good ? Hm[k] : 0.0;
+    ok[t] = good ? 1 : 0;
 }
 
 // ============================================================================================
@@ -322,15 +278,17 @@ __host__ __device__ inline int warp_block_w(int H, int W) {
     return bw0 < W ? bw0 : W;
 }
 
+// `src` / `mask` may be row WINDOWS: they are addressed with absolute row numbers (the caller passes pointers already
+// offset by -ylo rows) and only rows ylo..yhi exist; a tap outside them is a tap outside the plane's polygon, i.e. zero.
 template <bool MASKED, typename SrcPtr>
-__device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask, int mask_words, int H, int W, int X, int Y) {
+__device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask, int mask_words, int ylo, int yhi, int W, int X, int Y) {
     int sx = X >> 5, sy = Y >> 5;
     const int a = X & 31, b = Y & 31;
     sx = max(-32768, min(32767, sx));
     sy = max(-32768, min(32767, sy));
     const int w00 = (32 - a) * (32 - b) * 32, w01 = a * (32 - b) * 32, w10 = (32 - a) * b * 32, w11 = a * b * 32;
     const bool xin0 = (unsigned)sx < (unsigned)W, xin1 = (unsigned)(sx + 1) < (unsigned)W;
-    const bool yin0 = (unsigned)sy < (unsigned)H, yin1 = (unsigned)(sy + 1) < (unsigned)H;
+    const bool yin0 = sy >= ylo && sy <= yhi, yin1 = sy + 1 >= ylo && sy + 1 <= yhi;
     bool t00 = xin0 && yin0, t01 = xin1 && yin0, t10 = xin0 && yin1, t11 = xin1 && yin1;
     if (MASKED) {
         if (t00) t00 = (mask[sy * mask_words + (sx >> 5)] >> (sx & 31)) & 1u;
@@ -347,20 +305,43 @@ __device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask
 }
 
 // ============================================================================================
-// k_warp: one CTA (512 threads) per crop
+// The gather stage for crops up to 256 x 256.
+//
+// 97 % of the 5 output planes of a crop is zero: a written plane is non-zero only inside the destination polygon, and
+// ~3 of the 5 planes have no writer at all.  So the bytes are written by the simplest possible kernel, k_zero_planes
+// (16-byte grid-stride stores over the whole output: 6.2 TB/s measured, the HBM write roofline), which depends on
+// nothing and is launched first.  k_warp_rows then only visits the rows of each written plane
+// whose active span is not empty: it stages just the source rows the crop's polygons cover (TMA bulk copy of one
+// contiguous row range into a WIN-row window of shared memory), builds the polygon bit masks of those rows, gathers
+// with cv2's 1/32-px fixed-point bilinear rule and overwrites the rows with 16-byte coalesced stores.
+// Crops whose polygons span more than WIN source rows are queued for a second launch with a full-height window.
 // ============================================================================================
-constexpr int WARP_THREADS = 512;
+constexpr int WARP_THREADS = 256;
 constexpr int WARP_NWARPS = WARP_THREADS / 32;
 constexpr int MAX_HW = 256;
 constexpr int ROW_BYTES_MAX = MAX_HW * 3;          // 768
 constexpr int MASK_WORDS = MAX_HW / 32;            // 8 words per row
+constexpr int WIN_SMALL = 128;                     // source rows of the common-case window (2 CTAs per SM)
+
+__global__ void __launch_bounds__(128) k_zero_planes(int4 *__restrict__ out, size_t n16, uint8_t *__restrict__ tail, int ntail) {
+    const int4 z4 = make_int4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) out[i] = z4;
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
 
 struct WarpSmemHeader {
     unsigned long long mbar;
+    unsigned wait_failures, pad0;                  // must directly follow mbar (mbar_wait)
     double Minv[N_TEX][9];
     int sel[N_TEX];                                // source plane feeding output plane j, or -1
     int polyx[6], polyy[6], polyn;
+    float fwdx[6], fwdy[6];                        // forward image of the source polygon under H12 (destination pixels)
+    int fwd_ok;                                    // 0: a vertex is on / behind the horizon of H12 -> bbox spans only
+    float fwd_pad;                                 // how far (destination px) a 2-px step in the source can move, worst vertex, with slack
     int bbox[4];                                   // xmin,xmax,ymin,ymax of the source polygon
+    int win_lo, win_hi;                            // source rows held in the window (absolute row numbers)
+    int skip;                                      // this crop does not fit the window: queued for the big-window launch
     short span_lo[MAX_HW], span_hi[MAX_HW];        // conservative active span per output row
 };
 
@@ -374,7 +355,6 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
     uint32_t done = 0;
-    unsigned long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -383,7 +363,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phas
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
-        if (!done) fusg_spin_guard(t0);
+        if (!done) fusg_wait_failed<400000000u>(smem_u32(bar) + 8);      // WarpSmemHeader::wait_failures follows mbar
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
@@ -422,134 +402,220 @@ __device__ __forceinline__ void row_active_span(const double *M, int y, int W, c
     xhi = min(W - 1, (int)ceil(h) + 1);
 }
 
-__global__ void __launch_bounds__(WARP_THREADS, 1)
-k_warp(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
-       const double *__restrict__ Minv, uint8_t *__restrict__ warped, int H, int W) {
+// Row span of the destination region: every non-zero pixel of warped[j] has a bilinear tap inside the source polygon, so it
+// has a source point within 2 px of that polygon (mask outline + tap footprint + 1/32-px rounding).  With P' the forward
+// image of the polygon under H12 and PAD the distance a 2-px source step can move in the destination (measured at the
+// vertices, where the projective magnification ~ 1/w^2 of a polygon peaks, times 1.5, plus 1), the pixel lies within PAD of
+// P'.  For output row y the span is the x-range of the parts of the boundary of P' (a closed polyline through
+// fwd[0..n-1]) inside the band [y - PAD, y + PAD], widened by PAD -- the boundary of a closed polygon crosses every row
+// that P' reaches, so the range between its extreme crossings covers the interior too.  fp32 is ample for a bound.
+__device__ __forceinline__ void row_polygon_span(const float *fx, const float *fy, int n, float PAD, int y, int W, int &xlo, int &xhi) {
+    const float y0 = (float)y - PAD, y1 = (float)y + PAD;
+    float lo = 1e30f, hi = -1e30f;
+    float ax = fx[n - 1], ay = fy[n - 1];
+    for (int k = 0; k < n; ++k) {
+        const float bx = fx[k], by = fy[k];
+        const float emin = fminf(ay, by), emax = fmaxf(ay, by);
+        if (emax >= y0 && emin <= y1) {
+            // clip the edge to the band and take the x-range of the clipped piece
+            float t0 = 0.f, t1 = 1.f;
+            const float dy = by - ay;
+            if (fabsf(dy) > 1e-6f) {
+                const float ta = (y0 - ay) / dy, tb = (y1 - ay) / dy;
+                t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+            }
+            if (t0 <= t1) {
+                const float xa = ax + (bx - ax) * t0, xb = ax + (bx - ax) * t1;
+                lo = fminf(lo, fminf(xa, xb)); hi = fmaxf(hi, fmaxf(xa, xb));
+            }
+        }
+        ax = bx; ay = by;
+    }
+    if (lo > hi) { xlo = 1; xhi = 0; return; }     // no boundary in the band: the row is outside P' (+ PAD)
+    xlo = max(0, (int)floorf(lo - PAD));
+    xhi = min(W - 1, (int)ceilf(hi + PAD));
+}
+
+// WIN = rows of the source window.  First launch: grid = B, crop = blockIdx.x, oversize crops appended to big_list.
+// Second launch (big_list != nullptr as INPUT, `from_list`): a fixed grid strides over the queued crops.
+template <int WIN>
+__global__ void __launch_bounds__(WARP_THREADS, WIN == WIN_SMALL ? 2 : 1)
+k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
+            const double *__restrict__ Minv, uint8_t *__restrict__ warped, int H, int W, int *__restrict__ big_count, int *__restrict__ big_list,
+            int from_list) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crop_bytes = H * W * 3;
     const int row_bytes = W * 3;
     // smem carve-up
-    uint8_t *s_src = smem;                                                    // crop_bytes (padded to 128)
-    const int src_pad = (crop_bytes + 127) & ~127;
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + src_pad);          // H * MASK_WORDS words
-    uint8_t *s_rows = reinterpret_cast<uint8_t *>(s_mask + MAX_HW * MASK_WORDS);  // WARP_NWARPS * 768
+    uint8_t *s_win = smem;                                                            // WIN * 768 bytes
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + WIN * ROW_BYTES_MAX);       // WIN * MASK_WORDS words
+    uint8_t *s_rows = reinterpret_cast<uint8_t *>(s_mask + WIN * MASK_WORDS);          // WARP_NWARPS * 768
     WarpSmemHeader *hd = reinterpret_cast<WarpSmemHeader *>(s_rows + WARP_NWARPS * ROW_BYTES_MAX);
-
-    const uint8_t *gsrc = src + (size_t)b * crop_bytes;
-    uint8_t *gout = warped + (size_t)b * N_TEX * crop_bytes;
-    const bool use_tma = (crop_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0);
-
     if (tid == 0) {
         mbar_init(&hd->mbar, 1);
+        hd->wait_failures = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < N_TEX) hd->sel[tid] = -1;
-    __syncthreads();
-    if (tid == 0) {
-        // last writer wins (planes_utils.py:79): ascending i
-        for (int i = 0; i < N_TEX; ++i) {
-            const int j = plane_j[b * N_TEX + i];
-            if (j >= 0) hd->sel[j] = i;
-        }
-        if (use_tma) {
-            mbar_expect_tx(&hd->mbar, (uint32_t)crop_bytes);
-            const int CH = 32768;
-            for (int off = 0; off < crop_bytes; off += CH)
-                bulk_g2s(s_src + off, gsrc + off, (uint32_t)min(CH, crop_bytes - off), &hd->mbar);
-        }
-    }
-    if (tid >= 32 && tid < 32 + N_TEX * 9) hd->Minv[0][tid - 32] = Minv[(size_t)b * N_TEX * 9 + (tid - 32)];
-    if (!use_tma) {
-        for (int i = tid; i < crop_bytes; i += WARP_THREADS) s_src[i] = gsrc[i];
-    }
-    __syncthreads();
-
-    // ---- pass 1: planes nobody writes -> zeros (no source needed; overlaps the TMA load)
-    const int4 z4 = make_int4(0, 0, 0, 0);
-    for (int j = 0; j < N_TEX; ++j) {
-        if (hd->sel[j] >= 0) continue;
-        uint8_t *o = gout + (size_t)j * crop_bytes;
-        if ((crop_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            int4 *o4 = reinterpret_cast<int4 *>(o);
-            for (int i = tid; i < crop_bytes / 16; i += WARP_THREADS) o4[i] = z4;
-        } else {
-            for (int i = tid; i < crop_bytes; i += WARP_THREADS) o[i] = 0;
-        }
-    }
-    if (use_tma) mbar_wait(&hd->mbar, 0);
-
-    // ---- pass 2: written planes
-    const int bw = warp_block_w(H, W);
-    const bool vec_rows = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
-    uint8_t *my_row = s_rows + warp * ROW_BYTES_MAX;
-    for (int j = 0; j < N_TEX; ++j) {
-        const int i = hd->sel[j];
-        if (i < 0) continue;
-        __syncthreads();                                  // previous plane done with mask / spans
+    uint32_t phase = 0;
+    const int n_items = from_list ? *big_count : (int)gridDim.x;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = from_list ? big_list[item] : item;
+        const uint8_t *gsrc = src + (size_t)b * crop_bytes;
+        uint8_t *gout = warped + (size_t)b * N_TEX * crop_bytes;
+        __syncthreads();                                      // previous item done with the header / window
+        if (tid < N_TEX) hd->sel[tid] = -1;
+        __syncthreads();
         if (tid == 0) {
-            const int n = c_plane_n[i];
-            int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
-            for (int k = 0; k < n; ++k) {
-                const int vx = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2], vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
-                hd->polyx[k] = vx; hd->polyy[k] = vy;
-                x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
+            // last writer wins (planes_utils.py:79): ascending i
+            for (int i = 0; i < N_TEX; ++i) {
+                const int j = plane_j[b * N_TEX + i];
+                if (j >= 0) hd->sel[j] = i;
             }
-            hd->polyn = n;
-            hd->bbox[0] = x0; hd->bbox[1] = x1; hd->bbox[2] = y0; hd->bbox[3] = y1;
-        }
-        __syncthreads();
-        const double *M = hd->Minv[i];
-        // polygon bit mask of source plane i + active span of every output row
-        for (int y = tid; y < H; y += WARP_THREADS) {
-            int px[6], py[6], lo[MAX_RANGES], hi[MAX_RANGES];
-            const int n = hd->polyn;
-            for (int k = 0; k < n; ++k) { px[k] = hd->polyx[k]; py[k] = hd->polyy[k]; }
-            const int rc = poly_row_ranges(px, py, n, y, H, W, lo, hi);
-            for (int w = 0; w < MASK_WORDS; ++w) s_mask[y * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
-            int xlo, xhi;
-            row_active_span(M, y, W, hd->bbox, xlo, xhi);
-            hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
-        }
-        __syncthreads();
-        uint8_t *oplane = gout + (size_t)j * crop_bytes;
-        for (int y = warp; y < H; y += WARP_NWARPS) {
-            const int xlo = hd->span_lo[y], xhi = hd->span_hi[y];
-            uint8_t *orow = oplane + (size_t)y * row_bytes;
-            if (xlo > xhi) {                               // whole row is zero
-                if (vec_rows) { int4 *o4 = reinterpret_cast<int4 *>(orow); for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = z4; }
-                else for (int k = lane; k < row_bytes; k += 32) orow[k] = 0;
-                continue;
-            }
-            // zero the staging row, then fill the active 32-pixel groups
-            for (int k = lane; k < (row_bytes + 15) / 16; k += 32) reinterpret_cast<int4 *>(my_row)[k] = z4;
-            __syncwarp();
-            for (int g = xlo >> 5; g <= (xhi >> 5); ++g) {
-                const int x = g * 32 + lane;
-                if (x < W) {
-                    const int bx = (x / bw) * bw;
-                    const RowBase rb = row_base(M, bx, y);
-                    int X, Y;
-                    src_coord(M, rb, x - bx, X, Y);
-                    const uchar3 v = bilinear_tap4<true>(s_src, s_mask, MASK_WORDS, H, W, X, Y);
-                    my_row[3 * x] = v.x; my_row[3 * x + 1] = v.y; my_row[3 * x + 2] = v.z;
+            // source rows the selected polygons cover (only there can a mask bit be set)
+            int lo = INT_MAX, hi = INT_MIN;
+            for (int j = 0; j < N_TEX; ++j) {
+                const int i = hd->sel[j];
+                if (i < 0) continue;
+                for (int k = 0; k < c_plane_n[i]; ++k) {
+                    const int vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
+                    lo = min(lo, vy); hi = max(hi, vy);
                 }
             }
-            __syncwarp();
-            if (vec_rows) {
-                int4 *o4 = reinterpret_cast<int4 *>(orow);
-                for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = reinterpret_cast<const int4 *>(my_row)[k];
-            } else {
-                for (int k = lane; k < row_bytes; k += 32) orow[k] = my_row[k];
+            lo = max(lo, 0); hi = min(hi, H - 1);
+            hd->win_lo = lo; hd->win_hi = hi;
+            hd->skip = 0;
+            if (lo <= hi && hi - lo + 1 > WIN) {
+                hd->skip = 1;
+                big_list[atomicAdd(big_count, 1)] = b;        // (only reachable with WIN == WIN_SMALL: the big window holds any crop)
             }
-            __syncwarp();
         }
+        if (tid >= 32 && tid < 32 + N_TEX * 9) hd->Minv[0][tid - 32] = Minv[(size_t)b * N_TEX * 9 + (tid - 32)];
+        __syncthreads();
+        const int win_lo = hd->win_lo, win_hi = hd->win_hi;
+        if (hd->skip || win_lo > win_hi) continue;            // nothing to warp: the planes stay zero
+        const int win_rows = win_hi - win_lo + 1;
+        const uint8_t *gwin = gsrc + (size_t)win_lo * row_bytes;
+        const uint32_t win_bytes = (uint32_t)win_rows * row_bytes;
+        const bool use_tma = (win_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gwin) & 15) == 0);
+        if (use_tma) {
+            if (tid == 0) {
+                mbar_expect_tx(&hd->mbar, win_bytes);
+                const uint32_t CH = 32768;
+                for (uint32_t off = 0; off < win_bytes; off += CH) bulk_g2s(s_win + off, gwin + off, min(CH, win_bytes - off), &hd->mbar);
+            }
+        } else {
+            for (uint32_t i = tid; i < win_bytes; i += WARP_THREADS) s_win[i] = gwin[i];
+        }
+        const uint8_t *s_src = s_win - (size_t)win_lo * row_bytes;                    // absolute-row addressing
+        const uint32_t *mask_abs = s_mask - (size_t)win_lo * MASK_WORDS;
+        const int bw = warp_block_w(H, W);
+        const bool vec_rows = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+        uint8_t *my_row = s_rows + warp * ROW_BYTES_MAX;
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        bool src_ready = !use_tma;
+        for (int j = 0; j < N_TEX; ++j) {
+            const int i = hd->sel[j];
+            if (i < 0) continue;
+            __syncthreads();                                  // previous plane done with mask / spans
+            if (tid == 0) {
+                const int n = c_plane_n[i];
+                int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+                for (int k = 0; k < n; ++k) {
+                    const int vx = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2], vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
+                    hd->polyx[k] = vx; hd->polyy[k] = vy;
+                    x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
+                }
+                hd->polyn = n;
+                hd->bbox[0] = x0; hd->bbox[1] = x1; hd->bbox[2] = y0; hd->bbox[3] = y1;
+                // A polygon that leaves the frame is rasterised with cv2's clipped-edge rules, whose mask can set pixels well
+                // away from the ideal polygon (e.g. a run along the border column): only in-frame polygons get the tight spans.
+                const bool inframe = x0 >= 0 && x1 < W && y0 >= 0 && y1 < H;
+                // forward image of the vertices: H12 = inverse of the stored inverse map (any accuracy better than a pixel will do)
+                double Hf[9];
+                invert3(hd->Minv[i], Hf);
+                int ok = 1;
+                double reach = 0;
+                for (int k = 0; k < n; ++k) {
+                    const double vx = hd->polyx[k], vy = hd->polyy[k];
+                    const double wv = Hf[6] * vx + Hf[7] * vy + Hf[8];
+                    const double px = (Hf[0] * vx + Hf[1] * vy + Hf[2]) / wv, py = (Hf[3] * vx + Hf[4] * vy + Hf[5]) / wv;
+                    if (!(fabs(px) < 1e6) || !(fabs(py) < 1e6)) ok = 0;
+                    hd->fwdx[k] = (float)px; hd->fwdy[k] = (float)py;
+                    for (int d = 0; d < 4; ++d) {              // where does a 2-px step away from the vertex land?
+                        const double ux = vx + (d == 0 ? 2. : d == 1 ? -2. : 0.), uy = vy + (d == 2 ? 2. : d == 3 ? -2. : 0.);
+                        const double wu = Hf[6] * ux + Hf[7] * uy + Hf[8];
+                        if (!(wu * wv > 0)) { ok = 0; continue; }
+                        const double qx = (Hf[0] * ux + Hf[1] * uy + Hf[2]) / wu, qy = (Hf[3] * ux + Hf[4] * uy + Hf[5]) / wu;
+                        reach = fmax(reach, fmax(fabs(qx - px), fabs(qy - py)));
+                    }
+                }
+                if (!(reach < 64.) || !inframe) ok = 0;        // absurd magnification / clipped polygon: keep the bbox spans
+                hd->fwd_pad = (float)(1.5 * 1.4143 * reach + 1.0);   // diagonal source steps, then slack
+                // the sign of the projective denominator must not change over the polygon (no horizon through it)
+                const double w0 = Hf[6] * hd->polyx[0] + Hf[7] * hd->polyy[0] + Hf[8];
+                for (int k = 1; k < n; ++k) {
+                    const double wk = Hf[6] * hd->polyx[k] + Hf[7] * hd->polyy[k] + Hf[8];
+                    if (!(wk * w0 > 0)) ok = 0;
+                }
+                hd->fwd_ok = ok;
+            }
+            __syncthreads();
+            const double *M = hd->Minv[i];
+            const int pl_lo = max(hd->bbox[2], 0), pl_hi = min(hd->bbox[3], H - 1);   // rows of THIS plane's polygon (inside the window)
+            // polygon bit mask of the plane's source rows + active span of every output row
+            for (int y = pl_lo + tid; y <= pl_hi; y += WARP_THREADS) {
+                int px[6], py[6], lo[MAX_RANGES], hi[MAX_RANGES];
+                const int n = hd->polyn;
+                for (int k = 0; k < n; ++k) { px[k] = hd->polyx[k]; py[k] = hd->polyy[k]; }
+                const int rc = poly_row_ranges(px, py, n, y, H, W, lo, hi);
+#pragma unroll
+                for (int w = 0; w < MASK_WORDS; ++w) s_mask[(y - win_lo) * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
+            }
+            for (int y = tid; y < H; y += WARP_THREADS) {
+                int xlo, xhi;
+                row_active_span(M, y, W, hd->bbox, xlo, xhi);
+                if (hd->fwd_ok && xlo <= xhi) {
+                    int plo, phi;
+                    row_polygon_span(hd->fwdx, hd->fwdy, hd->polyn, hd->fwd_pad, y, W, plo, phi);
+                    xlo = max(xlo, plo); xhi = min(xhi, phi);
+                }
+                hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
+            }
+            if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; src_ready = true; }
+            __syncthreads();
+            uint8_t *oplane = gout + (size_t)j * crop_bytes;
+            for (int y = warp; y < H; y += WARP_NWARPS) {
+                const int xlo = hd->span_lo[y], xhi = hd->span_hi[y];
+                if (xlo > xhi) continue;                       // the row stays zero (k_zero_planes)
+                uint8_t *orow = oplane + (size_t)y * row_bytes;
+                // zero the staging row, then fill the active 32-pixel groups
+                for (int k = lane; k < (row_bytes + 15) / 16; k += 32) reinterpret_cast<int4 *>(my_row)[k] = z4;
+                __syncwarp();
+                for (int g = xlo >> 5; g <= (xhi >> 5); ++g) {
+                    const int x = g * 32 + lane;
+                    if (x < W) {
+                        const int bx = (x / bw) * bw;
+                        const RowBase rb = row_base(M, bx, y);
+                        int X, Y;
+                        src_coord(M, rb, x - bx, X, Y);
+                        const uchar3 v = bilinear_tap4<true>(s_src, mask_abs, MASK_WORDS, pl_lo, pl_hi, W, X, Y);
+                        my_row[3 * x] = v.x; my_row[3 * x + 1] = v.y; my_row[3 * x + 2] = v.z;
+                    }
+                }
+                __syncwarp();
+                if (vec_rows) {
+                    int4 *o4 = reinterpret_cast<int4 *>(orow);
+                    for (int k = lane; k < row_bytes / 16; k += 32) o4[k] = reinterpret_cast<const int4 *>(my_row)[k];
+                } else {
+                    for (int k = lane; k < row_bytes; k += 32) orow[k] = my_row[k];
+                }
+                __syncwarp();
+            }
+        }
+        if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; }          // never leave a bulk copy in flight into the window
     }
 }
-
-// refused crops (plane_j == -2, vertex magnitude beyond POLY_COORD_MAX): k_warp already zero-filled them
-// because no plane has a writer; the Python host raises on them (warp_learn/batch.py).
 
 // ============================================================================================
 // Stand-alone kernels for the per-function drop-ins
@@ -595,7 +661,7 @@ __global__ void __launch_bounds__(256) k_warp_perspective(const uint8_t *__restr
     int X, Y;
     src_coord(M, rb, x - bx, X, Y);
     const uint8_t *s = img + (size_t)n * H * W * 3;
-    const uchar3 v = bilinear_tap4<false>(s, nullptr, 0, H, W, X, Y);
+    const uchar3 v = bilinear_tap4<false>(s, nullptr, 0, 0, H - 1, W, X, Y);
     uint8_t *o = out + (((size_t)n * H + y) * W + x) * 3;
     o[0] = v.x; o[1] = v.y; o[2] = v.z;
 }
@@ -686,7 +752,7 @@ __global__ void __launch_bounds__(32 * WF_ROWS) k_warp_frame(const uint8_t *__re
             const RowBase rb = row_base(M, bx, y);
             int X, Y;
             src_coord(M, rb, x - bx, X, Y);
-            v = bilinear_tap4<true>(simg, mk, words, H, W, X, Y);
+            v = bilinear_tap4<true>(simg, mk, words, 0, H - 1, W, X, Y);
         }
         s_row[3 * x] = v.x; s_row[3 * x + 1] = v.y; s_row[3 * x + 2] = v.z;
     }
@@ -707,14 +773,28 @@ __global__ void __launch_bounds__(32 * WF_ROWS) k_warp_frame(const uint8_t *__re
 // ================================================================================================
 using namespace fusg;
 
-static size_t warp_smem_bytes(int H, int W) {
-    const int crop_bytes = H * W * 3;
-    const int src_pad = (crop_bytes + 127) & ~127;
-    return (size_t)src_pad + (size_t)MAX_HW * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + sizeof(WarpSmemHeader) + 128;
+// dynamic shared memory opt-in of the solver kernels (per device) and the number of point sets per warp
+static int solver_prepare() {
+    const cudaError_t e = fusg_once_per_device(3, 0, [] {
+        cudaError_t r = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_SMEM_BYTES);
+        return r != cudaSuccess ? r : cudaFuncSetAttribute(k_find_homography, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_SMEM_BYTES);
+    });
+    return fusg_record_cuda(e);
+}
+// one point set per warp while the warps fit on the device at once (latency of a single solve), up to 32 (throughput)
+static int solver_lanes(long long tasks) {
+    const long long slots = (long long)fusg_num_sms() * 3;         // 3 x 72 KB of scratch per SM
+    long long l = (tasks + slots - 1) / slots;
+    return (int)(l < 1 ? 1 : (l > 32 ? 32 : l));
 }
 
-// workspace: Minv [B,5,9] f64 | counters [4] i32 | list6 [2B] i32 | list4 [3B] i32 | (frames > 256: plane bit masks [B,5,H,ceil(W/32)] u32)
-static size_t warp_ws_base(int B) { return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 5 * (size_t)B) * sizeof(int); }
+static size_t warp_smem_bytes(int win) {
+    return (size_t)win * ROW_BYTES_MAX + (size_t)win * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + sizeof(WarpSmemHeader) + 128;
+}
+
+// workspace: Minv [B,5,9] f64 | counters [4] i32 (6-point tasks, 4-point tasks, big-window crops, -) | list6 [2B] i32 | list4 [3B] i32 |
+//            big_list [B] i32 | (frames > 256: plane bit masks [B,5,H,ceil(W/32)] u32)
+static size_t warp_ws_base(int B) { return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 6 * (size_t)B) * sizeof(int); }
 
 extern "C" size_t fusg_warp_workspace_bytes(int B) { return B <= 0 ? 0 : warp_ws_base(B); }
 
@@ -747,7 +827,9 @@ extern "C" int fusg_find_homography(const int32_t *src, const int32_t *dst, int 
     if (!src || !dst || !Hm || !ok || N <= 0) return FUSG_ERR_ARG;
     if (n < 4 || n > 6) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    k_find_homography<<<(N + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src, dst, n, Hm, ok, N);
+    if (solver_prepare() != FUSG_OK) return FUSG_ERR_CUDA;
+    const int lanes = solver_lanes(N);
+    k_find_homography<<<(N + lanes - 1) / lanes, 32, SOLVER_SMEM_BYTES, st>>>(src, dst, n, Hm, ok, N, lanes);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
@@ -772,23 +854,48 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     if (workspace_bytes < fusg_warp_workspace_bytes_hw(B, H, W)) return FUSG_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     double *Minv = reinterpret_cast<double *>(workspace);
-    const size_t smem = H <= MAX_HW && W <= MAX_HW ? warp_smem_bytes(H, W) : 0;
-    if (fusg_once_per_device(1, 0, [] { return cudaFuncSetAttribute(k_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW, MAX_HW)); }) != cudaSuccess)
-        return fusg_check_launch();
-    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, kp3d_dst, vis, nullptr, nullptr, 2 * B, H, W);
-    // small batches: latency matters -> one warp per solve; large batches: throughput -> one thread per solve
-    if (B * N_TEX <= 8192) k_homography<<<(B * N_TEX + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, B, H, W);
-    else {
-        int *counters = reinterpret_cast<int *>(Minv + (size_t)B * N_TEX * 9);
-        int *list6 = counters + 4, *list4 = list6 + 2 * (size_t)B;
-        if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
-        k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
-        k_homography_list<<<(N_TEX * B + HG_WARPS - 1) / HG_WARPS, HG_WARPS * 32, 0, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4);
+    int *counters = reinterpret_cast<int *>(Minv + (size_t)B * N_TEX * 9);
+    int *list6 = counters + 4, *list4 = list6 + 2 * (size_t)B, *big_list = list4 + 3 * (size_t)B;
+    if (!frame_path) {
+        if (fusg_once_per_device(1, 0, [] {
+                cudaError_t e = cudaFuncSetAttribute(k_warp_rows<WIN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(WIN_SMALL));
+                return e != cudaSuccess ? e : cudaFuncSetAttribute(k_warp_rows<MAX_HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW));
+            }) != cudaSuccess)
+            return fusg_check_launch();
+        // The zero fill runs on the caller's stream, ahead of the geometry kernels.  (Forking it onto a helper stream so that it
+        // overlaps visibility / gating / solves was measured SLOWER at every grid size -- 14.4 vs 12.3 ms for 16k crops,
+        // profiles/r2_summary.md: the co-running kernels slow each other down by more than the overlap gains.)
+        const size_t total = (size_t)B * N_TEX * H * W * 3;
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(warped) & 15)) & 15;       // (torch allocations are 512-byte aligned: 0)
+        if (head == 0) {
+            const size_t n16 = total / 16;
+            const size_t want = (n16 + 127) / 128;
+            const int zgrid = (int)(want < (size_t)fusg_num_sms() * 16 ? want : (size_t)fusg_num_sms() * 16);
+            k_zero_planes<<<zgrid, 128, 0, st>>>(reinterpret_cast<int4 *>(warped), n16, warped + n16 * 16, (int)(total - n16 * 16));
+        } else if (fusg_record_cuda(cudaMemsetAsync(warped, 0, total, st)) != FUSG_OK) {
+            return FUSG_ERR_CUDA;
+        }
         fusg_count_launch(1);
     }
-    if (!frame_path) {
-        k_warp<<<B, WARP_THREADS, smem, st>>>(src, src_kp, plane_j, Minv, warped, H, W);
+    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, kp3d_dst, vis, nullptr, nullptr, 2 * B, H, W);
+    {
+        if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
+        k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
+        if (solver_prepare() != FUSG_OK) return FUSG_ERR_CUDA;
+        // 32 point sets per warp whatever the batch: the lanes of a warp run in lock step, so a fuller warp costs no
+        // latency, and the fewest possible SMs lose 72 KB of shared memory to a solver warp (the VUNet convolutions of the
+        // same step want all of it); the grid covers the worst case, warps beyond the task count exit at once
+        const int lanes = 32;
+        const int blocks6 = (2 * B + lanes - 1) / lanes, blocks4 = (3 * B + lanes - 1) / lanes;
+        k_solve<<<blocks6 + blocks4, 32, SOLVER_SMEM_BYTES, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4, blocks6, lanes);
         fusg_count_launch(3);
+    }
+    if (!frame_path) {
+        k_warp_rows<WIN_SMALL><<<B, WARP_THREADS, warp_smem_bytes(WIN_SMALL), st>>>(src, src_kp, plane_j, Minv, warped, H, W, counters + 2, big_list, 0);
+        // crops whose polygons span more than WIN_SMALL source rows (a vehicle filling the crop): full-height window
+        const int bgrid = B < fusg_num_sms() ? B : fusg_num_sms();
+        k_warp_rows<MAX_HW><<<bgrid, WARP_THREADS, warp_smem_bytes(MAX_HW), st>>>(src, src_kp, plane_j, Minv, warped, H, W, counters + 2, big_list, 1);
+        fusg_count_launch(2);
     } else {
         const int words = (W + 31) / 32;
         uint32_t *masks = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(workspace) + ((warp_ws_base(B) + 15) & ~(size_t)15));

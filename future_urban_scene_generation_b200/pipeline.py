@@ -79,7 +79,18 @@ class NovelViewPipeline:
         self.n = 0
 
     # ------------------------------------------------------------------ one step of device work
+    #: SMs the persistent conv grids leave to the warp stage's solver warps while both run in one step (a persistent CTA
+    #: that cannot be placed doubles its layer's time; measured 8.50 -> 8.15 ms per 64-crop step, profiles/r2_summary.md)
+    SM_RESERVE = 4
+
     def _compute(self, inp):
+        prev = _lib.lib().fusg_conv2d_set_sm_reserve(self.SM_RESERVE)      # baked into the captured launches' grids
+        try:
+            return self._compute_inner(inp)
+        finally:
+            _lib.lib().fusg_conv2d_set_sm_reserve(prev)
+
+    def _compute_inner(self, inp):
         # the planar warp is a chain of small latency-bound kernels (visibility -> homographies -> gather) that does
         # not feed the VUNet of the same batch: fork it onto a side stream so it fills the SMs the narrow VUNet
         # layers leave idle, and join before the outputs are read (inside a graph this becomes a parallel branch)

@@ -17,8 +17,8 @@
  * cached per device under a mutex, nothing else is shared.  fusg_last_error / fusg_kernel_launches are
  * process-wide diagnostics.
  *
- * Faults: device-side mbarrier waits are bounded (~4 s); a TMA-descriptor or pipeline bug aborts the
- * kernel with a device assertion (the next call returns FUSG_ERR_CUDA, fusg_last_error names it) instead
+ * Faults: device-side mbarrier waits are bounded (seconds); a TMA-descriptor or pipeline bug makes the
+ * kernel trap (the next call returns FUSG_ERR_CUDA, fusg_last_error names the launch failure) instead
  * of hanging the GPU.
  *
  * Environment switches (read once per process; DEBUG / A-B measurement only, never needed for correctness,
@@ -229,6 +229,10 @@ int fusg_conv2d_select(const fusg_conv_desc *desc);
  * cluster size), stages, group (k-blocks per barrier round trip), w_resident, fast_epi}.  Tests use it to assert that
  * a case really exercises the variant it is named after. */
 void fusg_conv2d_last_plan(int32_t *plan8_host);
+/* Persistent conv grids use (SM count - n) CTAs from now on (process-wide; returns the previous value; n < 0 only queries).
+ * A pipeline that runs another kernel family next to the convolutions (NovelViewPipeline: the homography solver of the
+ * warp stage) reserves a few SMs for it: a persistent CTA that cannot be placed doubles its layer's time.  Default 0. */
+int fusg_conv2d_set_sm_reserve(int n);
 
 /* weight_norm fold (vunet/layers.py:29-31): w = g * v / ||v||, repacked from [cout][cin][k][k]
  * fp32 to [cout_pad][k*k][cin_pad] in `dtype` (zero padded).  Run once per load_state_dict. */

@@ -29,6 +29,8 @@ def run():
     warp_batch(dev["src"], dev["src_kp"], dev["dst_kp"], dev["K"], dev["E_src"], dev["E_dst"], dev["kp3d"], out=out)
 
 
+stream = torch.cuda.Stream() if os.environ.get("BENCH_WARP_STREAM") else torch.cuda.current_stream()
+torch.cuda.set_stream(stream)
 for _ in range(3):
     run()
 torch.cuda.synchronize()
