@@ -60,6 +60,8 @@ def _load():
         "fusg_mask_bbox": ([vp] * 4 + [i, i, vp], i),
         "fusg_pack_icn_inputs": ([vp] * 8 + [i, vp, vp, i, i, i, i, vp], i),
         "fusg_pack_vunet_inputs": ([vp] * 10 + [i, i, i, i, vp], i),
+        "fusg_render_workspace_bytes": ([i, i, i, i], sz),
+        "fusg_render_normals": ([vp] * 4 + [i, i] + [vp] * 6 + [vp, sz, i, i, i, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

@@ -245,3 +245,41 @@ def make_icn_pack_case(idx: int, frame_hw=(360, 640), res: int = 256):
         planes[p][band] = tex[band]
     central = rng.integers(0, 256, (res, res, 3), dtype=np.uint8)
     return planes, normal, veh, central
+
+
+def make_car_mesh(cad_id: int = 0, n_lon: int = 64, n_lat: int = 24):
+    """A closed synthetic "CAD" mesh for the normal-sketch renderer (no Pascal3D PLYs offline): a superellipsoid body the
+    size of the box-car the keypoints of `cad_keypoints` sit on (x = left/right, y = back/front, z = up), with a raised
+    cabin; per-id jitter like the keypoints.  Returns (vertices (Nv,3) f64, triangles (Nt,3) i32), outward oriented."""
+    rng = np.random.default_rng(10_000 + cad_id)
+    sx, sy, sz = 0.9 * (1 + rng.uniform(-0.05, 0.05)), 2.5 * (1 + rng.uniform(-0.05, 0.05)), 0.75 * (1 + rng.uniform(-0.05, 0.05))
+    lat = np.linspace(-np.pi / 2, np.pi / 2, n_lat + 1)[1:-1]
+    lon = np.linspace(0, 2 * np.pi, n_lon, endpoint=False)
+
+    def spow(t, e):
+        return np.sign(t) * np.abs(t) ** e
+    verts = [np.array([0.0, 0.0, -sz])]
+    for la in lat:
+        for lo in lon:
+            x = sx * spow(np.cos(la), 0.5) * spow(np.cos(lo), 0.5)
+            y = sy * spow(np.cos(la), 0.5) * spow(np.sin(lo), 0.5)
+            z = sz * spow(np.sin(la), 0.6)
+            if z > 0.3 * sz and abs(y) < 0.45 * sy:          # cabin
+                z = z + 0.55 * sz * np.cos(y / (0.45 * sy) * np.pi / 2) ** 0.5
+            verts.append(np.array([x, y, z]))
+    verts.append(np.array([0.0, 0.0, sz + 0.55 * sz]))
+    V = np.stack(verts)
+    V[:, 2] += sz + 0.05                                      # wheels-on-ground: z >= 0
+    tris = []
+    R = len(lat)
+    for k in range(n_lon):
+        k1 = (k + 1) % n_lon
+        tris.append((0, 1 + k1, 1 + k))
+        for r in range(R - 1):
+            a, b = 1 + r * n_lon + k, 1 + r * n_lon + k1
+            c, d = a + n_lon, b + n_lon
+            tris.append((a, b, d))
+            tris.append((a, d, c))
+        top = 1 + (R - 1) * n_lon
+        tris.append((len(V) - 1, top + k, top + k1))
+    return V, np.asarray(tris, np.int32)

@@ -344,6 +344,28 @@ int fusg_norm_apply(const void *x, const float *ss, const void *residual, int rb
 /* NHWC elementwise ELU (activation dtype) over n elements. */
 int fusg_elu(const void *in, void *out, size_t n, int dtype, void *stream);
 
+/* ====================================================================================== */
+/* Normal-sketch renderer                                          */
+/* ====================================================================================== */
+
+/* Replaces warp_learn/render_open3d.py:29-50 `get_rendered(model_ply, w, h, extrinsic, intrinsic)` (Open3D's OpenGL
+ * visualiser: vertex colours (vertex_normal + 1) / 2, lighting off, black background) for B items of ONE mesh, each with
+ * its own camera and -- as the trajectory loop does, trajectory_inference.py:363 `orig_vertices @ z_rot(theta) + tr` --
+ * its own rigid move.
+ *   verts [Nv,3] f64, tris [Nt,3] i32;
+ *   adj_off [Nv+1], adj_tri [3*Nt] i32: CSR vertex -> incident triangles in ascending triangle order (host, once per mesh);
+ *   rot [B,9] f64 row-major (v @ rot) or NULL, tr [B,3] f64 or NULL (tr needs rot);
+ *   E [B,12] f64 world->camera 3x4, K [B,9] f64 (fx, fy are read; the principal point is the window centre
+ *   (W/2 - 0.5, H/2 - 0.5) like Open3D's view control keeps it, render_open3d.py:19-22);
+ *   normals [B,H,W,3] u8 RGB, mask [B,H,W] u8 (1 = background, the reference's `object_mask`);
+ *   workspace >= fusg_render_workspace_bytes(B, Nv, H, W).
+ * Rasterisation rules (top-left fill, z-buffer ties, perspective-correct interpolation, round(c * 255)) are those of
+ * oracle/render_oracle.py, which this entry point reproduces bit for bit. */
+size_t fusg_render_workspace_bytes(int B, int Nv, int H, int W);
+int fusg_render_normals(const double *verts, const int32_t *tris, const int32_t *adj_off, const int32_t *adj_tri, int Nv, int Nt,
+                        const double *rot, const double *tr, const double *E, const double *K, uint8_t *normals, uint8_t *mask,
+                        void *workspace, size_t workspace_bytes, int B, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

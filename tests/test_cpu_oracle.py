@@ -305,3 +305,42 @@ def test_frame_oracle_matches_cv2_goldens():
     for c in gold["pack"][:8]:
         x, y, bbox = FO.pack_vunet_inputs(frame, *synth.make_pack_case(c["idx"], (Hf, Wf)))
         assert bbox == c["bbox"] and sha(x) == c["sha1_x"] and sha(y) == c["sha1_y"], c["idx"]
+
+
+def test_render_oracle_properties():
+    """The software restatement of the Open3D normal sketch (oracle/render_oracle.py): area-weighted vertex normals equal a
+    direct per-triangle accumulation, the silhouette equals the union of the projected triangles, colours are the
+    camera-independent normal colours, and a mesh rendered from the opposite side shows the opposite normals."""
+    from oracle import render_oracle as RO
+    V, T = synth.make_car_mesh(0, n_lon=24, n_lat=10)
+    # vertex normals: unit length, outward on this convex-ish body
+    n = RO.vertex_normals(V, T)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0)
+    assert (np.sum(n * (V - V.mean(0)), 1) > 0).mean() > 0.95
+    acc = np.zeros_like(V)
+    tn = np.cross(V[T[:, 1]] - V[T[:, 0]], V[T[:, 2]] - V[T[:, 0]])
+    for t in range(len(T)):
+        acc[T[t]] += tn[t]
+    assert np.allclose(n, acc / np.linalg.norm(acc, axis=1, keepdims=True), atol=1e-12)
+    off, ids = RO.vertex_adjacency(T, len(V))
+    assert off[-1] == 3 * len(T) and all(v in T[t] for v in (0, 5, len(V) - 1) for t in ids[off[v]:off[v + 1]])
+    p = synth.make_pose_pair(3, 128, 128)
+    img, mask, tri = RO.render_normals(V, T, p["E_src"], p["K"], 128, 128, return_ids=True)
+    assert np.array_equal(mask, np.all(img == 0, axis=-1)) and (~mask).sum() > 300
+    # silhouette == union of filled projected triangles (cv2 polygons, up to the 1-px outline cv2 adds)
+    u, v, z = RO.project_vertices(V, p["E_src"], p["K"], 128, 128)
+    sil = np.zeros((128, 128), np.uint8)
+    for t in T:
+        cv2.fillPoly(sil, [np.round(np.stack([u[t], v[t]], 1)).astype(np.int32)], 1)
+    assert not ((~mask) & (sil == 0)).any()
+    assert ((sil == 1) & mask).sum() < 0.2 * (sil == 1).sum()
+    # visible surface faces the camera: decoded normal . (camera centre - point) > 0 for nearly all covered pixels
+    cam = -p["E_src"][:3, :3].T @ p["E_src"][:3, 3]
+    dec = img[~mask].astype(np.float64) / 255 * 2 - 1
+    view = cam / np.linalg.norm(cam)
+    assert (dec @ view > -0.15).mean() > 0.97
+    # a rigid move of the mesh by the identity changes nothing; moving it out of view clears the frame
+    img2, mask2 = RO.render_normals(V, T, p["E_src"], p["K"], 128, 128, rot=np.eye(3), tr=np.zeros(3))
+    assert np.array_equal(img, img2)
+    img3, mask3 = RO.render_normals(V, T, p["E_src"], p["K"], 128, 128, rot=np.eye(3), tr=np.array([500.0, 0, 0]))
+    assert mask3.all()
