@@ -241,7 +241,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
 }
 // the barriers of a CTA live in one 1024-byte aligned block: [full | empty | tfull[2] | tempty[2] | w_bar | tmem_slot[6]];
-// tmem_slot[4] doubles as the CTA's wait-failure counter
+// tmem_slot[4] holds the kernel's start time for the bounded waits (fusg_wait_failed)
 constexpr unsigned TC_WAIT_COUNTER_OFF = 312;        // (2 * TC_MAX_STAGES + 5) * 8 + 16, checked below
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
@@ -253,7 +253,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done) fusg_wait_failed<100000u>((s_addr(bar) & ~1023u) + TC_WAIT_COUNTER_OFF);
+        if (!done) fusg_wait_failed((s_addr(bar) & ~1023u) + TC_WAIT_COUNTER_OFF);
     }
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -359,7 +359,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
             : "=r"(done)
             : "r"(s_addr(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done) fusg_wait_failed<100000u>((s_addr(bar) & ~1023u) + TC_WAIT_COUNTER_OFF);
+        if (!done) fusg_wait_failed((s_addr(bar) & ~1023u) + TC_WAIT_COUNTER_OFF);
     }
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
@@ -516,7 +516,7 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_HALO_ROWS_MAX = TC_BLOCK_M + 6;                   // pixels of one halo A buffer: 128 + ksize - 1, ksize <= 7
 constexpr int TC_HALO_BYTES = ((TC_HALO_ROWS_MAX * 128 + 1023) / 1024) * 1024;   // 128-byte rows (kc = 64), 1024-aligned
 constexpr int TC_MAX_STAGES = 16;
-static_assert(TC_WAIT_COUNTER_OFF == (2 * TC_MAX_STAGES + 5) * 8 + 16, "wait-failure counter must sit in tmem_slot[4]");
+static_assert(TC_WAIT_COUNTER_OFF == (2 * TC_MAX_STAGES + 5) * 8 + 16, "the wait guard's start-time slot must be tmem_slot[4]");
 
 struct alignas(64) ConvTcParams {
     CUtensorMap tmA0, tmA1, tmW;
@@ -693,16 +693,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (swizzle atoms)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // [stages][group] A k-blocks | B k-blocks ([stages][group] streamed, or [num_kblocks] resident) | barriers | bias
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + (p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes);
+    // barriers (first KB: mbar_wait finds the CTA's wait-failure counter from a barrier's address, so the block must sit on a
+    // 1024-byte boundary) | [stages][group] A k-blocks | B k-blocks ([stages][group] streamed, or [num_kblocks] resident) | bias
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *sA = smem + 1024;
+    uint8_t *sB = sA + (p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes);
     const size_t b_region = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes
                                          : (p.halo ? (size_t)p.stages * p.hks * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + b_region);
     uint64_t *full_bar = bars, *empty_bar = bars + TC_MAX_STAGES, *tfull_bar = bars + 2 * TC_MAX_STAGES, *tempty_bar = tfull_bar + 2;
     uint64_t *w_bar = tempty_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
-    float *s_bias = reinterpret_cast<float *>(tmem_slot + 6);        // cout_pad floats, 16-byte aligned (float4 reads)
+    float *s_bias = reinterpret_cast<float *>(sB + ((b_region + 15) & ~(size_t)15));        // cout_pad floats, 16-byte aligned (float4 reads)
     uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_bias + p.d.cout_pad);   // fast_epi == 2: 32 KB of per-warp staging blocks
     float *s_recv = reinterpret_cast<float *>(s_stage);                      // ksplit > 1: block_n x 128 fp32 receive buffer (no staging then)
 
@@ -716,7 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
         mbar_init(w_bar, 1);
-        tmem_slot[4] = 0;                      // wait-failure counter (fusg_wait_failed), at bars + TC_WAIT_COUNTER_OFF
+        fusg_wait_guard_start(tmem_slot + 4);      // kernel start time, at bars + TC_WAIT_COUNTER_OFF
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1446,7 +1447,7 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     const size_t pipe_a = p.halo ? (size_t)p.stages * 2 * TC_HALO_BYTES : (size_t)p.stages * p.group * p.a_bytes;
     const size_t pipe_b = p.w_resident ? (size_t)p.num_kblocks * p.b_bytes : (p.halo ? (size_t)p.stages * d.ksize * p.b_bytes : (size_t)p.stages * p.group * p.b_bytes);
     const size_t smem = pipe_a + pipe_b +
-                        1024 /*align slack*/ + 512 /*barriers*/ + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
+                        1024 /*align slack*/ + 1024 /*barriers, first KB*/ + 16 + (size_t)d.cout_pad * 4 /*bias*/ + (want_staged ? 32768 : 0) /*epilogue staging*/ + (p.ksplit > 1 ? (size_t)p.block_n * TC_BLOCK_M * 4 : 0) /*split-K receive buffer*/;
     if (fusg_once_per_device(0, 0, [] {
             cudaError_t e = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             return e != cudaSuccess ? e : cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -19,16 +19,22 @@ int fusg_num_sms();                            // multiprocessor count of the cu
 cudaError_t fusg_once_per_device(int slot, size_t size, const std::function<cudaError_t()> &fn);
 #ifdef __CUDACC__
 // Bounded mbarrier waits without a live register in the hot kernels (k_conv_tc sits exactly at its register cap) and without
-// static shared memory (it also sits at the shared-memory cap): every try_wait that comes back empty-handed -- with the
-// 10 ms suspend hint the tensor-core kernels use, or after ~1 us of polling in the gather kernel -- bumps one CTA-wide
-// 32-bit counter whose shared-memory address the caller derives from the barrier's own address; a healthy pipeline never
-// comes near the limit, a TMA-descriptor / pipeline bug reaches it within seconds and makes the kernel trap instead of
-// hanging the GPU (the next library call returns FUSG_ERR_CUDA and fusg_last_error() names the launch failure).
-// Kernels zero the counter before their first wait.
-template <unsigned LIMIT>
-__device__ __forceinline__ void fusg_wait_failed(unsigned counter_smem_addr) {
-    unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(counter_smem_addr) : "memory");
-    if (old > LIMIT) __trap();      // (a trap, not an assert: no call, hence no ABI stack frame in the hot kernels)
+// static shared memory (it also sits at the shared-memory cap): the kernel stores its start time (%globaltimer_hi) in a
+// 32-bit shared-memory slot before its first wait; every try_wait that comes back empty-handed re-reads the timer and traps
+// once the KERNEL has been running for more than ~10 s -- healthy kernels of this library run for milliseconds, a
+// TMA-descriptor / pipeline bug would otherwise spin forever and take the GPU with it.  After the trap the next library call
+// returns FUSG_ERR_CUDA and fusg_last_error() names the launch failure.  The slot's address is derived by the caller from the
+// barrier's own address, so nothing has to stay live across the wait.
+// (the upper half of the nanosecond timer ticks every 4.29 s: 32-bit arithmetic, trap after 3 ticks = 8.6 .. 12.9 s)
+__device__ __forceinline__ void fusg_wait_guard_start(unsigned *slot) {
+    unsigned now;
+    asm volatile("mov.u32 %0, %%globaltimer_hi;" : "=r"(now));
+    *slot = now;
+}
+__device__ __forceinline__ void fusg_wait_failed(unsigned slot_smem_addr) {
+    unsigned t0, now;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t0) : "r"(slot_smem_addr) : "memory");
+    asm volatile("mov.u32 %0, %%globaltimer_hi;" : "=r"(now));
+    if (now - t0 >= 3u) __trap();      // (a trap, not an assert: no call, hence no ABI stack frame in the hot kernels)
 }
 #endif

@@ -11,14 +11,17 @@
 // top-left rule, z-buffer on the perspective-correct depth, perspective-correct colour interpolation, round(c * 255)).
 // This file follows the oracle operation for operation in fp64 (compiled with -fmad=false) and is bit-identical to it.
 //
-// One call renders B items of one mesh.  Five launches:
-//   k_render_vertices   (vertex, item): world position (optional rigid move), camera space, image-plane position
+// One call renders B items of one mesh.  A vehicle covers a small part of a 1080p frame, so only the screen bounding box of
+// each item's projected vertices is z-buffered and shaded; the rest of the outputs is a plain background fill:
+//   k_render_background frame-sized outputs <- background (sketch 0, mask 1), per-item bounding boxes <- empty
+//   k_render_vertices   (vertex, item): world position (optional rigid move), camera space, image-plane position; bounding box
 //   k_render_colours    (vertex, item): vertex normal from the incident triangles in ascending order (CSR), colour
-//   k_render_clear      z-buffer keys <- +inf
+//   k_render_clear      z-buffer keys of the bounding box <- +inf
 //   k_render_raster     (triangle, item): edge-function coverage over the triangle's bounding box, 64-bit atomicMin of
 //                       (float32 depth bits << 32 | triangle index): nearest wins, ties go to the lower index
-//   k_render_resolve    (pixel, item): winner triangle -> interpolated colour -> uint8 sketch + background mask
+//   k_render_resolve    (bounding-box pixel, item): winner triangle -> interpolated colour -> uint8 sketch + mask
 #include <cuda_runtime.h>
+#include <climits>
 #include <cstdint>
 #include "../../include/fusg.h"
 #include "fusg_common.h"
@@ -27,7 +30,7 @@ namespace fusg {
 
 __global__ void __launch_bounds__(256) k_render_vertices(const double *__restrict__ verts, const double *__restrict__ rot, const double *__restrict__ tr,
                                                          const double *__restrict__ E, const double *__restrict__ K, double *__restrict__ Vw,
-                                                         double *__restrict__ uvz, int Nv, int H, int W) {
+                                                         double *__restrict__ uvz, int *__restrict__ bbox, int Nv, int H, int W) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (v >= Nv) return;
     double x = verts[3 * v], y = verts[3 * v + 1], z = verts[3 * v + 2];
@@ -48,9 +51,32 @@ __global__ void __launch_bounds__(256) k_render_vertices(const double *__restric
     const double pcx = W / 2.0 - 0.5, pcy = H / 2.0 - 0.5;
     const double zs = cz > 1e-6 ? cz : 1.0;
     double *o = uvz + ((size_t)b * Nv + v) * 3;
-    o[0] = k[0] * cx / zs + pcx;
-    o[1] = k[4] * cy / zs + pcy;
+    const double pu = k[0] * cx / zs + pcx, pv = k[4] * cy / zs + pcy;
+    o[0] = pu;
+    o[1] = pv;
     o[2] = cz;
+    if (cz > 1e-6) {                                    // triangles with a vertex behind the camera are not drawn
+        int *bb = bbox + 4 * b;
+        const double lim = 1e9;
+        atomicMin(bb + 0, (int)floor(fmax(fmin(pu, lim), -lim)));
+        atomicMin(bb + 1, (int)floor(fmax(fmin(pv, lim), -lim)));
+        atomicMax(bb + 2, (int)ceil(fmax(fmin(pu, lim), -lim)));
+        atomicMax(bb + 3, (int)ceil(fmax(fmin(pv, lim), -lim)));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_render_background(uint8_t *__restrict__ img, uint8_t *__restrict__ mask, int *__restrict__ bbox, size_t npix, int B) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < npix * 3; i += stride) img[i] = 0;
+    for (size_t i = i0; i < npix; i += stride) mask[i] = 1;
+    if (i0 < (size_t)B) { bbox[4 * i0] = INT_MAX; bbox[4 * i0 + 1] = INT_MAX; bbox[4 * i0 + 2] = INT_MIN; bbox[4 * i0 + 3] = INT_MIN; }
+}
+
+// the part of item b's bounding box inside the frame: x0..x1, y0..y1 (empty: x1 < x0)
+__device__ __forceinline__ void item_box(const int *__restrict__ bbox, int b, int H, int W, int &x0, int &y0, int &x1, int &y1) {
+    x0 = max(bbox[4 * b], 0); y0 = max(bbox[4 * b + 1], 0);
+    x1 = min(bbox[4 * b + 2], W - 1); y1 = min(bbox[4 * b + 3], H - 1);
 }
 
 __global__ void __launch_bounds__(256) k_render_colours(const double *__restrict__ Vw, const int32_t *__restrict__ tris, const int32_t *__restrict__ adj_off,
@@ -76,13 +102,20 @@ __global__ void __launch_bounds__(256) k_render_colours(const double *__restrict
     c[2] = (az / norm + 1.0) / 2.0;
 }
 
-__global__ void __launch_bounds__(256) k_render_clear(unsigned long long *__restrict__ zbuf, size_t n) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) zbuf[i] = ~0ull;
+// grid (blocks, B): grid-stride over the item's bounding box
+__global__ void __launch_bounds__(256) k_render_clear(unsigned long long *__restrict__ zbuf, const int *__restrict__ bbox, int H, int W) {
+    const int b = blockIdx.y;
+    int x0, y0, x1, y1;
+    item_box(bbox, b, H, W, x0, y0, x1, y1);
+    if (x1 < x0 || y1 < y0) return;
+    const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
+    unsigned long long *zb = zbuf + (size_t)b * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) zb[(size_t)(y0 + i / bw) * W + x0 + i % bw] = ~0ull;
 }
 
 struct TriSetup {
     double x0, y0, x1, y1, x2, y2, z0, z1, z2, area;
+    double q0, q1, q2;                                 // 1 / (area * z_k): barycentric / depth weights are e_k * q_k
     int i0, i1, i2;
     bool ok;
 };
@@ -103,6 +136,7 @@ __device__ __forceinline__ TriSetup tri_setup(const double *__restrict__ uvz, co
         td = s.z1; s.z1 = s.z2; s.z2 = td;
         s.area = -s.area;
     }
+    s.q0 = 1.0 / (s.area * s.z0); s.q1 = 1.0 / (s.area * s.z1); s.q2 = 1.0 / (s.area * s.z2);
     return s;
 }
 
@@ -130,7 +164,7 @@ __global__ void __launch_bounds__(128) k_render_raster(const double *__restrict_
             const double e2 = (s.x1 - s.x0) * (py - s.y0) - (s.y1 - s.y0) * (px - s.x0);
             const bool in = (e0 > 0 || (e0 == 0 && tl0)) && (e1 > 0 || (e1 == 0 && tl1)) && (e2 > 0 || (e2 == 0 && tl2));
             if (!in) continue;
-            const double iz = ((e0 / s.area) / s.z0 + (e1 / s.area) / s.z1) + (e2 / s.area) / s.z2;
+            const double iz = (e0 * s.q0 + e1 * s.q1) + e2 * s.q2;
             const float depth = (float)(1.0 / iz);
             const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned)t;
             atomicMin(zb + (size_t)y * W + x, key);
@@ -139,13 +173,19 @@ __global__ void __launch_bounds__(128) k_render_raster(const double *__restrict_
 }
 
 __global__ void __launch_bounds__(256) k_render_resolve(const double *__restrict__ uvz_all, const double *__restrict__ col_all, const int32_t *__restrict__ tris,
-                                                        const unsigned long long *__restrict__ zbuf, uint8_t *__restrict__ img, uint8_t *__restrict__ mask,
-                                                        int Nv, int H, int W) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (p >= H * W) return;
+                                                        const unsigned long long *__restrict__ zbuf, const int *__restrict__ bbox,
+                                                        uint8_t *__restrict__ img, uint8_t *__restrict__ mask, int Nv, int H, int W) {
+    const int b = blockIdx.y;
+    int bx0, by0, bx1, by1;
+    item_box(bbox, b, H, W, bx0, by0, bx1, by1);
+    if (bx1 < bx0 || by1 < by0) return;
+    const int bw = bx1 - bx0 + 1, n = bw * (by1 - by0 + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int p = (by0 + i / bw) * W + bx0 + i % bw;
     const unsigned long long key = zbuf[(size_t)b * H * W + p];
+    if (key == ~0ull) continue;                        // background: already filled
     uint8_t r = 0, g = 0, bl = 0;
-    if (key != ~0ull) {
+    {
         const int t = (int)(key & 0xffffffffull);
         const TriSetup s = tri_setup(uvz_all + (size_t)b * Nv * 3, tris, t);
         const double *col = col_all + (size_t)b * Nv * 3;
@@ -153,7 +193,7 @@ __global__ void __launch_bounds__(256) k_render_resolve(const double *__restrict
         const double e0 = (s.x2 - s.x1) * (py - s.y1) - (s.y2 - s.y1) * (px - s.x1);
         const double e1 = (s.x0 - s.x2) * (py - s.y2) - (s.y0 - s.y2) * (px - s.x2);
         const double e2 = (s.x1 - s.x0) * (py - s.y0) - (s.y1 - s.y0) * (px - s.x0);
-        const double w0 = (e0 / s.area) / s.z0, w1 = (e1 / s.area) / s.z1, w2 = (e2 / s.area) / s.z2;
+        const double w0 = e0 * s.q0, w1 = e1 * s.q1, w2 = e2 * s.q2;
         const double iz = (w0 + w1) + w2;
         uint8_t out[3];
 #pragma unroll
@@ -167,6 +207,7 @@ __global__ void __launch_bounds__(256) k_render_resolve(const double *__restrict
     uint8_t *o = img + ((size_t)b * H * W + p) * 3;
     o[0] = r; o[1] = g; o[2] = bl;
     mask[(size_t)b * H * W + p] = (r == 0 && g == 0 && bl == 0) ? 1 : 0;
+    }
 }
 
 }  // namespace fusg
@@ -175,7 +216,7 @@ using namespace fusg;
 
 extern "C" size_t fusg_render_workspace_bytes(int B, int Nv, int H, int W) {
     if (B <= 0 || Nv <= 0 || H <= 0 || W <= 0) return 0;
-    return (size_t)B * ((size_t)Nv * 9 * sizeof(double) + (size_t)H * W * sizeof(unsigned long long));
+    return (size_t)B * ((size_t)Nv * 9 * sizeof(double) + (size_t)H * W * sizeof(unsigned long long) + 4 * sizeof(int));
 }
 
 extern "C" int fusg_render_normals(const double *verts, const int32_t *tris, const int32_t *adj_off, const int32_t *adj_tri, int Nv, int Nt,
@@ -190,14 +231,18 @@ extern "C" int fusg_render_normals(const double *verts, const int32_t *tris, con
     double *uvz = Vw + (size_t)B * Nv * 3;
     double *col = uvz + (size_t)B * Nv * 3;
     unsigned long long *zbuf = reinterpret_cast<unsigned long long *>(col + (size_t)B * Nv * 3);
+    int *bbox = reinterpret_cast<int *>(zbuf + (size_t)B * H * W);
     const dim3 gv((Nv + 255) / 256, B);
-    k_render_vertices<<<gv, 256, 0, st>>>(verts, rot, tr, E, K, Vw, uvz, Nv, H, W);
-    k_render_colours<<<gv, 256, 0, st>>>(Vw, tris, adj_off, adj_tri, col, Nv);
     const size_t nz = (size_t)B * H * W;
-    const int cgrid = (int)((nz + 255) / 256 < (size_t)fusg_num_sms() * 16 ? (nz + 255) / 256 : (size_t)fusg_num_sms() * 16);
-    k_render_clear<<<cgrid, 256, 0, st>>>(zbuf, nz);
+    const int bgrid = (int)((nz * 3 / 16 + 255) / 256 < (size_t)fusg_num_sms() * 16 ? (nz * 3 / 16 + 255) / 256 + 1 : (size_t)fusg_num_sms() * 16);
+    k_render_background<<<bgrid, 256, 0, st>>>(normals, mask, bbox, nz, B);
+    k_render_vertices<<<gv, 256, 0, st>>>(verts, rot, tr, E, K, Vw, uvz, bbox, Nv, H, W);
+    k_render_colours<<<gv, 256, 0, st>>>(Vw, tris, adj_off, adj_tri, col, Nv);
+    // per item: enough blocks for a bounding box of a quarter of the frame in one sweep, grid-stride beyond
+    const int pgrid = (H * W / 4 + 255) / 256 < 64 ? ((H * W / 4 + 255) / 256 > 0 ? (H * W / 4 + 255) / 256 : 1) : 64;
+    k_render_clear<<<dim3(pgrid, B), 256, 0, st>>>(zbuf, bbox, H, W);
     k_render_raster<<<dim3((Nt + 127) / 128, B), 128, 0, st>>>(uvz, tris, zbuf, Nv, Nt, H, W);
-    k_render_resolve<<<dim3((H * W + 255) / 256, B), 256, 0, st>>>(uvz, col, tris, zbuf, normals, mask, Nv, H, W);
-    fusg_count_launch(5);
+    k_render_resolve<<<dim3(pgrid, B), 256, 0, st>>>(uvz, col, tris, zbuf, bbox, normals, mask, Nv, H, W);
+    fusg_count_launch(6);
     return fusg_check_launch();
 }

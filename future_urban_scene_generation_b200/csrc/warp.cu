@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_zero_planes(int4 *__restrict__ out, siz
 
 struct WarpSmemHeader {
     unsigned long long mbar;
-    unsigned wait_failures, pad0;                  // must directly follow mbar (mbar_wait)
+    unsigned wait_start, pad0;                     // kernel start time; must directly follow mbar (mbar_wait)
     double Minv[N_TEX][9];
     int sel[N_TEX];                                // source plane feeding output plane j, or -1
     int polyx[6], polyy[6], polyn;
@@ -363,7 +363,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phas
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
-        if (!done) fusg_wait_failed<400000000u>(smem_u32(bar) + 8);      // WarpSmemHeader::wait_failures follows mbar
+        if (!done) fusg_wait_failed(smem_u32(bar) + 8);      // WarpSmemHeader::wait_start follows mbar
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
@@ -454,7 +454,7 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
     WarpSmemHeader *hd = reinterpret_cast<WarpSmemHeader *>(s_rows + WARP_NWARPS * ROW_BYTES_MAX);
     if (tid == 0) {
         mbar_init(&hd->mbar, 1);
-        hd->wait_failures = 0;
+        fusg_wait_guard_start(&hd->wait_start);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t phase = 0;

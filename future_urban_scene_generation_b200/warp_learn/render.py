@@ -49,10 +49,11 @@ def _f64(torch, a, shape, dev):
     return t.to(device=dev, dtype=torch.float64).reshape(shape).contiguous()
 
 
-def render_normals_batch(mesh, extrinsics, intrinsics, h, w, rot=None, tr=None, max_items_per_call=None):
+def render_normals_batch(mesh, extrinsics, intrinsics, h, w, rot=None, tr=None, max_items_per_call=None, out=None):
     """mesh: MeshOnDevice or (vertices, triangles); extrinsics (B,3,4)|(B,4,4), intrinsics (B,3,3)|(3,3); rot (B,3,3) and
     tr (B,3), optional: item b renders `vertices @ rot[b] + tr[b]`.  -> (normals (B,h,w,3) u8, mask (B,h,w) bool) on the
-    device; mask is True on the BACKGROUND like the reference's `object_mask`.  Asynchronous on the current stream."""
+    device; mask is True on the BACKGROUND like the reference's `object_mask`.  Asynchronous on the current stream.
+    out = (normals u8 (B,h,w,3), mask u8 or bool (B,h,w)): contiguous device tensors (or slices) to render into."""
     torch = _lib.require_cuda()
     if not isinstance(mesh, MeshOnDevice):
         mesh = MeshOnDevice(*mesh)
@@ -70,13 +71,24 @@ def render_normals_batch(mesh, extrinsics, intrinsics, h, w, rot=None, tr=None, 
     T = _f64(torch, tr, (B, 3), dev) if tr is not None else None
     if T is not None and R is None:
         raise ValueError("tr needs rot")
-    normals = torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev)
-    mask = torch.empty((B, h, w), dtype=torch.uint8, device=dev)
+    if out is None:
+        normals = torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev)
+        mask = torch.empty((B, h, w), dtype=torch.uint8, device=dev)
+    else:
+        normals, mask = out
+        if tuple(normals.shape) != (B, h, w, 3) or tuple(mask.shape) != (B, h, w) or normals.dtype != torch.uint8 or \
+                mask.dtype not in (torch.uint8, torch.bool) or not (normals.is_contiguous() and mask.is_contiguous()):
+            raise ValueError("out must be contiguous (B,h,w,3) uint8 and (B,h,w) uint8/bool device tensors")
+        mask = mask.view(torch.uint8)
     L = _lib.lib()
     # the z-buffer costs 8 bytes per pixel and item: bound the workspace (default 1 GiB) by rendering in chunks
     per_item = L.fusg_render_workspace_bytes(1, mesh.nv, h, w)
     chunk = max_items_per_call or max(1, min(B, (1 << 30) // max(per_item, 1)))
-    ws = torch.empty((L.fusg_render_workspace_bytes(min(chunk, B), mesh.nv, h, w),), dtype=torch.uint8, device=dev)
+    need = L.fusg_render_workspace_bytes(min(chunk, B), mesh.nv, h, w)
+    ws = getattr(mesh, "_ws", None)                        # the workspace is reused across calls on the same mesh (stream ordered)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        mesh._ws = ws
     with torch.cuda.device(dev):
         for b0 in range(0, B, chunk):
             n = min(chunk, B - b0)
@@ -86,7 +98,7 @@ def render_normals_batch(mesh, extrinsics, intrinsics, h, w, rot=None, tr=None, 
                                        _lib.ptr(ws), ws.numel(), n, int(h), int(w), _lib.stream_ptr(torch))
             _lib.check(rc, "fusg_render_normals")
     normals._keep = (ws, E, Kt, R, T, mesh)
-    return normals, mask.bool()
+    return normals, mask.view(torch.bool)                  # the kernel writes 0 / 1
 
 
 def get_rendered(model_ply, w, h, extrinsic, intrinsic):

@@ -25,7 +25,7 @@ rasteriser equals THIS restatement bit for bit (tests/test_render_gpu.py):
     round(c * 255); the float readback * 255 -> astype(uint8) of the reference is the identity on those values
     (checked for all 256 levels).
 
-Everything is fp64 with the operation order spelled out in `_raster_triangle`, which the kernel follows
+Everything is fp64 with the operation order spelled out in `render_normals`, which the kernel follows
 (csrc/render.cu, compiled with -fmad=false).  Only tests/ and __graft_entry__.smoke() import this module.
 """
 import numpy as np
@@ -131,7 +131,8 @@ def render_normals(vertices, triangles, extrinsic, intrinsic, h, w, rot=None, tr
         inside = in0 & in1 & in2
         if not inside.any():
             continue
-        iz = (e0 / area) / z[i0] + (e1 / area) / z[i1] + (e2 / area) / z[i2]
+        q0, q1, q2 = 1.0 / (area * z[i0]), 1.0 / (area * z[i1]), 1.0 / (area * z[i2])
+        iz = (e0 * q0 + e1 * q1) + e2 * q2
         depth = (1.0 / iz).astype(np.float32)
         sub_d = key_depth[ymin:ymax + 1, xmin:xmax + 1]
         sub_t = key_tri[ymin:ymax + 1, xmin:xmax + 1]
@@ -153,8 +154,8 @@ def render_normals(vertices, triangles, extrinsic, intrinsic, h, w, rot=None, tr
         e0 = (x2 - x1) * (py - y1) - (y2 - y1) * (px - x1)
         e1 = (x0 - x2) * (py - y2) - (y0 - y2) * (px - x2)
         e2 = (x1 - x0) * (py - y0) - (y1 - y0) * (px - x0)
-        w0, w1, w2 = (e0 / area) / z[i0], (e1 / area) / z[i1], (e2 / area) / z[i2]
-        iz = w0 + w1 + w2
+        w0, w1, w2 = e0 * (1.0 / (area * z[i0])), e1 * (1.0 / (area * z[i1])), e2 * (1.0 / (area * z[i2]))
+        iz = (w0 + w1) + w2
         for c in range(3):
             val = ((w0 * col[i0, c] + w1 * col[i1, c]) + w2 * col[i2, c]) / iz
             k = np.floor(val * 255.0 + 0.5)
