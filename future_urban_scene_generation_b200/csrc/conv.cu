@@ -420,8 +420,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+// fp16 activations (ICN): saturate instead of overflowing to inf -- a pre-norm convolution output beyond +-65504 would
+// otherwise turn the whole InstanceNorm plane into NaN (random-init weights stay below ~1e2; real checkpoints are unverified)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }

@@ -97,16 +97,24 @@ __global__ void __launch_bounds__(ST_THREADS) k_norm_stats(const T *__restrict__
     const int g = threadIdx.x % groups, l = threadIdx.x / groups;
     const int split = blockIdx.x, b = blockIdx.y;
     const int per = (HW + nsplit - 1) / nsplit, p0 = split * per, p1 = min(HW, p0 + per);
-    float sum[N], sq[N];
+    // Shifted sums: the statistics are taken of (x - k) with k = the channel's value at pixel 0 of the sample, so that
+    // E[(x-k)^2] - E[x-k]^2 does not cancel when |mean| >> std (a one-pass sum of x and x^2 in fp32 does; the reference's
+    // InstanceNorm uses Welford).  Every split of a sample uses the same k; the finalize kernel adds it back.
+    float sum[N], sq[N], shift[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) sum[k] = sq[k] = 0.f;
     if (l < lanes) {
         const T *base = x + ((size_t)b * HW) * C + g * N;
+        Vec<T>::load(base, shift);
         for (int p = p0 + l; p < p1; p += lanes) {
             float v[N];
             Vec<T>::load(base + (size_t)p * C, v);
 #pragma unroll
-            for (int k = 0; k < N; ++k) { sum[k] += v[k]; sq[k] += v[k] * v[k]; }
+            for (int k = 0; k < N; ++k) { const float dv = v[k] - shift[k]; sum[k] += dv; sq[k] += dv * dv; }
+        }
+        if (split == 0 && l == 0) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) partial[(size_t)gridDim.y * nsplit * C * 2 + (size_t)b * C + g * N + k] = shift[k];
         }
     }
 #pragma unroll
@@ -128,6 +136,7 @@ __global__ void __launch_bounds__(256) k_norm_finalize(const float *__restrict__
                                                        int kind, float eps) {
     __shared__ double s_a[256], s_q[256];
     const int b = blockIdx.x;
+    const float *shifts = partial + (size_t)gridDim.x * nsplit * C * 2 + (size_t)b * C;      // k of the shifted sums
     double tot_a = 0, tot_q = 0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double a = 0, q = 0;
@@ -135,13 +144,16 @@ __global__ void __launch_bounds__(256) k_norm_finalize(const float *__restrict__
             const float *pp = partial + (((size_t)b * nsplit + s) * C + c) * 2;
             a += (double)pp[0]; q += (double)pp[1];
         }
+        const double k = (double)shifts[c];
         if (kind == 0) {
-            const double mean = a / HW, var = fmax(q / HW - mean * mean, 0.0);
+            const double dm = a / HW, mean = k + dm, var = fmax(q / HW - dm * dm, 0.0);
             const double sc = 1.0 / sqrt(var + (double)eps);
             ss[((size_t)b * C + c) * 2] = (float)sc;
             ss[((size_t)b * C + c) * 2 + 1] = (float)(-mean * sc);
         }
-        tot_a += a; tot_q += q;
+        // un-shift for the per-sample statistics: sum x = a + HW k, sum x^2 = q + 2 k a + HW k^2 (fp64)
+        tot_a += a + (double)HW * k;
+        tot_q += q + 2.0 * k * a + (double)HW * k * k;
     }
     if (kind != 1) return;
     s_a[threadIdx.x] = tot_a; s_q[threadIdx.x] = tot_q;

@@ -108,6 +108,12 @@ class VunetEngine:
     def _empty(self, *shape, dtype=None):
         return self.torch.empty(shape, dtype=dtype or self.tdtype, device=self.device())
 
+    def record_stream(self, act, stream):
+        """Marks every tensor of an activation as in use on `stream` (torch's caching allocator)."""
+        for t in (act.raw, act.elu, act.f32) + tuple(v for v in act.aux.values() if hasattr(v, "record_stream")):
+            if t is not None and t.is_cuda:
+                t.record_stream(stream)
+
     # ------------------------------------------------------------------ weights
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.m.parameters())

@@ -233,6 +233,10 @@ class Vunet_fix_res(nn.Module):
                         out_e, skips_e = e.enc_up(x)
                         mu_app, z_app = e.enc_down(out_e, skips_e)
                         cur.wait_stream(side)
+                        # the shape-encoder activations were allocated on the side stream and are consumed on `cur`:
+                        # tell the caching allocator, or another caller stream could be handed their blocks too early
+                        for a in list(out_d) + list(skips_d):
+                            e.record_stream(a, cur)
                     else:
                         out_e, skips_e = e.enc_up(x)
                         mu_app, z_app = e.enc_down(out_e, skips_e)

@@ -165,7 +165,7 @@ class IcnEngine:
         B, Cn = raw.shape[0], raw.shape[-1]
         HW = H * W
         nsplit = max(1, min(64, HW // 512))
-        partial = self._empty(B, nsplit, Cn, 2, dtype=torch.float32)
+        partial = self._empty(B * nsplit * Cn * 2 + B * Cn, dtype=torch.float32)      # (sum, sumsq) of the shifted values per split + the shifts
         ss = self._empty(B, Cn, 2, dtype=torch.float32)
         L = _lib.lib()
         esz = raw.element_size()

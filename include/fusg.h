@@ -321,11 +321,13 @@ int fusg_u8_to_vunet_inputs(const uint8_t *mask_bbox, const uint8_t *normal_src,
  * by reflection (nn.ReflectionPad2d, warp_learn/models.py:43-44): the input of the first 7x7 Conv2dBlock (:125-127). */
 int fusg_nchw_to_nhwc_reflect(const float *in, void *out, int B, int C, int H, int W, int cpad, int border, int dtype, void *stream);
 
-/* Per-(sample, channel) partial sums of an NHWC [B,HW,C] tensor: partial [B, nsplit, C, 2] fp32 = (sum, sum of squares)
- * of the pixels of split s.  C a multiple of 8 and <= 256; deterministic (no atomics). */
+/* Per-(sample, channel) partial sums of an NHWC [B,HW,C] tensor: partial = [B, nsplit, C, 2] fp32 (sum, sum of squares) of
+ * (x - k) over the pixels of split s, followed by [B, C] fp32 shifts k = x[b, pixel 0, c] -- B*nsplit*C*2 + B*C floats in all.
+ * The shift keeps the one-pass variance free of cancellation when |mean| >> std.  C a multiple of 8 and <= 256;
+ * deterministic (no atomics). */
 int fusg_norm_stats(const void *x, float *partial, int B, int HW, int C, int nsplit, int dtype, void *stream);
 
-/* Folds the partial sums into per-(sample, channel) scale/shift pairs, ss [B,C,2] fp32, y = x*scale + shift:
+/* Folds the partial sums (layout above, written by fusg_norm_stats) into per-(sample, channel) scale/shift pairs, ss [B,C,2] fp32, y = x*scale + shift:
  *   kind 0  nn.InstanceNorm2d(affine=False, eps) (warp_learn/models.py:55-56): per (b,c) biased variance,
  *           scale = 1/sqrt(var + eps), shift = -mean*scale;
  *   kind 1  the reference's own LayerNorm (warp_learn/models.py:15-35): per sample over C*H*W, UNBIASED std,

@@ -69,6 +69,27 @@ def test_reflect_layout_and_norm_passes(cuda, dtype):
     assert (out.t.float() - want).abs().max().item() <= (2e-5 if dtype == "fp32" else 1e-3 * T16[dtype] * max(1.0, want.abs().max().item()))
 
 
+def test_norm_statistics_survive_a_large_mean(cuda):
+    """|mean| >> std (here 300 against 0.5 per channel): a one-pass E[x^2] - mean^2 in fp32 loses the variance to
+    cancellation; the shifted sums of fusg_norm_stats do not (the reference's InstanceNorm is Welford-accurate)."""
+    torch = cuda
+    import torch.nn.functional as F
+    m, _ = _engine(torch, "fp32")
+    e = m.engine()
+    g = torch.Generator(device="cpu").manual_seed(9)
+    off = (torch.rand(1, 64, 1, 1, generator=g) * 2 - 1) * 300.0
+    x = (torch.randn(2, 64, 32, 48, generator=g) * 0.5 + off).cuda()
+    raw = x.permute(0, 2, 3, 1).contiguous()
+    out = e.norm("t", raw, 32, 48, "inst", relu=False, up=1, border=0)
+    want = F.instance_norm(x.double(), eps=1e-5).permute(0, 2, 3, 1)
+    assert (out.t.double() - want).abs().max().item() < 2e-3
+    gamma, beta = torch.ones(64).cuda(), torch.zeros(64).cuda()
+    out = e.norm("t", raw, 32, 48, "ln", gamma, beta, relu=False, up=1, border=0)
+    flat = x.double().reshape(2, -1)
+    want = ((x.double() - flat.mean(1).view(-1, 1, 1, 1)) / (flat.std(1).view(-1, 1, 1, 1) + 1e-5)).permute(0, 2, 3, 1)
+    assert (out.t.double() - want).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("path,res,stride,pad", [
     ("enc_content.model.0", 64, 1, 3),                 # 7x7 21(32)->64
     ("enc_content.model.1", 64, 2, 1),                 # 4x4 s2 64->128
