@@ -422,7 +422,10 @@ def run_ours(args):
             a[0] += flops
             a[1] += e0.elapsed_time(e1) * 1e-3
             a[2] += 1
-        tc = agg.get(1, [0.0, 1e-9, 0])
+        # every convolution launch of the forward counts (the 110 tcgen05 launches AND the two streaming first-layer NiNs,
+        # impl 3, which hold 0.15 % of the FLOPs): FLOP-weighted over all 112 convs, the conservative reading
+        tc = [sum(a[0] for a in agg.values()), sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values())]
+        tc_only = agg.get(1, [0.0, 1e-9, 0])
         achieved = tc[0] / tc[1] / 1e12
         peak = peaks["bf16_tflops_sustained"]
         traffic, traffic_src = None, None
@@ -432,7 +435,8 @@ def run_ours(args):
                 tj = json.load(open(tpath))
                 traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
                 break
-        roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv; all 112 conv launches of a forward are summed)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "k_conv_tc_only": {"achieved": tc_only[0] / tc_only[1] / 1e12, "frac": tc_only[0] / tc_only[1] / 1e12 / peak, "launches_per_step": tc_only[2] // 2},
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu; B=64)", "traffic_source": traffic_src, "peak_source": peaks["source"] + ", sustained bf16",
                 "launches_per_step": tc[2] // 2, "avg_launch_ms": 1e3 * tc[1] / max(1, tc[2]),
                 "algorithmic_flops_per_step": tc[0] / 2, "share_of_vunet_time": tc[1] / max(1e-9, sum(a[1] for a in agg.values()))}

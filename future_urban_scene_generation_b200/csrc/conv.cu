@@ -1497,9 +1497,91 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
 
 extern "C" size_t fusg_sizeof_conv_desc(void) { return sizeof(fusg_conv_desc); }
 
+// ------------------------------------------------------------------------------------------------
+// FUSG_IMPL_SMALLCIN: 1x1 convolution of a network INPUT (NiN of the 6- / 3-channel images, vunet/models.py:141-150,
+// stored 16 channels wide, of which at most 8 are real) -- K is so small that the layer is a pure stream: read 32 bytes per pixel, write cout bf16 raw
+// and/or ELU values per pixel.  On the tensor-core kernel its epilogue warps (8 of 12) are the bottleneck (0.50 ms for the
+// 6->128 layer at 64 crops, 2.2 TB/s); here EVERY thread is an "epilogue" thread: a thread owns 8 output channels, keeps
+// their 8 x 8 weights in registers and walks over pixels, four in flight; 16-byte coalesced stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_CIN = 8;                                  // real input channels served (the images have 6 and 3)
+constexpr int SC_PIX = 4;                                  // pixels in flight per thread: their loads are issued before any math
+
+__global__ void __launch_bounds__(SC_THREADS, 2) k_conv1x1_smallcin(const __nv_bfloat16 *__restrict__ in, int pitch_in, const __nv_bfloat16 *__restrict__ w,
+                                                                    int cin_pad, const float *__restrict__ bias, __nv_bfloat16 *__restrict__ raw,
+                                                                    __nv_bfloat16 *__restrict__ elu, int cout, long long npix) {
+    const int chunks = cout >> 3;                          // 16-byte output chunks per pixel
+    const int chunk = threadIdx.x % chunks, pl = threadIdx.x / chunks, ppc = SC_THREADS / chunks;
+    float wr[8][SC_CIN], bs[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        bs[o] = bias[chunk * 8 + o];
+        const uint4 a = *reinterpret_cast<const uint4 *>(w + (size_t)(chunk * 8 + o) * cin_pad);
+        const uint32_t ww[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { wr[o][2 * c] = bf16lo_to_f(ww[c]); wr[o][2 * c + 1] = bf16hi_to_f(ww[c]); }
+    }
+    if (pl >= ppc) return;                                 // (cout/8 not a divisor of 256: idle tail threads)
+    const long long step = (long long)gridDim.x * ppc;
+    for (long long p0 = (long long)blockIdx.x * ppc + pl; p0 < npix; p0 += step * SC_PIX) {
+        uint4 xin[SC_PIX];
+#pragma unroll
+        for (int j = 0; j < SC_PIX; ++j) {
+            const long long p = p0 + j * step;
+            xin[j] = p < npix ? __ldg(reinterpret_cast<const uint4 *>(in + (size_t)p * pitch_in)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < SC_PIX; ++j) {
+            const long long p = p0 + j * step;
+            if (p >= npix) break;
+            const uint32_t xw[4] = {xin[j].x, xin[j].y, xin[j].z, xin[j].w};
+            float x[SC_CIN];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { x[2 * c] = bf16lo_to_f(xw[c]); x[2 * c + 1] = bf16hi_to_f(xw[c]); }
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s0 = bs[2 * i], s1 = bs[2 * i + 1];
+#pragma unroll
+                for (int c = 0; c < SC_CIN; ++c) { s0 = fmaf(wr[2 * i][c], x[c], s0); s1 = fmaf(wr[2 * i + 1][c], x[c], s1); }
+                pk[i] = pack_bf16x2(s0, s1);
+            }
+            const size_t off = (size_t)p * cout + chunk * 8;
+            if (raw) *reinterpret_cast<uint4 *>(raw + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (elu) {
+                uint32_t ek[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ek[i] = pack_bf16x2(elu1(bf16lo_to_f(pk[i])), elu1(bf16hi_to_f(pk[i])));   // ELU of the rounded value, like the tensor-core epilogue
+                *reinterpret_cast<uint4 *>(elu + off) = make_uint4(ek[0], ek[1], ek[2], ek[3]);
+            }
+        }
+    }
+}
+
+// the layers FUSG_IMPL_SMALLCIN serves: one bf16 input stored 16 channels wide of which <= 8 are real (cin_real), 1x1, stride 1,
+// plain NHWC bf16 outputs
+static bool smallcin_supported(const fusg_conv_desc &d, __nv_bfloat16 **raw, __nv_bfloat16 **elu) {
+    if (d.dtype != FUSG_DTYPE_BF16 || d.ksize != 1 || d.stride != 1 || d.pad_mode != 0 || d.in1 || d.residual || d.noise) return false;
+    if (d.cphys0 != 16 || d.pitch0 != 16 || d.cin_real <= 0 || d.cin_real > SC_CIN || d.cout % 8 || d.cout > 256 || SC_THREADS % (d.cout / 8)) return false;
+    if ((reinterpret_cast<uintptr_t>(d.in0) & 15) || (reinterpret_cast<uintptr_t>(d.weight) & 15)) return false;
+    __nv_bfloat16 *r = nullptr, *e = nullptr;
+    for (int s = 0; s < FUSG_CONV_MAX_OUTS; ++s) {
+        const fusg_conv_out &o = d.outs[s];
+        if (!o.ptr) continue;
+        if (o.layout != 0 || o.source != 0 || o.mode != FUSG_OUT_PLAIN || o.elu > 1 || (reinterpret_cast<uintptr_t>(o.ptr) & 15)) return false;
+        if (o.elu) { if (e) return false; e = reinterpret_cast<__nv_bfloat16 *>(o.ptr); }
+        else { if (r) return false; r = reinterpret_cast<__nv_bfloat16 *>(o.ptr); }
+    }
+    if (raw) *raw = r;
+    if (elu) *elu = e;
+    return r || e;
+}
+
 extern "C" int fusg_conv2d_select(const fusg_conv_desc *desc) {
     if (!desc) return FUSG_ERR_ARG;
     const int Ho = conv_out_size(desc->H, desc->ksize, desc->stride, desc_pad(*desc)), Wo = conv_out_size(desc->W, desc->ksize, desc->stride, desc_pad(*desc));
+    if (smallcin_supported(*desc, nullptr, nullptr)) return FUSG_IMPL_SMALLCIN;
     return tc_supported(*desc, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT;
 }
 
@@ -1529,7 +1611,20 @@ extern "C" int fusg_conv2d(const fusg_conv_desc *desc, void *stream) {
     if (Ho <= 0 || Wo <= 0) return FUSG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     int impl = d.impl;
-    if (impl == FUSG_IMPL_AUTO) impl = tc_supported(d, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT;
+    __nv_bfloat16 *sc_raw = nullptr, *sc_elu = nullptr;
+    if (impl == FUSG_IMPL_AUTO) impl = smallcin_supported(d, &sc_raw, &sc_elu) ? FUSG_IMPL_SMALLCIN : (tc_supported(d, Ho, Wo) ? FUSG_IMPL_TCGEN05 : FUSG_IMPL_DIRECT);
+    if (impl == FUSG_IMPL_SMALLCIN) {
+        if (!smallcin_supported(d, &sc_raw, &sc_elu)) return FUSG_ERR_UNSUPPORTED;
+        const long long npix = (long long)d.B * d.H * d.W;
+        const int ppc = SC_THREADS / (d.cout / 8);
+        const long long want = (npix + ppc - 1) / ppc;
+        const int grid = (int)(want < (long long)fusg_num_sms() * 2 ? want : (long long)fusg_num_sms() * 2);
+        // weights: [cout_pad][1][cin_pad] bf16, the first 8 input channels of every row (the rest is the zero padding of K)
+        k_conv1x1_smallcin<<<grid, SC_THREADS, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(d.in0), d.pitch0, reinterpret_cast<const __nv_bfloat16 *>(d.weight),
+                                                      d.c0, d.bias, sc_raw, sc_elu, d.cout, npix);
+        fusg_count_launch(1);
+        return fusg_check_launch();
+    }
     if (impl == FUSG_IMPL_TCGEN05) {
         if (!tc_supported(d, Ho, Wo)) return FUSG_ERR_UNSUPPORTED;
         return launch_tc(d, Ho, Wo, st);

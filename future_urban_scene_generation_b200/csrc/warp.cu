@@ -862,25 +862,39 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
                 return e != cudaSuccess ? e : cudaFuncSetAttribute(k_warp_rows<MAX_HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(MAX_HW));
             }) != cudaSuccess)
             return fusg_check_launch();
-        // The zero fill runs on the caller's stream, ahead of the geometry kernels.  (Forking it onto a helper stream so that it
-        // overlaps visibility / gating / solves was measured SLOWER at every grid size -- 14.4 vs 12.3 ms for 16k crops,
-        // profiles/r2_summary.md: the co-running kernels slow each other down by more than the overlap gains.)
+    }
+    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, kp3d_dst, vis, nullptr, nullptr, 2 * B, H, W);
+    if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
+    k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
+    fusg_count_launch(2);
+    // The zero fill of all five planes depends on nothing, and the solves (latency-bound: a few warps per SM, almost no memory
+    // traffic) leave the memory system idle: fork the fill onto a helper stream HERE, next to k_solve, and join before the
+    // gather.  (Forked from the very start it also overlapped k_visibility, which it slowed down by more than it gained:
+    // 14.4 vs 12.3 ms for 16k crops.)
+    FusgFork fk;
+    cudaStream_t zs = st;
+    if (!frame_path) {
+        static const int no_fork = getenv("FUSG_WARP_NO_FORK") ? 1 : 0;               // debug / A-B timing: fill inline on the caller's stream
+        if (!no_fork) {
+            if (fusg_record_cuda(fusg_fork_resources(st, &fk)) != FUSG_OK || fusg_record_cuda(cudaEventRecord(fk.fork, st)) != FUSG_OK ||
+                fusg_record_cuda(cudaStreamWaitEvent(fk.side, fk.fork, 0)) != FUSG_OK)
+                return FUSG_ERR_CUDA;
+            zs = fk.side;
+        }
         const size_t total = (size_t)B * N_TEX * H * W * 3;
         const size_t head = (16 - (reinterpret_cast<uintptr_t>(warped) & 15)) & 15;       // (torch allocations are 512-byte aligned: 0)
         if (head == 0) {
             const size_t n16 = total / 16;
             const size_t want = (n16 + 127) / 128;
             const int zgrid = (int)(want < (size_t)fusg_num_sms() * 16 ? want : (size_t)fusg_num_sms() * 16);
-            k_zero_planes<<<zgrid, 128, 0, st>>>(reinterpret_cast<int4 *>(warped), n16, warped + n16 * 16, (int)(total - n16 * 16));
-        } else if (fusg_record_cuda(cudaMemsetAsync(warped, 0, total, st)) != FUSG_OK) {
+            k_zero_planes<<<zgrid, 128, 0, zs>>>(reinterpret_cast<int4 *>(warped), n16, warped + n16 * 16, (int)(total - n16 * 16));
+        } else if (fusg_record_cuda(cudaMemsetAsync(warped, 0, total, zs)) != FUSG_OK) {
             return FUSG_ERR_CUDA;
         }
         fusg_count_launch(1);
+        if (zs != st && fusg_record_cuda(cudaEventRecord(fk.join, zs)) != FUSG_OK) return FUSG_ERR_CUDA;
     }
-    k_visibility<<<(2 * B + VIS_WARPS - 1) / VIS_WARPS, VIS_WARPS * 32, 0, st>>>(K, E_src, E_dst, kp3d, kp3d_dst, vis, nullptr, nullptr, 2 * B, H, W);
     {
-        if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
-        k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
         if (solver_prepare() != FUSG_OK) return FUSG_ERR_CUDA;
         // 32 point sets per warp whatever the batch: the lanes of a warp run in lock step, so a fuller warp costs no
         // latency, and the fewest possible SMs lose 72 KB of shared memory to a solver warp (the VUNet convolutions of the
@@ -888,9 +902,10 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
         const int lanes = 32;
         const int blocks6 = (2 * B + lanes - 1) / lanes, blocks4 = (3 * B + lanes - 1) / lanes;
         k_solve<<<blocks6 + blocks4, 32, SOLVER_SMEM_BYTES, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4, blocks6, lanes);
-        fusg_count_launch(3);
+        fusg_count_launch(1);
     }
     if (!frame_path) {
+        if (zs != st && fusg_record_cuda(cudaStreamWaitEvent(st, fk.join, 0)) != FUSG_OK) return FUSG_ERR_CUDA;
         k_warp_rows<WIN_SMALL><<<B, WARP_THREADS, warp_smem_bytes(WIN_SMALL), st>>>(src, src_kp, plane_j, Minv, warped, H, W, counters + 2, big_list, 0);
         // crops whose polygons span more than WIN_SMALL source rows (a vehicle filling the crop): full-height window
         const int bgrid = B < fusg_num_sms() ? B : fusg_num_sms();

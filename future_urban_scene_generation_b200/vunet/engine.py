@@ -35,7 +35,7 @@ class ConvDesc(C.Structure):
                 ("cout", C.c_int32), ("cout_pad", C.c_int32), ("residual", C.c_void_p), ("noise", C.c_void_p),
                 ("outs", ConvOut * MAX_OUTS), ("dtype", C.c_int32), ("impl", C.c_int32), ("zero_kblocks", C.c_uint64),
                 ("pad_mode", C.c_int32), ("pad", C.c_int32), ("border", C.c_int32), ("cphys0", C.c_int32), ("cphys1", C.c_int32),
-                ("reserved2", C.c_int32)]
+                ("cin_real", C.c_int32)]
 
 
 class Act:
@@ -201,6 +201,8 @@ class VunetEngine:
         d.in0 = t0.data_ptr() + a0.off * esz
         d.c0, d.pitch0 = a0.C * pm, a0.pitch * pm
         d.cphys0 = a0.cphys or 0
+        if a0.cphys and len(srcs) == 1 and path in self.m.convs:
+            d.cin_real = self.m.convs[path].cin            # a network input stored 16 wide: lets AUTO pick the streaming 1x1 kernel
         ctot = a0.C * pm
         keep = [t0]
         if len(srcs) > 1:

@@ -158,6 +158,8 @@ int fusg_warp_perspective(const uint8_t *img, const double *Hm, uint8_t *out, in
 #define FUSG_IMPL_AUTO 0
 #define FUSG_IMPL_TCGEN05 1       /* implicit-GEMM tcgen05/TMEM kernel fed by TMA (bf16 only) */
 #define FUSG_IMPL_DIRECT 2        /* CUDA-core direct convolution (any dtype; the in-library check) */
+#define FUSG_IMPL_SMALLCIN 3      /* streaming 1x1 convolution of a network input stored 16 channels wide (cphys0 = pitch0 = 16, cin_real <= 8):
+                                   * the first NiN of each encoder, where K is 3 or 6 and the layer is pure HBM streaming */
 
 #define FUSG_OUT_PLAIN 0          /* out[b, y, x, n]                                              */
 #define FUSG_OUT_D2S 1            /* DepthToSpace(2), vunet/layers.py:173-194 (block-major):      */
@@ -216,13 +218,14 @@ typedef struct fusg_conv_desc {
     int32_t cphys0, cphys1;     /* 0, or the number of channels in0 / in1 really hold (< c0 / c1, multiple of 8): channels
                                  * cphys..c-1 read as zero.  The network inputs (6 / 3 real channels) are stored 16 wide and
                                  * widened to a 64- / 32-channel K block by TMA's out-of-bounds zero fill instead of in HBM  */
-    int32_t reserved2;
+    int32_t cin_real;           /* optional hint: the number of REAL input channels of in0 when it is smaller than c0 / cphys0 (the
+                                 * rest is zero padding whose weights are zero); 0 = unknown.  Lets FUSG_IMPL_AUTO pick FUSG_IMPL_SMALLCIN. */
 } fusg_conv_desc;
 
 int fusg_conv2d(const fusg_conv_desc *desc, void *stream);
 /* sizeof(fusg_conv_desc) as this library was compiled (binding self-check). */
 size_t fusg_sizeof_conv_desc(void);
-/* Which kernel FUSG_IMPL_AUTO resolves to for this descriptor (FUSG_IMPL_TCGEN05 or FUSG_IMPL_DIRECT). */
+/* Which kernel FUSG_IMPL_AUTO resolves to for this descriptor (FUSG_IMPL_SMALLCIN, FUSG_IMPL_TCGEN05 or FUSG_IMPL_DIRECT). */
 int fusg_conv2d_select(const fusg_conv_desc *desc);
 /* Diagnostics: the tiling plan of the calling thread's last tcgen05 launch --
  * plan8 = {msub (128-row sub-tiles per CTA tile), pair (cta_group::2), halo (sliding-window A tiles), ksplit (split-K

@@ -155,6 +155,43 @@ CONV_CASES = [
 ]
 
 
+def test_smallcin_streaming_nin(cuda):
+    """FUSG_IMPL_SMALLCIN (the first NiN of each encoder: 6 / 3 real channels stored 16 wide, 1x1): selected automatically,
+    equal to the tensor-core kernel on the same descriptor and to torch on the bf16-rounded operands."""
+    torch = cuda
+    import ctypes as C
+    from future_urban_scene_generation_b200 import _lib
+    from future_urban_scene_generation_b200.vunet.engine import ConvDesc
+    g = torch.Generator(device="cpu").manual_seed(12)
+    for cin, cout, B, H in ((6, 128, 3, 64), (3, 32, 2, 128)):
+        x = torch.randn((B, H, H, cin), generator=g)
+        xin = torch.zeros((B, H, H, 16), dtype=torch.bfloat16, device="cuda")
+        xin[..., :cin] = x.cuda().bfloat16()
+        w = torch.zeros((cout, 1, 64), dtype=torch.bfloat16, device="cuda")
+        w[:, 0, :cin] = (torch.randn((cout, cin), generator=g) / cin ** 0.5).cuda().bfloat16()
+        bias = (torch.randn((cout,), generator=g) * 0.1).cuda()
+        outs = {}
+        for impl in (0, 1):
+            raw = torch.empty((B, H, H, cout), dtype=torch.bfloat16, device="cuda")
+            elu = torch.empty_like(raw)
+            d = ConvDesc()
+            d.in0, d.c0, d.pitch0, d.cphys0, d.cin_real = xin.data_ptr(), 64, 16, 16, cin
+            d.B, d.H, d.W, d.ksize, d.stride = B, H, H, 1, 1
+            d.weight, d.bias, d.cout, d.cout_pad = w.data_ptr(), bias.data_ptr(), cout, cout
+            d.outs[0].ptr, d.outs[1].ptr, d.outs[1].elu = raw.data_ptr(), elu.data_ptr(), 1
+            d.dtype, d.impl = 0, impl
+            if impl == 0:
+                assert _lib.lib().fusg_conv2d_select(C.byref(d)) == 3
+            _lib.check(_lib.lib().fusg_conv2d(C.byref(d), _lib.stream_ptr(torch)), "fusg_conv2d")
+            torch.cuda.synchronize()
+            outs[impl] = (raw.float(), elu.float())
+        ref = torch.einsum("bhwc,oc->bhwo", xin[..., :cin].float(), w[:, 0, :cin].float()) + bias
+        for impl in (0, 1):
+            assert (outs[impl][0] - ref).abs().max().item() < 1.0 / 128 * max(1.0, ref.abs().max().item())
+            assert (outs[impl][1] - torch.nn.functional.elu(outs[impl][0])).abs().max().item() < 1.0 / 128
+        assert (outs[0][0] - outs[1][0]).abs().max().item() < 1.0 / 64 * max(1.0, ref.abs().max().item())
+
+
 # the kernel variant a case is named after must really be the one that ran (fusg_conv2d_last_plan)
 EXPECTED_PLAN = {
     "msub2_wide": {"msub": 2, "halo": 1, "pair": 1},
