@@ -21,16 +21,16 @@ wr = sum(per[i]["dram__bytes_write.sum"] for i in ids)
 tt = sum(per[i]["gpu__time_duration.sum"] for i in ids)
 top = max(ids, key=lambda i: per[i]["gpu__time_duration.sum"])
 tp = paths[ids.index(top)]
-out = {"source": "profiles/r1_conv_traffic.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum over the "
-                 "112 k_conv_tc launches of one VUNet forward, B=64 (scripts/layer_paths.py)",
+out = {"source": sys.argv[2] + ": ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum over the "
+                 f"{len(ids)} convolution launches of one VUNet forward, B=64 (scripts/layer_paths.py)",
        "launches": len(ids), "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
        "avg_traffic_bytes_per_launch": int((rd + wr) / len(ids)), "kernel_time_ms_sum": tt / 1e6,
        "top_launch": {"layer": tp[0], "dram_read_bytes": int(per[top]["dram__bytes_read.sum"]),
                       "dram_write_bytes": int(per[top]["dram__bytes_write.sum"]), "duration_us": per[top]["gpu__time_duration.sum"] / 1e3,
                       "flops": float(tp[2])}}
 print(json.dumps(out, indent=1))
-with open(sys.argv[2].replace("r1_conv_traffic.csv", "r1_layers_ncu.txt"), "w") as f:
-    f.write(f"{len(ids)} k_conv_tc launches of one forward (B=64), ncu serialised/cold-cache: {tt/1e6:.3f} ms, "
+with open(sys.argv[2].replace("_conv_traffic.csv", "_layers_ncu.txt"), "w") as f:
+    f.write(f"{len(ids)} convolution launches of one forward (B=64), ncu serialised/cold-cache: {tt/1e6:.3f} ms, "
             f"{rd/1e9:.2f} GB read + {wr/1e9:.2f} GB written\n")
     f.write(f"{'layer':46s} {'grid':>5s} {'GFLOP':>9s} {'us':>8s} {'TFLOP/s':>8s} {'GB moved':>9s} {'TB/s':>6s}\n")
     for i, (p, impl, fl) in zip(ids, paths):
