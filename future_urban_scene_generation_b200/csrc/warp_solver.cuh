@@ -43,11 +43,13 @@ struct LaneMem {
     __device__ __forceinline__ double &operator()(int base, int e) const { return p[(base + e) * 32]; }
 };
 
+// OpenCV's hypot: (a > b) ? a * sqrt(1 + (b/a)^2) : (b > 0 ? b * sqrt(1 + (a/b)^2) : 0) on the magnitudes -- written
+// branch-free (larger / smaller magnitude; a == b takes the same values either way), the operations are the same
 __device__ __forceinline__ double sv_hypot(double a, double b) {
     a = fabs(a); b = fabs(b);
-    if (a > b) { b /= a; return a * sqrt(1 + b * b); }
-    if (b > 0) { a /= b; return b * sqrt(1 + a * a); }
-    return 0;
+    const double mx = a > b ? a : b, mn = a > b ? b : a;
+    const double r = mn / (mx > 0 ? mx : 1.0);
+    return mx > 0 ? mx * sqrt(1 + r * r) : 0.0;
 }
 
 __device__ __forceinline__ int nib_get(unsigned long long pk, int i) { return (int)((pk >> (4 * i)) & 15ull); }
@@ -117,7 +119,7 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
     const int maxIters = n * n * 30;
     for (int iters = 0; iters < maxIters; ++iters) {
         int k = 0, l = 1;
-        double p = 0;
+        double p = 0, Wk = 0, Wl = 0;
         if (active) {
             // pivot: first strict maximum over [row candidates k = 0..7, then column candidates i = 1..8]
             double cv[16];
@@ -129,11 +131,11 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
             if (pos < 8) { k = pos; l = nib_get32(indR, pos); }
             else { l = pos - 7; k = nib_get32(indC, l - 1); }
             p = m(SOLVER_A, n * k + l);
+            Wk = m(SOLVER_W, k); Wl = m(SOLVER_W, l);      // (issued with the pivot load, ahead of the vote)
             if (fabs(p) <= DBL_EPSILON) active = false;
         }
         if (!__any_sync(0xffffffffu, active)) break;
         if (active) {
-            const double Wk = m(SOLVER_W, k), Wl = m(SOLVER_W, l);
             const double y = (Wl - Wk) * 0.5;
             double t = fabs(y) + sv_hypot(p, y);
             double s = sv_hypot(p, t);
@@ -146,22 +148,25 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
             // rotate rows/columns k and l of the (upper-triangular) matrix: for every i != k, l the pair is
             // (S[i][k], S[i][l]) of the symmetric matrix S, i.e. A[min][max] -- JacobiImpl_'s three loops in one.
             // r0[i] = |new S[i][k]|, r1[i] = |new S[i][l]| stay in registers for the index scans.
-            double r0[n], r1[n];
+            // (all 36 operands are loaded before the first store: the compiler cannot move a shared-memory load above a store
+            // that might alias it, and a load-rotate-store sequence per pair exposes the load latency 18 times per rotation)
+            double r0[n], r1[n], a0[n], b0[n], va[n], vb[n];
+            int e0[n], e1[n];
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                const bool on = i != k && i != l;
-                const int e0 = i < k ? n * i + k : n * k + i;
-                const int e1 = i < l ? n * i + l : n * l + i;
-                const double a0 = m(SOLVER_A, e0), b0 = m(SOLVER_A, e1);
-                const double n0 = a0 * c - b0 * s, n1 = a0 * s + b0 * c;
-                if (on) { m(SOLVER_A, e0) = n0; m(SOLVER_A, e1) = n1; }
-                r0[i] = fabs(n0); r1[i] = fabs(n1);
+                e0[i] = i < k ? n * i + k : n * k + i;
+                e1[i] = i < l ? n * i + l : n * l + i;
+                a0[i] = m(SOLVER_A, e0[i]); b0[i] = m(SOLVER_A, e1[i]);
+                va[i] = m(SOLVER_V, n * k + i); vb[i] = m(SOLVER_V, n * l + i);
             }
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                const double a0 = m(SOLVER_V, n * k + i), b0 = m(SOLVER_V, n * l + i);
-                m(SOLVER_V, n * k + i) = a0 * c - b0 * s;
-                m(SOLVER_V, n * l + i) = a0 * s + b0 * c;
+                const bool on = i != k && i != l;
+                const double n0 = a0[i] * c - b0[i] * s, n1 = a0[i] * s + b0[i] * c;
+                if (on) { m(SOLVER_A, e0[i]) = n0; m(SOLVER_A, e1[i]) = n1; }
+                r0[i] = fabs(n0); r1[i] = fabs(n1);
+                m(SOLVER_V, n * k + i) = va[i] * c - vb[i] * s;
+                m(SOLVER_V, n * l + i) = va[i] * s + vb[i] * c;
             }
             // indR[k]: i > k of S[k][i] (S[k][l] is now 0);  indC[k]: i < k of S[i][k];
             // indR[l]: i > l of S[l][i];                      indC[l]: i < l of S[i][l] (S[k][l] = 0)
