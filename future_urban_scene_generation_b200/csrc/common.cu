@@ -52,24 +52,6 @@ cudaError_t fusg_once_per_device(int slot, size_t size, const std::function<cuda
     return e;
 }
 
-static std::map<std::pair<int, cudaStream_t>, FusgFork> g_forks;
-
-cudaError_t fusg_fork_resources(cudaStream_t caller, FusgFork *out) {
-    const int dev = fusg_current_device();
-    std::lock_guard<std::mutex> lk(g_dev_mutex);
-    auto it = g_forks.find({dev, caller});
-    if (it == g_forks.end()) {
-        FusgFork f;
-        cudaError_t e = cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-        it = g_forks.emplace(std::make_pair(dev, caller), f).first;
-    }
-    *out = it->second;
-    return cudaSuccess;
-}
-
 extern "C" int fusg_version(void) { return 200; }
 extern "C" const char *fusg_last_error(void) { return g_last_error; }
 extern "C" int fusg_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }

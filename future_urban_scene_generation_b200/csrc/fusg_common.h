@@ -17,11 +17,6 @@ int fusg_num_sms();                            // multiprocessor count of the cu
 // A slot that carries a size (dynamic shared memory limit) is re-run when `size` exceeds what was set before.
 #include <functional>
 cudaError_t fusg_once_per_device(int slot, size_t size, const std::function<cudaError_t()> &fn);
-// Helper stream + fork / join events for overlapping two independent kernels of ONE call, cached per (device, caller
-// stream): two host threads driving two streams never share them, and a stream that is being captured into a CUDA graph
-// records the fork / join as graph edges.  The resources live until the process exits.
-struct FusgFork { cudaStream_t side; cudaEvent_t fork, join; };
-cudaError_t fusg_fork_resources(cudaStream_t caller, FusgFork *out);
 #ifdef __CUDACC__
 // Bounded mbarrier waits without a live register in the hot kernels (k_conv_tc sits exactly at its register cap) and without
 // static shared memory (it also sits at the shared-memory cap): the kernel stores its start time (%globaltimer_hi) in a

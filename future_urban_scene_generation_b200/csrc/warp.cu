@@ -34,7 +34,10 @@ namespace fusg {
 struct VisShared {
     int vx[N_KP], vy[N_KP];
     double dist[N_VIS];
+    PolyEdge edge[32];            // the 6 + 6 + 5 x 4 = 32 edges of the seven polygons, polygon after polygon
 };
+// first edge record of polygon p
+__device__ __forceinline__ int vis_edge_base(int p) { return p < 2 ? 6 * p : 12 + 4 * (p - 2); }
 
 constexpr int VIS_WARPS = 4;     // poses per CTA (one warp each; no block-level barriers)
 
@@ -99,15 +102,20 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
         bx0 = max(bx0, 0); bx1 = min(bx1, W - 1);
         by0 = max(by0, 0); by1 = min(by1, H - 1);
         const int w0 = bx0 >> 5, w1 = bx1 >> 5;
+        // row-independent part of the 32 polygon edges, one lane each (edge i of a polygon runs from vertex i-1 to vertex i)
+        {
+            const int p = lane < 12 ? lane / 6 : 2 + (lane - 12) / 4;
+            const int i = lane - vis_edge_base(p), n = c_plane_n[p];
+            const int ka = c_plane_kp[p][i == 0 ? n - 1 : i - 1], kb = c_plane_kp[p][i];
+            PolyEdge e;
+            poly_edge_setup(sm.vx[ka], sm.vy[ka], sm.vx[kb], sm.vy[kb], H, W, e);
+            sm.edge[lane] = e;
+        }
+        __syncwarp();
         for (int y = by0 + lane; y <= by1; y += 32) {
             int lo[N_VIS][MAX_RANGES], hi[N_VIS][MAX_RANGES], rc[N_VIS];
 #pragma unroll 1
-            for (int p = 0; p < N_VIS; ++p) {
-                int px[6], py[6];
-                const int n = c_plane_n[p];
-                for (int k = 0; k < n; ++k) { px[k] = sm.vx[c_plane_kp[p][k]]; py[k] = sm.vy[c_plane_kp[p][k]]; }
-                rc[p] = poly_row_ranges(px, py, n, y, H, W, lo[p], hi[p]);
-            }
+            for (int p = 0; p < N_VIS; ++p) rc[p] = poly_row_ranges_edges(sm.edge + vis_edge_base(p), c_plane_n[p], y, W, lo[p], hi[p]);
             for (int w = w0; w <= w1; ++w) {
                 unsigned bits[N_VIS];
 #pragma unroll
@@ -151,6 +159,15 @@ __global__ void __launch_bounds__(VIS_WARPS * 32) k_visibility(const double *__r
 // list order does not affect results.
 // workspace layout per crop: Minv[5][9] f64 (inverse maps indexed by SOURCE plane i)
 // ============================================================================================
+// What the gather needs to bound the destination region of a solved (crop, source plane): the forward image of the source
+// polygon under H12 and how far a 2-px source step can move in the destination.  Written by k_solve, whose lane holds the
+// point set and H12 in registers anyway (in the gather this was a serial section of one thread per plane).
+struct PlaneRec {
+    float fwdx[6], fwdy[6];       // destination pixels of the source polygon's vertices
+    float pad;                    // 1.5 * sqrt(2) * (reach of a 2-px source step, worst vertex) + 1
+    int ok;                       // 0: horizon through the polygon / absurd magnification -> bbox spans only
+};
+
 __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
                                                     const uint8_t *__restrict__ vis, int8_t *__restrict__ plane_j, double *__restrict__ H12,
                                                     double *__restrict__ Minv, int *__restrict__ counters, int *__restrict__ list6,
@@ -178,7 +195,7 @@ __global__ void __launch_bounds__(256) k_plane_gate(const int32_t *__restrict__ 
 __global__ void __launch_bounds__(32) k_solve(const int32_t *__restrict__ src_kp, const int32_t *__restrict__ dst_kp,
                                               int8_t *__restrict__ plane_j, double *__restrict__ H12, double *__restrict__ Minv,
                                               const int *__restrict__ counters, const int *__restrict__ list6,
-                                              const int *__restrict__ list4, int blocks6, int lanes) {
+                                              const int *__restrict__ list4, PlaneRec *__restrict__ recs, int blocks6, int lanes) {
     extern __shared__ double solver_smem[];
     const int lane = threadIdx.x;
     const bool six = (int)blockIdx.x < blocks6;
@@ -216,6 +233,37 @@ __global__ void __launch_bounds__(32) k_solve(const int32_t *__restrict__ src_kp
     if (H12) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) H12[9 * t + k] = good ? Hm[k] : 0.0;
+    }
+    if (recs && good) {
+        // forward image of the vertices and of 2-px steps away from them (any accuracy better than a pixel will do)
+        // (the vertices are re-read from global memory: a run-time index into ps.Mx / ps.My would move the point set of the
+        // whole solve from registers to local memory)
+        PlaneRec &r = recs[t];
+        int ok = 1;
+        double reach = 0;
+        const int pi = t % N_TEX, pn = c_plane_n[pi];
+        const int32_t *pk = src_kp + 2 * N_KP * (t / N_TEX);
+        const double w0 = Hm[6] * (double)pk[2 * c_plane_kp[pi][0]] + Hm[7] * (double)pk[2 * c_plane_kp[pi][0] + 1] + Hm[8];
+#pragma unroll 1
+        for (int k = 0; k < pn; ++k) {
+            const double vx = (double)pk[2 * c_plane_kp[pi][k]], vy = (double)pk[2 * c_plane_kp[pi][k] + 1];
+            const double wv = Hm[6] * vx + Hm[7] * vy + Hm[8];
+            const double px = (Hm[0] * vx + Hm[1] * vy + Hm[2]) / wv, py = (Hm[3] * vx + Hm[4] * vy + Hm[5]) / wv;
+            if (!(fabs(px) < 1e6) || !(fabs(py) < 1e6)) ok = 0;
+            if (!(wv * w0 > 0)) ok = 0;                     // the projective denominator must keep its sign over the polygon
+            r.fwdx[k] = (float)px; r.fwdy[k] = (float)py;
+#pragma unroll 1
+            for (int d = 0; d < 4; ++d) {                   // where does a 2-px step away from the vertex land?
+                const double ux = vx + (d == 0 ? 2. : d == 1 ? -2. : 0.), uy = vy + (d == 2 ? 2. : d == 3 ? -2. : 0.);
+                const double wu = Hm[6] * ux + Hm[7] * uy + Hm[8];
+                if (!(wu * wv > 0)) { ok = 0; continue; }
+                const double qx = (Hm[0] * ux + Hm[1] * uy + Hm[2]) / wu, qy = (Hm[3] * ux + Hm[4] * uy + Hm[5]) / wu;
+                reach = fmax(reach, fmax(fabs(qx - px), fabs(qy - py)));
+            }
+        }
+        if (!(reach < 64.)) ok = 0;                         // absurd magnification: keep the bbox spans
+        r.pad = (float)(1.5 * 1.4143 * reach + 1.0);        // diagonal source steps, then slack
+        r.ok = ok;
     }
 }
 
@@ -308,9 +356,9 @@ __device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask
 // The gather stage for crops up to 256 x 256.
 //
 // 97 % of the 5 output planes of a crop is zero: a written plane is non-zero only inside the destination polygon, and
-// ~3 of the 5 planes have no writer at all.  So the bytes are written by the simplest possible kernel, k_zero_planes
-// (16-byte grid-stride stores over the whole output: 6.2 TB/s measured, the HBM write roofline), which depends on
-// nothing and is launched first.  k_warp_rows then only visits the rows of each written plane
+// ~3 of the 5 planes have no writer at all.  So the bytes are written by the TMA engine -- bulk stores from a block of
+// zeros in shared memory, issued by k_warp_rows one crop ahead of its gather, so that the HBM write stream runs underneath
+// the per-pixel arithmetic -- and the gather itself only visits the rows of each written plane
 // whose active span is not empty: it stages just the source rows the crop's polygons cover (TMA bulk copy of one
 // contiguous row range into a WIN-row window of shared memory), builds the polygon bit masks of those rows, gathers
 // with cv2's 1/32-px fixed-point bilinear rule and overwrites the rows with 16-byte coalesced stores.
@@ -323,19 +371,13 @@ constexpr int ROW_BYTES_MAX = MAX_HW * 3;          // 768
 constexpr int MASK_WORDS = MAX_HW / 32;            // 8 words per row
 constexpr int WIN_SMALL = 128;                     // source rows of the common-case window (2 CTAs per SM)
 
-__global__ void __launch_bounds__(128) k_zero_planes(int4 *__restrict__ out, size_t n16, uint8_t *__restrict__ tail, int ntail) {
-    const int4 z4 = make_int4(0, 0, 0, 0);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) out[i] = z4;
-    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
-}
-
 struct WarpSmemHeader {
     unsigned long long mbar;
     unsigned wait_start, pad0;                     // kernel start time; must directly follow mbar (mbar_wait)
     double Minv[N_TEX][9];
     int sel[N_TEX];                                // source plane feeding output plane j, or -1
     int polyx[6], polyy[6], polyn;
+    PolyEdge edge[6];                              // row-independent part of the source polygon's edges (poly_edge_setup)
     float fwdx[6], fwdy[6];                        // forward image of the source polygon under H12 (destination pixels)
     int fwd_ok;                                    // 0: a vertex is on / behind the horizon of H12 -> bbox spans only
     float fwd_pad;                                 // how far (destination px) a 2-px step in the source can move, worst vertex, with slack
@@ -371,6 +413,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// shared -> global bulk copy (TMA), tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the `Pending` most recent groups of this thread have completed, writes included
+template <int Pending> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(Pending) : "memory"); }
 
 // conservative x-span of output row y whose source footprint can touch the polygon bbox
 __device__ __forceinline__ void row_active_span(const double *M, int y, int W, const int *bbox, int &xlo, int &xhi) {
@@ -436,13 +486,22 @@ __device__ __forceinline__ void row_polygon_span(const float *fx, const float *f
     xhi = min(W - 1, (int)ceilf(hi + PAD));
 }
 
-// WIN = rows of the source window.  First launch: grid = B, crop = blockIdx.x, oversize crops appended to big_list.
+// bulk zero fill of `bytes` (a multiple of 16) at `dst` (16-byte aligned) as ONE bulk async-group of the calling thread
+constexpr int ZERO_BYTES = 4096;
+constexpr int ZERO_AHEAD = 2;          // crops the fill runs ahead of the gather (per CTA)
+__device__ __forceinline__ void zero_crop(uint8_t *dst, const uint8_t *s_zero, size_t bytes) {
+    for (size_t off = 0; off < bytes; off += ZERO_BYTES) bulk_s2g(dst + off, s_zero, (uint32_t)(bytes - off < (size_t)ZERO_BYTES ? bytes - off : (size_t)ZERO_BYTES));
+    bulk_commit();
+}
+
+// WIN = rows of the source window.  First launch: a persistent grid strides over the crops (and zero-fills their planes one crop
+// ahead, see below); oversize crops are appended to big_list.
 // Second launch (big_list != nullptr as INPUT, `from_list`): a fixed grid strides over the queued crops.
 template <int WIN>
 __global__ void __launch_bounds__(WARP_THREADS, WIN == WIN_SMALL ? 2 : 1)
 k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
-            const double *__restrict__ Minv, uint8_t *__restrict__ warped, int H, int W, int *__restrict__ big_count, int *__restrict__ big_list,
-            int from_list) {
+            const double *__restrict__ Minv, const PlaneRec *__restrict__ recs, uint8_t *__restrict__ warped, int H, int W, int *__restrict__ big_count,
+            int *__restrict__ big_list, int from_list, int n_crops, int zero_fill) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crop_bytes = H * W * 3;
@@ -451,19 +510,44 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
     uint8_t *s_win = smem;                                                            // WIN * 768 bytes
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + WIN * ROW_BYTES_MAX);       // WIN * MASK_WORDS words
     uint8_t *s_rows = reinterpret_cast<uint8_t *>(s_mask + WIN * MASK_WORDS);          // WARP_NWARPS * 768
-    WarpSmemHeader *hd = reinterpret_cast<WarpSmemHeader *>(s_rows + WARP_NWARPS * ROW_BYTES_MAX);
+    uint8_t *s_zero = s_rows + WARP_NWARPS * ROW_BYTES_MAX;                            // ZERO_BYTES of zeros: source of the bulk zero fill
+    WarpSmemHeader *hd = reinterpret_cast<WarpSmemHeader *>(s_zero + ZERO_BYTES);
     if (tid == 0) {
         mbar_init(&hd->mbar, 1);
         fusg_wait_guard_start(&hd->wait_start);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Zero fill of the five output planes (97 % of the output): the TMA engine streams it from a small block of zeros,
+    // ZERO_AHEAD crops AHEAD of the gather -- the fills of this CTA's next crops are in flight while the current crop is computed, so
+    // the HBM write stream (the roofline term of the call) runs underneath the exact per-pixel arithmetic instead of in a
+    // kernel of its own.  Thread 0 owns the bulk groups; before the first row of a crop is stored it waits for that crop's
+    // fill (issued ZERO_AHEAD crops earlier) and the block barrier orders everyone's stores behind it.
+    if (zero_fill) {
+        for (int k = tid; k < ZERO_BYTES / 16; k += WARP_THREADS) reinterpret_cast<int4 *>(s_zero)[k] = make_int4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {                                        // groups 0 .. ZERO_AHEAD-1: this CTA's first crops
+            for (int a = 0; a < ZERO_AHEAD; ++a) {
+                const int it = (int)blockIdx.x + a * (int)gridDim.x;
+                if (it < n_crops) zero_crop(warped + (size_t)it * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes);
+                else bulk_commit();
+            }
+        }
+    }
     uint32_t phase = 0;
-    const int n_items = from_list ? *big_count : (int)gridDim.x;
+    const int n_items = from_list ? *big_count : n_crops;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = from_list ? big_list[item] : item;
         const uint8_t *gsrc = src + (size_t)b * crop_bytes;
         uint8_t *gout = warped + (size_t)b * N_TEX * crop_bytes;
         __syncthreads();                                      // previous item done with the header / window
+        bool zero_pending = false;                            // (thread 0) this crop's fill has not been waited for yet
+        if (zero_fill && tid == 0) {
+            const int nxt = item + ZERO_AHEAD * (int)gridDim.x;
+            if (nxt < n_items) zero_crop(warped + (size_t)nxt * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes);
+            else bulk_commit();                                // (empty group: "all but the ZERO_AHEAD newest" stays this crop's fill)
+            zero_pending = true;
+        }
         if (tid < N_TEX) hd->sel[tid] = -1;
         __syncthreads();
         if (tid == 0) {
@@ -518,57 +602,44 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
             const int i = hd->sel[j];
             if (i < 0) continue;
             __syncthreads();                                  // previous plane done with mask / spans
-            if (tid == 0) {
+            {
+                // polygon of source plane i: vertices and the row-independent part of its edges (one lane per edge), bounding
+                // box, and the destination-side bounds k_solve left in recs
                 const int n = c_plane_n[i];
-                int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
-                for (int k = 0; k < n; ++k) {
-                    const int vx = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2], vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
-                    hd->polyx[k] = vx; hd->polyy[k] = vy;
-                    x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
-                }
-                hd->polyn = n;
-                hd->bbox[0] = x0; hd->bbox[1] = x1; hd->bbox[2] = y0; hd->bbox[3] = y1;
-                // A polygon that leaves the frame is rasterised with cv2's clipped-edge rules, whose mask can set pixels well
-                // away from the ideal polygon (e.g. a run along the border column): only in-frame polygons get the tight spans.
-                const bool inframe = x0 >= 0 && x1 < W && y0 >= 0 && y1 < H;
-                // forward image of the vertices: H12 = inverse of the stored inverse map (any accuracy better than a pixel will do)
-                double Hf[9];
-                invert3(hd->Minv[i], Hf);
-                int ok = 1;
-                double reach = 0;
-                for (int k = 0; k < n; ++k) {
-                    const double vx = hd->polyx[k], vy = hd->polyy[k];
-                    const double wv = Hf[6] * vx + Hf[7] * vy + Hf[8];
-                    const double px = (Hf[0] * vx + Hf[1] * vy + Hf[2]) / wv, py = (Hf[3] * vx + Hf[4] * vy + Hf[5]) / wv;
-                    if (!(fabs(px) < 1e6) || !(fabs(py) < 1e6)) ok = 0;
-                    hd->fwdx[k] = (float)px; hd->fwdy[k] = (float)py;
-                    for (int d = 0; d < 4; ++d) {              // where does a 2-px step away from the vertex land?
-                        const double ux = vx + (d == 0 ? 2. : d == 1 ? -2. : 0.), uy = vy + (d == 2 ? 2. : d == 3 ? -2. : 0.);
-                        const double wu = Hf[6] * ux + Hf[7] * uy + Hf[8];
-                        if (!(wu * wv > 0)) { ok = 0; continue; }
-                        const double qx = (Hf[0] * ux + Hf[1] * uy + Hf[2]) / wu, qy = (Hf[3] * ux + Hf[4] * uy + Hf[5]) / wu;
-                        reach = fmax(reach, fmax(fabs(qx - px), fabs(qy - py)));
+                const int32_t *kp = src_kp + (size_t)b * N_KP * 2;
+                if (tid < n) {
+                    const int ka = c_plane_kp[i][tid == 0 ? n - 1 : tid - 1], kb = c_plane_kp[i][tid];
+                    const int bx = kp[2 * kb], by = kp[2 * kb + 1];
+                    hd->polyx[tid] = bx; hd->polyy[tid] = by;
+                    PolyEdge e;
+                    poly_edge_setup(kp[2 * ka], kp[2 * ka + 1], bx, by, H, W, e);
+                    hd->edge[tid] = e;
+                } else if (tid == 32) {
+                    int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+                    for (int k = 0; k < n; ++k) {
+                        const int vx = kp[2 * c_plane_kp[i][k]], vy = kp[2 * c_plane_kp[i][k] + 1];
+                        x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
                     }
+                    hd->polyn = n;
+                    hd->bbox[0] = x0; hd->bbox[1] = x1; hd->bbox[2] = y0; hd->bbox[3] = y1;
+                    // A polygon that leaves the frame is rasterised with cv2's clipped-edge rules, whose mask can set pixels well
+                    // away from the ideal polygon (e.g. a run along the border column): only in-frame polygons get the tight spans.
+                    const bool inframe = x0 >= 0 && x1 < W && y0 >= 0 && y1 < H;
+                    const PlaneRec &r = recs[(size_t)b * N_TEX + i];
+                    hd->fwd_ok = r.ok && inframe;
+                    hd->fwd_pad = r.pad;
+                } else if (tid >= 64 && tid < 64 + n) {
+                    const PlaneRec &r = recs[(size_t)b * N_TEX + i];
+                    hd->fwdx[tid - 64] = r.fwdx[tid - 64]; hd->fwdy[tid - 64] = r.fwdy[tid - 64];
                 }
-                if (!(reach < 64.) || !inframe) ok = 0;        // absurd magnification / clipped polygon: keep the bbox spans
-                hd->fwd_pad = (float)(1.5 * 1.4143 * reach + 1.0);   // diagonal source steps, then slack
-                // the sign of the projective denominator must not change over the polygon (no horizon through it)
-                const double w0 = Hf[6] * hd->polyx[0] + Hf[7] * hd->polyy[0] + Hf[8];
-                for (int k = 1; k < n; ++k) {
-                    const double wk = Hf[6] * hd->polyx[k] + Hf[7] * hd->polyy[k] + Hf[8];
-                    if (!(wk * w0 > 0)) ok = 0;
-                }
-                hd->fwd_ok = ok;
             }
             __syncthreads();
             const double *M = hd->Minv[i];
             const int pl_lo = max(hd->bbox[2], 0), pl_hi = min(hd->bbox[3], H - 1);   // rows of THIS plane's polygon (inside the window)
             // polygon bit mask of the plane's source rows + active span of every output row
             for (int y = pl_lo + tid; y <= pl_hi; y += WARP_THREADS) {
-                int px[6], py[6], lo[MAX_RANGES], hi[MAX_RANGES];
-                const int n = hd->polyn;
-                for (int k = 0; k < n; ++k) { px[k] = hd->polyx[k]; py[k] = hd->polyy[k]; }
-                const int rc = poly_row_ranges(px, py, n, y, H, W, lo, hi);
+                int lo[MAX_RANGES], hi[MAX_RANGES];
+                const int rc = poly_row_ranges_edges(hd->edge, hd->polyn, y, W, lo, hi);
 #pragma unroll
                 for (int w = 0; w < MASK_WORDS; ++w) s_mask[(y - win_lo) * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
             }
@@ -583,11 +654,12 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
                 hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
             }
             if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; src_ready = true; }
+            if (zero_pending) { bulk_wait<ZERO_AHEAD>(); zero_pending = false; }      // this crop's zero fill has landed
             __syncthreads();
             uint8_t *oplane = gout + (size_t)j * crop_bytes;
             for (int y = warp; y < H; y += WARP_NWARPS) {
                 const int xlo = hd->span_lo[y], xhi = hd->span_hi[y];
-                if (xlo > xhi) continue;                       // the row stays zero (k_zero_planes)
+                if (xlo > xhi) continue;                       // the row stays zero (bulk fill)
                 uint8_t *orow = oplane + (size_t)y * row_bytes;
                 // zero the staging row, then fill the active 32-pixel groups
                 for (int k = lane; k < (row_bytes + 15) / 16; k += 32) reinterpret_cast<int4 *>(my_row)[k] = z4;
@@ -615,6 +687,7 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
         }
         if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; }          // never leave a bulk copy in flight into the window
     }
+    if (zero_fill && tid == 0) bulk_wait<0>();                 // (a kernel may not exit with bulk stores reading its shared memory)
 }
 
 // ============================================================================================
@@ -783,18 +856,20 @@ static int solver_prepare() {
 }
 // one point set per warp while the warps fit on the device at once (latency of a single solve), up to 32 (throughput)
 static int solver_lanes(long long tasks) {
-    const long long slots = (long long)fusg_num_sms() * 3;         // 3 x 72 KB of scratch per SM
+    const long long slots = (long long)fusg_num_sms() * SOLVER_WARPS_PER_SM;         // 4 x 52 KB of scratch per SM
     long long l = (tasks + slots - 1) / slots;
     return (int)(l < 1 ? 1 : (l > 32 ? 32 : l));
 }
 
 static size_t warp_smem_bytes(int win) {
-    return (size_t)win * ROW_BYTES_MAX + (size_t)win * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + sizeof(WarpSmemHeader) + 128;
+    return (size_t)win * ROW_BYTES_MAX + (size_t)win * MASK_WORDS * 4 + (size_t)WARP_NWARPS * ROW_BYTES_MAX + ZERO_BYTES + sizeof(WarpSmemHeader) + 128;
 }
 
 // workspace: Minv [B,5,9] f64 | counters [4] i32 (6-point tasks, 4-point tasks, big-window crops, -) | list6 [2B] i32 | list4 [3B] i32 |
-//            big_list [B] i32 | (frames > 256: plane bit masks [B,5,H,ceil(W/32)] u32)
-static size_t warp_ws_base(int B) { return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 6 * (size_t)B) * sizeof(int); }
+//            big_list [B] i32 | PlaneRec [B,5] (56 bytes each) | (frames > 256: plane bit masks [B,5,H,ceil(W/32)] u32)
+static size_t warp_ws_base(int B) {
+    return (size_t)B * N_TEX * 9 * sizeof(double) + (size_t)(4 + 6 * (size_t)B) * sizeof(int) + (size_t)B * N_TEX * sizeof(PlaneRec);
+}
 
 extern "C" size_t fusg_warp_workspace_bytes(int B) { return B <= 0 ? 0 : warp_ws_base(B); }
 
@@ -856,6 +931,7 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     double *Minv = reinterpret_cast<double *>(workspace);
     int *counters = reinterpret_cast<int *>(Minv + (size_t)B * N_TEX * 9);
     int *list6 = counters + 4, *list4 = list6 + 2 * (size_t)B, *big_list = list4 + 3 * (size_t)B;
+    PlaneRec *recs = reinterpret_cast<PlaneRec *>(big_list + (size_t)B);
     if (!frame_path) {
         if (fusg_once_per_device(1, 0, [] {
                 cudaError_t e = cudaFuncSetAttribute(k_warp_rows<WIN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(WIN_SMALL));
@@ -867,49 +943,31 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
     k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
     fusg_count_launch(2);
-    // The zero fill of all five planes depends on nothing, and the solves (latency-bound: a few warps per SM, almost no memory
-    // traffic) leave the memory system idle: fork the fill onto a helper stream HERE, next to k_solve, and join before the
-    // gather.  (Forked from the very start it also overlapped k_visibility, which it slowed down by more than it gained:
-    // 14.4 vs 12.3 ms for 16k crops.)
-    FusgFork fk;
-    cudaStream_t zs = st;
-    if (!frame_path) {
-        static const int no_fork = getenv("FUSG_WARP_NO_FORK") ? 1 : 0;               // debug / A-B timing: fill inline on the caller's stream
-        if (!no_fork) {
-            if (fusg_record_cuda(fusg_fork_resources(st, &fk)) != FUSG_OK || fusg_record_cuda(cudaEventRecord(fk.fork, st)) != FUSG_OK ||
-                fusg_record_cuda(cudaStreamWaitEvent(fk.side, fk.fork, 0)) != FUSG_OK)
-                return FUSG_ERR_CUDA;
-            zs = fk.side;
-        }
-        const size_t total = (size_t)B * N_TEX * H * W * 3;
-        const size_t head = (16 - (reinterpret_cast<uintptr_t>(warped) & 15)) & 15;       // (torch allocations are 512-byte aligned: 0)
-        if (head == 0) {
-            const size_t n16 = total / 16;
-            const size_t want = (n16 + 127) / 128;
-            const int zgrid = (int)(want < (size_t)fusg_num_sms() * 16 ? want : (size_t)fusg_num_sms() * 16);
-            k_zero_planes<<<zgrid, 128, 0, zs>>>(reinterpret_cast<int4 *>(warped), n16, warped + n16 * 16, (int)(total - n16 * 16));
-        } else if (fusg_record_cuda(cudaMemsetAsync(warped, 0, total, zs)) != FUSG_OK) {
-            return FUSG_ERR_CUDA;
-        }
+    // The zero fill of the five planes (97 % of the output bytes) rides inside k_warp_rows as TMA bulk stores issued one crop
+    // ahead of the gather (see the kernel); only outputs that are not 16-byte granular are cleared by a memset up front.
+    const size_t out_crop_bytes = (size_t)N_TEX * H * W * 3;
+    const bool bulk_zero = !frame_path && out_crop_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(warped) & 15) == 0;
+    if (!frame_path && !bulk_zero) {
+        if (fusg_record_cuda(cudaMemsetAsync(warped, 0, (size_t)B * out_crop_bytes, st)) != FUSG_OK) return FUSG_ERR_CUDA;
         fusg_count_launch(1);
-        if (zs != st && fusg_record_cuda(cudaEventRecord(fk.join, zs)) != FUSG_OK) return FUSG_ERR_CUDA;
     }
     {
         if (solver_prepare() != FUSG_OK) return FUSG_ERR_CUDA;
         // 32 point sets per warp whatever the batch: the lanes of a warp run in lock step, so a fuller warp costs no
-        // latency, and the fewest possible SMs lose 72 KB of shared memory to a solver warp (the VUNet convolutions of the
+        // latency, and the fewest possible SMs lose 52 KB of shared memory to a solver warp (the VUNet convolutions of the
         // same step want all of it); the grid covers the worst case, warps beyond the task count exit at once
         const int lanes = 32;
         const int blocks6 = (2 * B + lanes - 1) / lanes, blocks4 = (3 * B + lanes - 1) / lanes;
-        k_solve<<<blocks6 + blocks4, 32, SOLVER_SMEM_BYTES, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4, blocks6, lanes);
+        k_solve<<<blocks6 + blocks4, 32, SOLVER_SMEM_BYTES, st>>>(src_kp, dst_kp, plane_j, H12, Minv, counters, list6, list4, frame_path ? nullptr : recs, blocks6, lanes);
         fusg_count_launch(1);
     }
     if (!frame_path) {
-        if (zs != st && fusg_record_cuda(cudaStreamWaitEvent(st, fk.join, 0)) != FUSG_OK) return FUSG_ERR_CUDA;
-        k_warp_rows<WIN_SMALL><<<B, WARP_THREADS, warp_smem_bytes(WIN_SMALL), st>>>(src, src_kp, plane_j, Minv, warped, H, W, counters + 2, big_list, 0);
+        // persistent: two CTAs per SM stride over the crops
+        const int grid = B < 2 * fusg_num_sms() ? B : 2 * fusg_num_sms();
+        k_warp_rows<WIN_SMALL><<<grid, WARP_THREADS, warp_smem_bytes(WIN_SMALL), st>>>(src, src_kp, plane_j, Minv, recs, warped, H, W, counters + 2, big_list, 0, B, bulk_zero ? 1 : 0);
         // crops whose polygons span more than WIN_SMALL source rows (a vehicle filling the crop): full-height window
         const int bgrid = B < fusg_num_sms() ? B : fusg_num_sms();
-        k_warp_rows<MAX_HW><<<bgrid, WARP_THREADS, warp_smem_bytes(MAX_HW), st>>>(src, src_kp, plane_j, Minv, warped, H, W, counters + 2, big_list, 1);
+        k_warp_rows<MAX_HW><<<bgrid, WARP_THREADS, warp_smem_bytes(MAX_HW), st>>>(src, src_kp, plane_j, Minv, recs, warped, H, W, counters + 2, big_list, 1, B, 0);
         fusg_count_launch(2);
     } else {
         const int words = (W + 31) / 32;

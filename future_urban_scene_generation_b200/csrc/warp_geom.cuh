@@ -156,6 +156,89 @@ __device__ __forceinline__ int poly_row_ranges(const int *px, const int *py, int
     return cnt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same coverage in two steps for the hot kernels, which evaluate MANY rows of one polygon: everything about an
+// edge that does not depend on the row -- clipLine, the sorted end points of the outline run, the 16.16 slope of the
+// interior crossing (a 64-bit division) -- is computed once per edge (poly_edge_setup, one lane per edge), and a row
+// only pays for range tests, the Bresenham closed form (one or two 32-bit unsigned divisions: every numerator is
+// non-negative) and one 64-bit multiply-add per crossing edge.  Integer operation for operation the same results as
+// poly_row_ranges (tests/test_warp_gpu.py compares k_visibility / the gather, which use this form, against the oracle).
+// ---------------------------------------------------------------------------------------------
+struct PolyEdge {
+    int sx, sy;          // left end point of the clipped segment (outline run)
+    int ddx, dys;        // ex - sx >= 0, ey - sy
+    int ymin, ymax;      // rows of the outline run (ymin > ymax: the segment is not drawn)
+    int yt, yb;          // rows [yt, yb) where the edge is an interior crossing (yt == yb: horizontal edge)
+    long long x0, dxf;   // 16.16 crossing at row yt, increment per row
+};
+
+// edge from vertex a to vertex b of a polygon on an H x W canvas
+__device__ __forceinline__ void poly_edge_setup(int ax, int ay, int bx, int by, int H, int W, PolyEdge &e) {
+    long long t0x = ax, t0y = ay, t1x = bx, t1y = by;
+    const bool outside = (unsigned)ax >= (unsigned)W || (unsigned)bx >= (unsigned)W || (unsigned)ay >= (unsigned)H || (unsigned)by >= (unsigned)H;
+    bool drawn = true;
+    if (outside) drawn = clip_line(W, H, t0x, t0y, t1x, t1y);
+    int sx = (int)t0x, sy = (int)t0y, ex = (int)t1x, ey = (int)t1y;
+    if (ex < sx) { const int tx = sx, ty = sy; sx = ex; sy = ey; ex = tx; ey = ty; }
+    e.sx = sx; e.sy = sy; e.ddx = ex - sx; e.dys = ey - sy;
+    e.ymin = drawn ? (sy < ey ? sy : ey) : 1;
+    e.ymax = drawn ? (sy < ey ? ey : sy) : 0;
+    e.yt = e.yb = 0; e.x0 = e.dxf = 0;
+    if (ay != by) {
+        e.yt = ay < by ? ay : by; e.yb = ay < by ? by : ay;
+        long long c0x = (long long)ax * 65536LL, c0y = ay, c1x = (long long)bx * 65536LL, c1y = by;
+        if (outside) {
+            if (t0y != t1y) { c0y = t0y; c1y = t1y; }
+            c0x = t0x * 65536LL; c1x = t1x * 65536LL;
+        }
+        const long long dxf = (c1x - c0x) / (c1y - c0y);
+        e.dxf = dxf;
+        e.x0 = ay < by ? c0x + ((long long)ay - c0y) * dxf : c1x + ((long long)by - c1y) * dxf;
+    }
+}
+
+// row y of a polygon whose n edges were prepared by poly_edge_setup (in polygon order): same result as poly_row_ranges
+__device__ __forceinline__ int poly_row_ranges_edges(const PolyEdge *ed, int n, int y, int W, int *lo, int *hi) {
+    int cnt = 0;
+    long long xs[6];
+    int na = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const PolyEdge &e = ed[i];
+        if (y >= e.ymin && y <= e.ymax) {
+            const unsigned ddx = (unsigned)e.ddx, ddy = (unsigned)(e.dys < 0 ? -e.dys : e.dys);
+            const unsigned cy = (unsigned)(y > e.sy ? y - e.sy : e.sy - y);
+            int l, h;
+            if (ddy > ddx) {
+                l = h = e.sx + (int)((2u * ddx * cy + ddy - 1u) / (2u * ddy));
+            } else if (ddy == 0) {
+                l = e.sx; h = e.sx + (int)ddx;
+            } else {
+                const unsigned il = cy == 0 ? 0u : (2u * ddx * cy - ddx + 2u * ddy) / (2u * ddy);
+                const unsigned ih = cy == ddy ? ddx : (2u * ddx * (cy + 1u) - ddx + 2u * ddy) / (2u * ddy) - 1u;
+                l = e.sx + (int)il; h = e.sx + (int)ih;
+            }
+            lo[cnt] = l; hi[cnt] = h; ++cnt;
+        }
+        if (y >= e.yt && y < e.yb) xs[na++] = e.x0 + (long long)(y - e.yt) * e.dxf;
+    }
+    for (int i = 1; i < na; ++i) {
+        long long v = xs[i];
+        int k = i - 1;
+        while (k >= 0 && xs[k] > v) { xs[k + 1] = xs[k]; --k; }
+        xs[k + 1] = v;
+    }
+    for (int k = 0; k + 1 < na; k += 2) {
+        long long l = (xs[k] + 65535LL) >> 16, h = xs[k + 1] >> 16;
+        if (l < W && h >= 0) {
+            if (l < 0) l = 0;
+            if (h >= W) h = W - 1;
+            if (l <= h) { lo[cnt] = (int)l; hi[cnt] = (int)h; ++cnt; }
+        }
+    }
+    return cnt;
+}
+
 // bits of 32-pixel word `w` (pixels 32w..32w+31, bit i = pixel 32w+i) covered by the ranges
 __device__ __forceinline__ unsigned ranges_word(const int *lo, const int *hi, int cnt, int w) {
     unsigned bits = 0;

@@ -26,17 +26,27 @@
 
 namespace fusg {
 
-// per-warp scratch, in doubles per lane
-constexpr int SOLVER_A = 0;                    // 81: Jacobi matrix (destroyed)
-constexpr int SOLVER_V = 81;                   // 81: eigenvectors (rows)
-constexpr int SOLVER_W = 162;                  // 9 : eigenvalues
-constexpr int SOLVER_N = 171;                  // 81: LM normal matrix J^T J
-constexpr int SOLVER_v = 252;                  // 9 : J^T r
-constexpr int SOLVER_x = 261;                  // 9 : current parameters
-constexpr int SOLVER_xd = 270;                 // 9 : trial parameters
-constexpr int SOLVER_D = 279;                  // 9 : diag(J^T J) of the first iterate
-constexpr int SOLVER_DOUBLES = 288;            // per lane
-constexpr int SOLVER_SMEM_BYTES = SOLVER_DOUBLES * 32 * 8;      // 73,728 B per warp
+// per-warp scratch, in doubles per lane.  JacobiImpl_ only ever touches the upper triangle of its (symmetric) input and keeps
+// the diagonal in W, and J^T J is symmetric: both are stored packed, which is what lets FOUR solver warps share an SM
+// (4 x 52 KB; with full 9x9 matrices it was three, and the 547 six-point warps of a 16k-crop batch needed two waves).
+constexpr int SOLVER_V = 0;                    // 81: eigenvectors (rows)
+constexpr int SOLVER_A = 81;                   // 36: Jacobi matrix, strict upper triangle: A[r][c], r < c, at tri_T(r) + c (destroyed)
+constexpr int SOLVER_W = 117;                  // 9 : eigenvalues; on entry of sv_jacobi the diagonal of the matrix
+constexpr int SOLVER_N = 126;                  // 45: LM normal matrix J^T J, upper triangle incl. diagonal (sym_idx)
+constexpr int SOLVER_v = 171;                  // 9 : J^T r
+constexpr int SOLVER_x = 180;                  // 9 : current parameters
+constexpr int SOLVER_xd = 189;                 // 9 : trial parameters
+constexpr int SOLVER_D = 198;                  // 9 : diag(J^T J) of the first iterate
+constexpr int SOLVER_DOUBLES = 207;            // per lane
+constexpr int SOLVER_SMEM_BYTES = SOLVER_DOUBLES * 32 * 8;      // 52,992 B per warp
+constexpr int SOLVER_WARPS_PER_SM = 4;
+
+// strict upper triangle of a 9x9 matrix, row-major: element (r, c), r < c, lives at tri_T(r) + c.  (r == c == 0 maps to -1:
+// SOLVER_A is not the first block, so the unconditional loads of the branch-free rotation stay inside the allocation.)
+__host__ __device__ constexpr int tri_T(int r) { return (r * (15 - r)) / 2 - 1; }
+__device__ __forceinline__ int tri_Td(int r) { return (int)((unsigned)(r * (15 - r)) >> 1) - 1; }       // run-time r in 0..8
+// upper triangle incl. diagonal of a symmetric 9x9 matrix
+__host__ __device__ constexpr int sym_idx(int i, int j) { return i <= j ? i * 9 - (i * (i - 1)) / 2 + (j - i) : j * 9 - (j * (j - 1)) / 2 + (i - j); }
 
 struct LaneMem {
     double *p;                                  // already offset by the lane
@@ -87,18 +97,19 @@ __device__ __forceinline__ int first_max16(const double *v) {
 __device__ __forceinline__ int sv_row_max(const LaneMem &m, int k) {
     double v[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) v[i] = i > k ? fabs(m(SOLVER_A, 9 * k + i)) : -1.0;
+    for (int i = 0; i < 9; ++i) v[i] = i > k ? fabs(m(SOLVER_A, tri_T(k) + i)) : -1.0;
     return first_max9(v);
 }
 // index of the first maximum of |A[i][k]|, i = 0..k-1 (indC[k]); k >= 1
 __device__ __forceinline__ int sv_col_max(const LaneMem &m, int k) {
     double v[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) v[i] = i < k ? fabs(m(SOLVER_A, 9 * i + k)) : -1.0;
+    for (int i = 0; i < 9; ++i) v[i] = i < k ? fabs(m(SOLVER_A, tri_T(i) + k)) : -1.0;
     return first_max9(v);
 }
 
-// cv::eigen (JacobiImpl_, n = 9) on A -> W (sorted descending), V (rows, NOT permuted), perm = row of V holding
+// cv::eigen (JacobiImpl_, n = 9) on the matrix whose strict upper triangle is in A and whose diagonal is in W
+// -> W (sorted descending), V (rows, NOT permuted), perm = row of V holding
 // eigenvector i (nibble-packed).  `active`: lanes without a job skip the sweep but take part in the warp votes.
 // The dependent chain of one rotation is what bounds a solve (~1150 rotations in sequence), so: the pivot search and
 // the four index scans are depth-4 trees, and the scans run on the freshly rotated values still in registers (the
@@ -111,7 +122,6 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
         for (int e = 0; e < n * n; ++e) m(SOLVER_V, e) = (e / n == e % n) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < n; ++k) {
-            m(SOLVER_W, k) = m(SOLVER_A, (n + 1) * k);
             if (k < n - 1) indR = nib_set32(indR, k, sv_row_max(m, k));
             if (k > 0) indC = nib_set32(indC, k - 1, sv_col_max(m, k));
         }
@@ -124,13 +134,13 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
             // pivot: first strict maximum over [row candidates k = 0..7, then column candidates i = 1..8]
             double cv[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cv[i] = fabs(m(SOLVER_A, n * i + nib_get32(indR, i)));
+            for (int i = 0; i < 8; ++i) cv[i] = fabs(m(SOLVER_A, tri_T(i) + nib_get32(indR, i)));
 #pragma unroll
-            for (int i = 1; i < 9; ++i) cv[7 + i] = fabs(m(SOLVER_A, n * nib_get32(indC, i - 1) + i));
+            for (int i = 1; i < 9; ++i) cv[7 + i] = fabs(m(SOLVER_A, tri_Td(nib_get32(indC, i - 1)) + i));
             const int pos = first_max16(cv);
             if (pos < 8) { k = pos; l = nib_get32(indR, pos); }
             else { l = pos - 7; k = nib_get32(indC, l - 1); }
-            p = m(SOLVER_A, n * k + l);
+            p = m(SOLVER_A, tri_Td(k) + l);
             Wk = m(SOLVER_W, k); Wl = m(SOLVER_W, l);      // (issued with the pivot load, ahead of the vote)
             if (fabs(p) <= DBL_EPSILON) active = false;
         }
@@ -142,7 +152,8 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
             const double c = t / s;
             s = p / s; t = (p / t) * p;
             if (y < 0) { s = -s; t = -t; }
-            m(SOLVER_A, n * k + l) = 0;
+            const int Tk = tri_Td(k), Tl = tri_Td(l);
+            m(SOLVER_A, Tk + l) = 0;
             m(SOLVER_W, k) = Wk - t;
             m(SOLVER_W, l) = Wl + t;
             // rotate rows/columns k and l of the (upper-triangular) matrix: for every i != k, l the pair is
@@ -154,8 +165,8 @@ __device__ inline unsigned long long sv_jacobi(const LaneMem &m, bool active) {
             int e0[n], e1[n];
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                e0[i] = i < k ? n * i + k : n * k + i;
-                e1[i] = i < l ? n * i + l : n * l + i;
+                e0[i] = i < k ? tri_T(i) + k : Tk + i;      // (i == k / i == l: some other valid slot, loaded but never stored)
+                e1[i] = i < l ? tri_T(i) + l : Tl + i;
                 a0[i] = m(SOLVER_A, e0[i]); b0[i] = m(SOLVER_A, e1[i]);
                 va[i] = m(SOLVER_V, n * k + i); vb[i] = m(SOLVER_V, n * l + i);
             }
@@ -296,7 +307,7 @@ __device__ __forceinline__ double sv_residual(const LaneMem &m, const PointSet &
     double vacc[lx][4];
     if (normal) {
 #pragma unroll
-        for (int e = 0; e < lx * lx; ++e) m(SOLVER_N, e) = 0;
+        for (int e = 0; e < 45; ++e) m(SOLVER_N, e) = 0;
 #pragma unroll
         for (int i = 0; i < lx; ++i) vacc[i][0] = vacc[i][1] = vacc[i][2] = vacc[i][3] = 0;
     }
@@ -319,10 +330,10 @@ __device__ __forceinline__ double sv_residual(const LaneMem &m, const PointSet &
                 for (int i = 0; i < lx; ++i)
 #pragma unroll
                     for (int j = i; j < lx; ++j) {
-                        double a = m(SOLVER_N, i * lx + j);
+                        double a = m(SOLVER_N, sym_idx(i, j));
                         a += J0[i] * J0[j];
                         a += J1[i] * J1[j];
-                        m(SOLVER_N, i * lx + j) = a;
+                        m(SOLVER_N, sym_idx(i, j)) = a;
                     }
                 // rows 2*pt and 2*pt+1 of J go to accumulator (row & 3); the tail rows of a 10-row system to accumulator 0
 #pragma unroll
@@ -336,11 +347,7 @@ __device__ __forceinline__ double sv_residual(const LaneMem &m, const PointSet &
     }
     if (normal) {
 #pragma unroll
-        for (int i = 0; i < lx; ++i) {
-#pragma unroll
-            for (int j = 0; j < i; ++j) m(SOLVER_N, i * lx + j) = m(SOLVER_N, j * lx + i);
-            m(SOLVER_v, i) = ((vacc[i][0] + vacc[i][1]) + vacc[i][2]) + vacc[i][3];
-        }
+        for (int i = 0; i < lx; ++i) m(SOLVER_v, i) = ((vacc[i][0] + vacc[i][1]) + vacc[i][2]) + vacc[i][3];     // (N's lower triangle is the mirror: sym_idx)
     }
     return S;
 }
@@ -377,7 +384,9 @@ __device__ inline bool sv_find_homography(const LaneMem &m, const PointSet &ps, 
         phase = DLT;
         // L^T L, upper triangle accumulated point by point (fundam.cpp runKernel), then mirrored
 #pragma unroll
-        for (int e = 0; e < 81; ++e) m(SOLVER_A, e) = 0;
+        for (int e = 0; e < 36; ++e) m(SOLVER_A, e) = 0;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) m(SOLVER_W, e) = 0;
 #pragma unroll
         for (int pt = 0; pt < 6; ++pt) {
             if (pt < ps.count) {
@@ -388,13 +397,12 @@ __device__ inline bool sv_find_homography(const LaneMem &m, const PointSet &ps, 
 #pragma unroll
                 for (int j = 0; j < 9; ++j)
 #pragma unroll
-                    for (int k = j; k < 9; ++k) m(SOLVER_A, j * 9 + k) += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+                    for (int k = j; k < 9; ++k) {
+                        if (k == j) m(SOLVER_W, j) += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+                        else m(SOLVER_A, tri_T(j) + k) += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+                    }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-#pragma unroll
-            for (int k = 0; k < j; ++k) m(SOLVER_A, j * 9 + k) = m(SOLVER_A, k * 9 + j);
     }
     // LM registers that persist across Jacobi jobs
     double S = 0, lambda = 1, lc = 0.75, Sd = 0, nu = 0, nd = 0, rinf = 0;
@@ -440,7 +448,7 @@ __device__ inline bool sv_find_homography(const LaneMem &m, const PointSet &ps, 
                 // LMSolverImpl::run prologue
                 S = sv_residual(m, ps, x0, true, rinf);
 #pragma unroll
-                for (int i = 0; i < lx; ++i) m(SOLVER_D, i) = m(SOLVER_N, i * lx + i);
+                for (int i = 0; i < lx; ++i) m(SOLVER_D, i) = m(SOLVER_N, sym_idx(i, i));
                 lambda = 1; lc = 0.75; iter = 0;
                 phase = SOLVE;
             }
@@ -464,12 +472,12 @@ __device__ inline bool sv_find_homography(const LaneMem &m, const PointSet &ps, 
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k += 4) {
-                    s0 += m(SOLVER_N, i * lx + k) * d[k];
-                    s1 += m(SOLVER_N, i * lx + k + 1) * d[k + 1];
-                    s2 += m(SOLVER_N, i * lx + k + 2) * d[k + 2];
-                    s3 += m(SOLVER_N, i * lx + k + 3) * d[k + 3];
+                    s0 += m(SOLVER_N, sym_idx(i, k)) * d[k];
+                    s1 += m(SOLVER_N, sym_idx(i, k + 1)) * d[k + 1];
+                    s2 += m(SOLVER_N, sym_idx(i, k + 2)) * d[k + 2];
+                    s3 += m(SOLVER_N, sym_idx(i, k + 3)) * d[k + 3];
                 }
-                s0 += m(SOLVER_N, i * lx + 8) * d[8];
+                s0 += m(SOLVER_N, sym_idx(i, 8)) * d[8];
                 td[i] = -1. * (((s0 + s1) + s2) + s3) + 2. * vv[i];
             }
             const double dS = sv_dot9(d, td);
@@ -485,7 +493,13 @@ __device__ inline bool sv_find_homography(const LaneMem &m, const PointSet &ps, 
                 if (lambda == 0) {
                     // needs invert(A, DECOMP_EIG): one more Jacobi job on N itself, then the tail below
 #pragma unroll
-                    for (int e = 0; e < lx * lx; ++e) m(SOLVER_A, e) = m(SOLVER_N, e);
+                    for (int i = 0; i < lx; ++i)
+#pragma unroll
+                        for (int j = i; j < lx; ++j) {
+                            const double a = m(SOLVER_N, sym_idx(i, j));
+                            if (i == j) m(SOLVER_W, i) = a;
+                            else m(SOLVER_A, tri_T(i) + j) = a;
+                        }
                     phase = INVERT;
                     finish = false;
                 } else {
@@ -514,11 +528,13 @@ __device__ inline bool sv_find_homography(const LaneMem &m, const PointSet &ps, 
         if (phase == SOLVE) {
             // Ap = N + lambda * D for the next solve
 #pragma unroll
-            for (int e = 0; e < lx * lx; ++e) {
-                double a = m(SOLVER_N, e);
-                if (e / lx == e % lx) a += lambda * m(SOLVER_D, e / lx);
-                m(SOLVER_A, e) = a;
-            }
+            for (int i = 0; i < lx; ++i)
+#pragma unroll
+                for (int j = i; j < lx; ++j) {
+                    const double a = m(SOLVER_N, sym_idx(i, j));
+                    if (i == j) m(SOLVER_W, i) = a + lambda * m(SOLVER_D, i);
+                    else m(SOLVER_A, tri_T(i) + j) = a;
+                }
         }
     }
     if (good) {

@@ -8,8 +8,8 @@ Contract kept (reference: warp_learn/models.py:190-208, run_test.py:74-78, traje
   * `forward(image (B,input_nc,H,W) fp32) -> (B,output_nc,H,W)` tanh-bounded fp32 on the module's device;
     `decode(content)`; `enc_content(image)` and `dec(content)` are callable like the reference's sub-modules.
 Only the configuration the reference ships (norm='inst', nl_layer='relu', n_res >= 1, num_downs >= 1) has kernels; anything
-else raises NotImplementedError.  There is no CPU path.  `get_icn_inputs` (host-side cv2 / PIL packing) is not part of this
-row; the import shim keeps serving the reference's own function.
+else raises NotImplementedError.  There is no CPU path.  The input packing `get_icn_inputs` (warp_learn/models.py:17-56) lives in
+`frame_ops.py` (`get_icn_inputs`, `get_icn_inputs_batch`) and is what the import shim serves.
 """
 import math
 

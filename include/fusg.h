@@ -86,8 +86,8 @@ size_t fusg_warp_workspace_bytes_hw(int B, int H, int W);
  *
  * H, W >= 8.  Up to 256 x 256 the crop is staged in shared memory (the HBM-bound fast path); larger
  * frames (the reference works on 1280 x 720) gather from global memory with the same arithmetic and need
- * fusg_warp_workspace_bytes_hw(B,H,W) of workspace.  Every vertex must lie inside the frame, else that
- * crop's outputs are zero and plane_j = -2 (the reference's clipped-polygon regime is not covered).
+ * fusg_warp_workspace_bytes_hw(B,H,W) of workspace.  Vertices outside the frame are handled like cv2.fillPoly
+ * handles them (clipped edges); only a crop with a vertex beyond +-2^20 px is refused: outputs zero, plane_j = -2.
  */
 int fusg_warp_fused(const uint8_t *src, const int32_t *src_kp, const int32_t *dst_kp,
                     const double *K, const double *E_src, const double *E_dst, const double *kp3d,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     L = _lib.lib()
     assert L.fusg_version() >= 100
-    assert L.fusg_warp_workspace_bytes(3) == 3 * 5 * 9 * 8 + (4 + 6 * 3) * 4      # Minv | counters[4] | list6[2B] | list4[3B] | big_list[B]
+    assert L.fusg_warp_workspace_bytes(3) == 3 * 5 * 9 * 8 + (4 + 6 * 3) * 4 + 3 * 5 * 56   # Minv | counters[4] | list6[2B] | list4[3B] | big_list[B] | PlaneRec[B,5]
     assert L.fusg_kernel_launches() >= 0
 
 
