@@ -357,7 +357,7 @@ __device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask
 //
 // 97 % of the 5 output planes of a crop is zero: a written plane is non-zero only inside the destination polygon, and
 // ~3 of the 5 planes have no writer at all.  So the bytes are written by the TMA engine -- bulk stores from a block of
-// zeros in shared memory, issued by k_warp_rows one crop ahead of its gather, so that the HBM write stream runs underneath
+// zeros in shared memory, issued by k_warp_rows two crops ahead of its gather, so that the HBM write stream runs underneath
 // the per-pixel arithmetic -- and the gather itself only visits the rows of each written plane
 // whose active span is not empty: it stages just the source rows the crop's polygons cover (TMA bulk copy of one
 // contiguous row range into a WIN-row window of shared memory), builds the polygon bit masks of those rows, gathers
@@ -377,6 +377,7 @@ struct WarpSmemHeader {
     double Minv[N_TEX][9];
     int sel[N_TEX];                                // source plane feeding output plane j, or -1
     int polyx[6], polyy[6], polyn;
+    unsigned row_bits[WARP_NWARPS];                // output rows of the current plane with a non-empty span (bit r of word w: row 32w + r)
     PolyEdge edge[6];                              // row-independent part of the source polygon's edges (poly_edge_setup)
     float fwdx[6], fwdy[6];                        // forward image of the source polygon under H12 (destination pixels)
     int fwd_ok;                                    // 0: a vertex is on / behind the horizon of H12 -> bbox spans only
@@ -419,8 +420,25 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all but the `Pending` most recent groups of this thread have completed, writes included
-template <int Pending> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(Pending) : "memory"); }
+// all but the `pending` most recent groups of this thread have completed, writes included
+__device__ __forceinline__ void bulk_wait(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+    }
+}
+constexpr int ZERO_BYTES = 4096;
+constexpr int ZERO_AHEAD = 2;          // crops the fill runs ahead of the gather (per CTA)
+// bulk zero fill of `bytes` (a multiple of 16) at `dst` (16-byte aligned): one bulk async-group of the calling thread,
+// which takes every nsh-th block (share `sh`)
+__device__ __forceinline__ void zero_crop(uint8_t *dst, const uint8_t *s_zero, size_t bytes, int sh, int nsh) {
+    for (size_t off = (size_t)sh * ZERO_BYTES; off < bytes; off += (size_t)nsh * ZERO_BYTES)
+        bulk_s2g(dst + off, s_zero, (uint32_t)(bytes - off < (size_t)ZERO_BYTES ? bytes - off : (size_t)ZERO_BYTES));
+    bulk_commit();
+}
 
 // conservative x-span of output row y whose source footprint can touch the polygon bbox
 __device__ __forceinline__ void row_active_span(const double *M, int y, int W, const int *bbox, int &xlo, int &xhi) {
@@ -486,22 +504,13 @@ __device__ __forceinline__ void row_polygon_span(const float *fx, const float *f
     xhi = min(W - 1, (int)ceilf(hi + PAD));
 }
 
-// bulk zero fill of `bytes` (a multiple of 16) at `dst` (16-byte aligned) as ONE bulk async-group of the calling thread
-constexpr int ZERO_BYTES = 4096;
-constexpr int ZERO_AHEAD = 2;          // crops the fill runs ahead of the gather (per CTA)
-__device__ __forceinline__ void zero_crop(uint8_t *dst, const uint8_t *s_zero, size_t bytes) {
-    for (size_t off = 0; off < bytes; off += ZERO_BYTES) bulk_s2g(dst + off, s_zero, (uint32_t)(bytes - off < (size_t)ZERO_BYTES ? bytes - off : (size_t)ZERO_BYTES));
-    bulk_commit();
-}
-
-// WIN = rows of the source window.  First launch: a persistent grid strides over the crops (and zero-fills their planes one crop
-// ahead, see below); oversize crops are appended to big_list.
+// WIN = rows of the source window.  First launch: a persistent grid strides over the crops; oversize crops are appended to big_list.
 // Second launch (big_list != nullptr as INPUT, `from_list`): a fixed grid strides over the queued crops.
 template <int WIN>
 __global__ void __launch_bounds__(WARP_THREADS, WIN == WIN_SMALL ? 2 : 1)
 k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp, const int8_t *__restrict__ plane_j,
             const double *__restrict__ Minv, const PlaneRec *__restrict__ recs, uint8_t *__restrict__ warped, int H, int W, int *__restrict__ big_count,
-            int *__restrict__ big_list, int from_list, int n_crops, int zero_fill) {
+            int *__restrict__ big_list, int from_list, int n_crops, int zero_ahead) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crop_bytes = H * W * 3;
@@ -517,19 +526,21 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
         fusg_wait_guard_start(&hd->wait_start);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // Zero fill of the five output planes (97 % of the output): the TMA engine streams it from a small block of zeros,
-    // ZERO_AHEAD crops AHEAD of the gather -- the fills of this CTA's next crops are in flight while the current crop is computed, so
-    // the HBM write stream (the roofline term of the call) runs underneath the exact per-pixel arithmetic instead of in a
-    // kernel of its own.  Thread 0 owns the bulk groups; before the first row of a crop is stored it waits for that crop's
-    // fill (issued ZERO_AHEAD crops earlier) and the block barrier orders everyone's stores behind it.
-    if (zero_fill) {
+    // Zero fill of the five output planes (97 % of the output bytes): the TMA engine streams it from a small block of zeros,
+    // `zero_ahead` crops AHEAD of the gather -- the fills of this CTA's next crops are in flight while the current crop is
+    // computed, so most of the HBM write stream (the roofline term of the call) runs underneath the exact per-pixel arithmetic
+    // instead of in a kernel of its own.  Lane 0 of warps 1..7 each issue a seventh of a crop's 240 bulk stores and own those
+    // bulk groups; before the first row of a crop is stored each waits for its share of that crop's fill and the block barrier
+    // orders everyone's stores behind it.  Warp 0 is left out: it runs the crop's prologue meanwhile.
+    const bool filler = zero_ahead > 0 && lane == 0 && warp >= 1;
+    if (zero_ahead > 0) {
         for (int k = tid; k < ZERO_BYTES / 16; k += WARP_THREADS) reinterpret_cast<int4 *>(s_zero)[k] = make_int4(0, 0, 0, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {                                        // groups 0 .. ZERO_AHEAD-1: this CTA's first crops
-            for (int a = 0; a < ZERO_AHEAD; ++a) {
+        if (filler) {
+            for (int a = 0; a < zero_ahead; ++a) {
                 const int it = (int)blockIdx.x + a * (int)gridDim.x;
-                if (it < n_crops) zero_crop(warped + (size_t)it * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes);
+                if (it < n_crops) zero_crop(warped + (size_t)it * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes, warp - 1, WARP_NWARPS - 1);
                 else bulk_commit();
             }
         }
@@ -541,43 +552,60 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
         const uint8_t *gsrc = src + (size_t)b * crop_bytes;
         uint8_t *gout = warped + (size_t)b * N_TEX * crop_bytes;
         __syncthreads();                                      // previous item done with the header / window
-        bool zero_pending = false;                            // (thread 0) this crop's fill has not been waited for yet
-        if (zero_fill && tid == 0) {
-            const int nxt = item + ZERO_AHEAD * (int)gridDim.x;
-            if (nxt < n_items) zero_crop(warped + (size_t)nxt * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes);
-            else bulk_commit();                                // (empty group: "all but the ZERO_AHEAD newest" stays this crop's fill)
+        bool zero_pending = false;
+        if (filler) {
+            const int nxt = item + zero_ahead * (int)gridDim.x;
+            if (nxt < n_items) zero_crop(warped + (size_t)nxt * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes, warp - 1, WARP_NWARPS - 1);
+            else bulk_commit();
             zero_pending = true;
         }
-        if (tid < N_TEX) hd->sel[tid] = -1;
-        __syncthreads();
-        if (tid == 0) {
-            // last writer wins (planes_utils.py:79): ascending i
-            for (int i = 0; i < N_TEX; ++i) {
-                const int j = plane_j[b * N_TEX + i];
-                if (j >= 0) hd->sel[j] = i;
+        if (!from_list && warp == 2 && lane < 8) {
+            // pull the next crop's few hundred bytes of per-crop inputs towards L2: its prologue is a chain of dependent loads
+            // that otherwise waits behind the zero-fill traffic
+            const size_t nb = (size_t)item + gridDim.x;
+            if (nb < (size_t)n_items) {
+                const void *pp = lane == 0 ? (const void *)(plane_j + nb * N_TEX)
+                               : lane == 1 ? (const void *)(src_kp + nb * N_KP * 2)
+                               : lane < 5  ? (const void *)(reinterpret_cast<const uint8_t *>(Minv + nb * N_TEX * 9) + (lane - 2) * 128)
+                                           : (const void *)(reinterpret_cast<const uint8_t *>(recs + nb * N_TEX) + (lane - 5) * 128);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
             }
-            // source rows the selected polygons cover (only there can a mask bit be set)
+        }
+        if (warp == 0) {
+            // which source plane feeds output plane j -- last writer wins (planes_utils.py:79): the largest i with plane_j[i] == j --
+            // and the source rows the selected polygons cover (only there can a mask bit be set); lane = output plane
+            const int pj = lane < N_TEX ? (int)plane_j[b * N_TEX + lane] : -1;
+            int sel = -1;
+#pragma unroll
+            for (int i = 0; i < N_TEX; ++i)
+                if (__shfl_sync(0xffffffffu, pj, i) == lane) sel = i;
             int lo = INT_MAX, hi = INT_MIN;
-            for (int j = 0; j < N_TEX; ++j) {
-                const int i = hd->sel[j];
-                if (i < 0) continue;
-                for (int k = 0; k < c_plane_n[i]; ++k) {
-                    const int vy = src_kp[(b * N_KP + c_plane_kp[i][k]) * 2 + 1];
+            if (lane < N_TEX && sel >= 0) {
+                for (int k = 0; k < c_plane_n[sel]; ++k) {
+                    const int vy = src_kp[(b * N_KP + c_plane_kp[sel][k]) * 2 + 1];
                     lo = min(lo, vy); hi = max(hi, vy);
                 }
             }
-            lo = max(lo, 0); hi = min(hi, H - 1);
-            hd->win_lo = lo; hd->win_hi = hi;
-            hd->skip = 0;
-            if (lo <= hi && hi - lo + 1 > WIN) {
-                hd->skip = 1;
-                big_list[atomicAdd(big_count, 1)] = b;        // (only reachable with WIN == WIN_SMALL: the big window holds any crop)
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            }
+            if (lane < N_TEX) hd->sel[lane] = sel;
+            if (lane == 0) {
+                lo = max(lo, 0); hi = min(hi, H - 1);
+                hd->win_lo = lo; hd->win_hi = hi;
+                hd->skip = 0;
+                if (lo <= hi && hi - lo + 1 > WIN) {
+                    hd->skip = 1;
+                    big_list[atomicAdd(big_count, 1)] = b;    // (only reachable with WIN == WIN_SMALL: the big window holds any crop)
+                }
             }
         }
         if (tid >= 32 && tid < 32 + N_TEX * 9) hd->Minv[0][tid - 32] = Minv[(size_t)b * N_TEX * 9 + (tid - 32)];
         __syncthreads();
         const int win_lo = hd->win_lo, win_hi = hd->win_hi;
-        if (hd->skip || win_lo > win_hi) continue;            // nothing to warp: the planes stay zero
+        if (hd->skip || win_lo > win_hi) continue;            // nothing to warp here: the planes stay zero
         const int win_rows = win_hi - win_lo + 1;
         const uint8_t *gwin = gsrc + (size_t)win_lo * row_bytes;
         const uint32_t win_bytes = (uint32_t)win_rows * row_bytes;
@@ -643,23 +671,33 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
 #pragma unroll
                 for (int w = 0; w < MASK_WORDS; ++w) s_mask[(y - win_lo) * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
             }
-            for (int y = tid; y < H; y += WARP_THREADS) {
-                int xlo, xhi;
-                row_active_span(M, y, W, hd->bbox, xlo, xhi);
-                if (hd->fwd_ok && xlo <= xhi) {
-                    int plo, phi;
-                    row_polygon_span(hd->fwdx, hd->fwdy, hd->polyn, hd->fwd_pad, y, W, plo, phi);
-                    xlo = max(xlo, plo); xhi = min(xhi, phi);
+            {   // thread = output row (H <= 256 = WARP_THREADS on this path); the rows with a non-empty span as one bit word per warp
+                const int y = tid;
+                int xlo = 1, xhi = 0;
+                if (y < H) {
+                    row_active_span(M, y, W, hd->bbox, xlo, xhi);
+                    if (hd->fwd_ok && xlo <= xhi) {
+                        int plo, phi;
+                        row_polygon_span(hd->fwdx, hd->fwdy, hd->polyn, hd->fwd_pad, y, W, plo, phi);
+                        xlo = max(xlo, plo); xhi = min(xhi, phi);
+                    }
+                    hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
                 }
-                hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
+                const unsigned act = __ballot_sync(0xffffffffu, xlo <= xhi);
+                if (lane == 0) hd->row_bits[warp] = act;
             }
             if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; src_ready = true; }
-            if (zero_pending) { bulk_wait<ZERO_AHEAD>(); zero_pending = false; }      // this crop's zero fill has landed
+            if (zero_pending) { bulk_wait(zero_ahead); zero_pending = false; }
             __syncthreads();
             uint8_t *oplane = gout + (size_t)j * crop_bytes;
-            for (int y = warp; y < H; y += WARP_NWARPS) {
+            // the ACTIVE rows are dealt round-robin to the warps (neighbouring rows have similar spans; a static share of all rows
+            // left warps idle at the barrier below, a shared-memory ticket per row cost more than it balanced)
+            int ridx = 0;
+            for (int ww = 0; ww < WARP_NWARPS; ++ww)
+            for (unsigned rbits = hd->row_bits[ww]; rbits; rbits &= rbits - 1) {
+                if ((ridx++ & (WARP_NWARPS - 1)) != warp) continue;
+                const int y = ww * 32 + __ffs(rbits) - 1;
                 const int xlo = hd->span_lo[y], xhi = hd->span_hi[y];
-                if (xlo > xhi) continue;                       // the row stays zero (bulk fill)
                 uint8_t *orow = oplane + (size_t)y * row_bytes;
                 // zero the staging row, then fill the active 32-pixel groups
                 for (int k = lane; k < (row_bytes + 15) / 16; k += 32) reinterpret_cast<int4 *>(my_row)[k] = z4;
@@ -687,7 +725,7 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
         }
         if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; }          // never leave a bulk copy in flight into the window
     }
-    if (zero_fill && tid == 0) bulk_wait<0>();                 // (a kernel may not exit with bulk stores reading its shared memory)
+    if (filler) bulk_wait(0);
 }
 
 // ============================================================================================
@@ -943,12 +981,15 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     if (fusg_record_cuda(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st)) != FUSG_OK) return FUSG_ERR_CUDA;
     k_plane_gate<<<(B * N_TEX + 255) / 256, 256, 0, st>>>(src_kp, dst_kp, vis, plane_j, H12, Minv, counters, list6, list4, B, H, W);
     fusg_count_launch(2);
-    // The zero fill of the five planes (97 % of the output bytes) rides inside k_warp_rows as TMA bulk stores issued one crop
-    // ahead of the gather (see the kernel); only outputs that are not 16-byte granular are cleared by a memset up front.
-    const size_t out_crop_bytes = (size_t)N_TEX * H * W * 3;
-    const bool bulk_zero = !frame_path && out_crop_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(warped) & 15) == 0;
+    // The zero fill of the five planes (97 % of the output bytes stay zero) rides inside k_warp_rows as TMA bulk stores issued
+    // two crops ahead of the gather (see the kernel); only outputs that are not 16-byte granular are cleared by a memset.
+    // (Measured alternatives, 16k crops: a fill kernel of its own costs 2.6 ms when serial; on a helper stream underneath
+    // k_visibility / k_solve it gains 0.2 ms as plain stores -- the store flood slows the latency-bound solver by as much as
+    // it saves -- and as bulk stores it made the call 2-4x SLOWER; plain stores from the gather's own warps: 6.0 ms against
+    // 4.8 ms for this form.  The gather without any fill takes 3.6 ms.)
+    const bool bulk_zero = !frame_path && ((size_t)N_TEX * H * W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(warped) & 15) == 0;
     if (!frame_path && !bulk_zero) {
-        if (fusg_record_cuda(cudaMemsetAsync(warped, 0, (size_t)B * out_crop_bytes, st)) != FUSG_OK) return FUSG_ERR_CUDA;
+        if (fusg_record_cuda(cudaMemsetAsync(warped, 0, (size_t)B * N_TEX * H * W * 3, st)) != FUSG_OK) return FUSG_ERR_CUDA;
         fusg_count_launch(1);
     }
     {
@@ -964,7 +1005,7 @@ static int warp_fused_impl(const uint8_t *src, const int32_t *src_kp, const int3
     if (!frame_path) {
         // persistent: two CTAs per SM stride over the crops
         const int grid = B < 2 * fusg_num_sms() ? B : 2 * fusg_num_sms();
-        k_warp_rows<WIN_SMALL><<<grid, WARP_THREADS, warp_smem_bytes(WIN_SMALL), st>>>(src, src_kp, plane_j, Minv, recs, warped, H, W, counters + 2, big_list, 0, B, bulk_zero ? 1 : 0);
+        k_warp_rows<WIN_SMALL><<<grid, WARP_THREADS, warp_smem_bytes(WIN_SMALL), st>>>(src, src_kp, plane_j, Minv, recs, warped, H, W, counters + 2, big_list, 0, B, bulk_zero ? ZERO_AHEAD : 0);
         // crops whose polygons span more than WIN_SMALL source rows (a vehicle filling the crop): full-height window
         const int bgrid = B < fusg_num_sms() ? B : fusg_num_sms();
         k_warp_rows<MAX_HW><<<bgrid, WARP_THREADS, warp_smem_bytes(MAX_HW), st>>>(src, src_kp, plane_j, Minv, recs, warped, H, W, counters + 2, big_list, 1, B, 0);
