@@ -507,6 +507,25 @@ __device__ __forceinline__ void fast_chunk16(const FastEpi &fe, const float *s_b
     }
 }
 
+// fast_epi == 3: the network's last layer (shape_decoder_6.conv, 32 -> 3, run on pixel pairs: n = dx * cq + c, cq = cout / 2 <= 8)
+// straight to the NCHW fp32 API tensor.  A thread holds both pixels of its pair for every channel: one 8-byte store per
+// channel, and the 32 lanes of a warp (consecutive pairs of one image row) cover 256 contiguous bytes.  The generic
+// epilogue spent 160 us on this layer's 50 MB (scalar stores, per-element index arithmetic, a code path that does not fit
+// the instruction cache).
+__device__ __forceinline__ void unpair_chunk(float *out, const float *s_bias, int cq, int Ho, int Wo, int b, int y, int x, const uint32_t *acc) {
+    float *p = out + (((size_t)b * cq) * Ho + y) * (size_t)(2 * Wo) + 2 * x;
+    const size_t plane = (size_t)Ho * (2 * Wo);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (c < cq) {
+            float2 v;
+            v.x = __uint_as_float(acc[c]) + s_bias[c];
+            v.y = __uint_as_float(acc[cq + c]) + s_bias[cq + c];
+            *reinterpret_cast<float2 *>(p + c * plane) = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_conv_tc
 // ------------------------------------------------------------------------------------------------
@@ -1024,7 +1043,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     if (c + 16 < ncols) tmem_ld16(t_base + (uint32_t)(c + 16), r);      // prefetch the next chunk
                     if (b < d.B) {
                         const int n = nt * p.block_n + c_begin + c;
-                        if (p.fast_epi) fast_chunk16(p.fe, s_bias, d.cout, p.Ho, p.Wo, opix, b, oy, ox, n, rr);
+                        if (p.fast_epi == 3) unpair_chunk(reinterpret_cast<float *>(p.fe.raw), s_bias, d.cout >> 1, p.Ho, p.Wo, b, oy, ox, rr);
+                        else if (p.fast_epi) fast_chunk16(p.fe, s_bias, d.cout, p.Ho, p.Wo, opix, b, oy, ox, n, rr);
                         else {
                             float v[16];
 #pragma unroll
@@ -1333,7 +1353,9 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     p.kb_local = p.num_kblocks / p.ksplit;
     // warp-staged epilogue for the big layers (needs 32 KB): applies to the lean-epilogue case with Wt >= 32
     static const int staged_on = getenv("FUSG_EPI_DIRECT") ? 0 : 1;
-    bool want_staged = p.ksplit == 1 && staged_on && (d.ksize >= 3 || p.block_n == 128) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
+    // (1x1 layers too: their direct epilogue touches 32 lines per store instruction -- 64 % LSU wavefronts, 236 -> 169 us on the 32->32 skip NiN at 256^2)
+    static const int staged_1x1 = getenv("FUSG_STAGED_1X1") ? atoi(getenv("FUSG_STAGED_1X1")) : 1;
+    bool want_staged = p.ksplit == 1 && staged_on && (d.ksize >= 3 || p.block_n == 128 || staged_1x1) && p.Wt >= 32 && p.block_n >= 32 && is_pow2(p.block_n) && d.noise == nullptr && d.cout % 16 == 0;
     const int smem_budget = (want_staged ? 168 : 200) * 1024 - (p.ksplit > 1 ? p.block_n * TC_BLOCK_M * 4 : 0);
     // weights resident when the whole (single) N tile fits next to a useful pipeline
     p.w_resident = (p.ksplit == 1 && p.n_tiles == 1 && p.num_kblocks * p.b_bytes <= 72 * 1024) ? 1 : 0;
@@ -1420,6 +1442,19 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
             case FUSG_OUT_D2S_BLOCK: fe.stride_a = 4 * d.cout; fe.stride_b = 2 * d.cout; break;
         }
         p.fast_epi = ok ? (want_staged ? 2 : 1) : 0;
+        // pixel-pair packed layer -> NCHW fp32, nothing else (the network's last convolution)
+        if (!ok && p.ksplit == 1 && d.noise == nullptr && d.residual == nullptr && d.dtype == FUSG_DTYPE_BF16 && d.cout <= 16 && d.cout % 2 == 0 && p.block_n == 16) {
+            int nouts = 0;
+            const fusg_conv_out *only = nullptr;
+            for (int sidx = 0; sidx < FUSG_CONV_MAX_OUTS; ++sidx)
+                if (d.outs[sidx].ptr) { ++nouts; only = &d.outs[sidx]; }
+            if (nouts == 1 && only->layout == 1 && only->mode == FUSG_OUT_UNPAIR && only->source == 0 && only->elu == 0 &&
+                (reinterpret_cast<uintptr_t>(only->ptr) & 7) == 0) {
+                memset(&fe, 0, sizeof(fe));
+                fe.raw = reinterpret_cast<__nv_bfloat16 *>(only->ptr);        // (an fp32 NCHW tensor on this path)
+                p.fast_epi = 3;
+            }
+        }
         p.fe = fe;
     }
     PFN_encodeTiled enc = get_encode();
