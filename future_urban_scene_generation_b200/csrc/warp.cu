@@ -431,6 +431,7 @@ __device__ __forceinline__ void bulk_wait(int pending) {
     }
 }
 constexpr int ZERO_BYTES = 4096;
+constexpr int ZERO_PER_ROW = 1;        // blocks a filler lane issues after each row its warp gathers
 constexpr int ZERO_AHEAD = 2;          // crops the fill runs ahead of the gather (per CTA)
 // bulk zero fill of `bytes` (a multiple of 16) at `dst` (16-byte aligned): one bulk async-group of the calling thread,
 // which takes every nsh-th block (share `sh`)
@@ -552,13 +553,20 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
         const uint8_t *gsrc = src + (size_t)b * crop_bytes;
         uint8_t *gout = warped + (size_t)b * N_TEX * crop_bytes;
         __syncthreads();                                      // previous item done with the header / window
-        bool zero_pending = false;
+        // (filler lanes) this lane's blocks of the crop `zero_ahead` crops on are issued a block at a time between the rows of
+        // the current crop -- a burst of bulk stores clogs the SM's memory-instruction queue for everybody -- and committed as
+        // one group at the end of the crop
+        bool zero_pending = filler;
+        size_t zoff = 0, zend = 0;
+        uint8_t *zdst = nullptr;
         if (filler) {
             const int nxt = item + zero_ahead * (int)gridDim.x;
-            if (nxt < n_items) zero_crop(warped + (size_t)nxt * N_TEX * crop_bytes, s_zero, (size_t)N_TEX * crop_bytes, warp - 1, WARP_NWARPS - 1);
-            else bulk_commit();
-            zero_pending = true;
+            if (nxt < n_items) { zdst = warped + (size_t)nxt * N_TEX * crop_bytes; zoff = (size_t)(warp - 1) * ZERO_BYTES; zend = (size_t)N_TEX * crop_bytes; }
         }
+        auto zero_step = [&](int n) {
+            for (; n > 0 && zoff < zend; --n, zoff += (size_t)(WARP_NWARPS - 1) * ZERO_BYTES)
+                bulk_s2g(zdst + zoff, s_zero, (uint32_t)(zend - zoff < (size_t)ZERO_BYTES ? zend - zoff : (size_t)ZERO_BYTES));
+        };
         if (!from_list && warp == 2 && lane < 8) {
             // pull the next crop's few hundred bytes of per-crop inputs towards L2: its prologue is a chain of dependent loads
             // that otherwise waits behind the zero-fill traffic
@@ -605,7 +613,10 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
         if (tid >= 32 && tid < 32 + N_TEX * 9) hd->Minv[0][tid - 32] = Minv[(size_t)b * N_TEX * 9 + (tid - 32)];
         __syncthreads();
         const int win_lo = hd->win_lo, win_hi = hd->win_hi;
-        if (hd->skip || win_lo > win_hi) continue;            // nothing to warp here: the planes stay zero
+        if (hd->skip || win_lo > win_hi) {                    // nothing to warp here: the planes stay zero
+            if (filler) { zero_step(1 << 30); bulk_commit(); }
+            continue;
+        }
         const int win_rows = win_hi - win_lo + 1;
         const uint8_t *gwin = gsrc + (size_t)win_lo * row_bytes;
         const uint32_t win_bytes = (uint32_t)win_rows * row_bytes;
@@ -687,7 +698,7 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
                 if (lane == 0) hd->row_bits[warp] = act;
             }
             if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; src_ready = true; }
-            if (zero_pending) { bulk_wait(zero_ahead); zero_pending = false; }
+            if (zero_pending) { bulk_wait(zero_ahead - 1); zero_pending = false; }     // groups are committed at the END of a crop: one fewer may be pending
             __syncthreads();
             uint8_t *oplane = gout + (size_t)j * crop_bytes;
             // the ACTIVE rows are dealt round-robin to the warps (neighbouring rows have similar spans; a static share of all rows
@@ -720,10 +731,12 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
                 } else {
                     for (int k = lane; k < row_bytes; k += 32) orow[k] = my_row[k];
                 }
+                if (filler) zero_step(ZERO_PER_ROW);
                 __syncwarp();
             }
         }
         if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; }          // never leave a bulk copy in flight into the window
+        if (filler) { zero_step(1 << 30); bulk_commit(); }                    // what the rows did not cover
     }
     if (filler) bulk_wait(0);
 }
