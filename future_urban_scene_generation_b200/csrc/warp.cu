@@ -364,12 +364,12 @@ __device__ __forceinline__ uchar3 bilinear_tap4(SrcPtr src, const uint32_t *mask
 // with cv2's 1/32-px fixed-point bilinear rule and overwrites the rows with 16-byte coalesced stores.
 // Crops whose polygons span more than WIN source rows are queued for a second launch with a full-height window.
 // ============================================================================================
-constexpr int WARP_THREADS = 256;
+constexpr int WARP_THREADS = 512;
 constexpr int WARP_NWARPS = WARP_THREADS / 32;
 constexpr int MAX_HW = 256;
 constexpr int ROW_BYTES_MAX = MAX_HW * 3;          // 768
 constexpr int MASK_WORDS = MAX_HW / 32;            // 8 words per row
-constexpr int WIN_SMALL = 128;                     // source rows of the common-case window (2 CTAs per SM)
+constexpr int WIN_SMALL = 120;                     // source rows of the common-case window (2 CTAs per SM)
 
 struct WarpSmemHeader {
     unsigned long long mbar;
@@ -377,7 +377,7 @@ struct WarpSmemHeader {
     double Minv[N_TEX][9];
     int sel[N_TEX];                                // source plane feeding output plane j, or -1
     int polyx[6], polyy[6], polyn;
-    unsigned row_bits[WARP_NWARPS];                // output rows of the current plane with a non-empty span (bit r of word w: row 32w + r)
+    unsigned row_bits[MAX_HW / 32];                // output rows of the current plane with a non-empty span (bit r of word w: row 32w + r)
     PolyEdge edge[6];                              // row-independent part of the source polygon's edges (poly_edge_setup)
     float fwdx[6], fwdy[6];                        // forward image of the source polygon under H12 (destination pixels)
     int fwd_ok;                                    // 0: a vertex is on / behind the horizon of H12 -> bbox spans only
@@ -682,10 +682,11 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
 #pragma unroll
                 for (int w = 0; w < MASK_WORDS; ++w) s_mask[(y - win_lo) * MASK_WORDS + w] = ranges_word(lo, hi, rc, w);
             }
-            {   // thread = output row (H <= 256 = WARP_THREADS on this path); the rows with a non-empty span as one bit word per warp
-                const int y = tid;
+            {   // the upper half of the CTA: thread = output row (H <= 256); the rows with a non-empty span as one bit word per warp
+                // (the lower half is busy with the mask rows above: the two loops run side by side instead of one after the other)
+                const int y = tid - MAX_HW;
                 int xlo = 1, xhi = 0;
-                if (y < H) {
+                if (y >= 0 && y < H) {
                     row_active_span(M, y, W, hd->bbox, xlo, xhi);
                     if (hd->fwd_ok && xlo <= xhi) {
                         int plo, phi;
@@ -695,7 +696,7 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
                     hd->span_lo[y] = (short)xlo; hd->span_hi[y] = (short)xhi;
                 }
                 const unsigned act = __ballot_sync(0xffffffffu, xlo <= xhi);
-                if (lane == 0) hd->row_bits[warp] = act;
+                if (lane == 0 && warp >= MAX_HW / 32) hd->row_bits[warp - MAX_HW / 32] = act;
             }
             if (!src_ready) { mbar_wait(&hd->mbar, phase); phase ^= 1; src_ready = true; }
             if (zero_pending) { bulk_wait(zero_ahead - 1); zero_pending = false; }     // groups are committed at the END of a crop: one fewer may be pending
@@ -703,11 +704,18 @@ k_warp_rows(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_kp,
             uint8_t *oplane = gout + (size_t)j * crop_bytes;
             // the ACTIVE rows are dealt round-robin to the warps (neighbouring rows have similar spans; a static share of all rows
             // left warps idle at the barrier below, a shared-memory ticket per row cost more than it balanced)
-            int ridx = 0;
-            for (int ww = 0; ww < WARP_NWARPS; ++ww)
-            for (unsigned rbits = hd->row_bits[ww]; rbits; rbits &= rbits - 1) {
-                if ((ridx++ & (WARP_NWARPS - 1)) != warp) continue;
-                const int y = ww * 32 + __ffs(rbits) - 1;
+            // active row k of the plane = the k-th set bit of row_bits (a find-n-th-set over the eight words)
+            int n_active = 0;
+#pragma unroll
+            for (int ww = 0; ww < MAX_HW / 32; ++ww) n_active += __popc(hd->row_bits[ww]);
+            for (int k = warp; k < n_active; k += WARP_NWARPS) {
+                int y = -1, rem = k;
+#pragma unroll
+                for (int ww = 0; ww < MAX_HW / 32; ++ww) {
+                    const unsigned m = hd->row_bits[ww];
+                    const int c = __popc(m);
+                    if (y < 0) { if (rem < c) y = ww * 32 + (int)__fns(m, 0, rem + 1); else rem -= c; }
+                }
                 const int xlo = hd->span_lo[y], xhi = hd->span_hi[y];
                 uint8_t *orow = oplane + (size_t)y * row_bytes;
                 // zero the staging row, then fill the active 32-pixel groups
