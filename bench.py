@@ -479,6 +479,19 @@ def run_ours(args):
             warp_roof["large_batch"] = {"crops": BL, "ms": bsec * 1e3, "achieved": bgbs, "unit": "GB/s", "frac": bgbs / peaks["hbm_gbs"]}
             del big, rb
             torch.cuda.empty_cache()
+            # 5/6 of this path's algorithmic bytes are writes and a pure write stream does not reach the copy bandwidth:
+            # measured on the spot for the record (torch fill_ of 1 GiB); `frac` above stays against the copy peak
+            probe = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+            probe.fill_(0)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                probe.fill_(0)
+            e1.record()
+            torch.cuda.synchronize()
+            warp_roof["write_stream_GBps"] = probe.numel() * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            del probe
+            torch.cuda.empty_cache()
         except RuntimeError as exc:                       # e.g. not enough free memory: report, do not fail the bench
             warp_roof["large_batch"] = {"skipped": str(exc)[:120]}
 
