@@ -30,8 +30,9 @@
  *   FUSG_NO_PAIR2=1         conv: no cta_group::2 CTA pairs
  *   FUSG_KSPLIT_MAX=<n>     conv: largest split-K cluster (default 8); FUSG_KSPLIT_MIN_KB=<n> smallest K (in
  *                           k-blocks) that is split (default 36)
- *   FUSG_EPI_DIRECT=1       conv: no warp-staged epilogue
+ *   FUSG_EPI_DIRECT=1       conv: no warp-staged epilogue; FUSG_STAGED_1X1=0: not for the 1x1 layers
  *   FUSG_NO_PDL=1           conv: no programmatic dependent launch
+ *   FUSG_SM_RESERVE=<n>     conv: initial value of fusg_conv2d_set_sm_reserve (default 0)
  */
 #ifndef FUSG_H_
 #define FUSG_H_
