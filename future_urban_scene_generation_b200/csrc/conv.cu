@@ -564,6 +564,7 @@ struct alignas(64) ConvTcParams {
     uint32_t halo_skip;             // halo mode: bit (ky * chunks + chunk) set = all three taps of that stage have zero weights -> skipped
     int pair;                       // halo mode on CTA pairs (cta_group::2): M = 256 per MMA, each CTA holds half of the weight rows
     int pdl;                        // launched with programmatic stream serialization (griddepcontrol in the kernel)
+    unsigned long long w_prefetch_bytes;   // > 0: bytes of the weight matrix the grid pulls into L2 before the dependency wait
     int ksplit;                     // > 1: thread-block cluster of `ksplit` CTAs per tile, each reducing 1/ksplit of K (few-tile layers)
     int kb_local;                   // k-blocks per CTA = num_kblocks / ksplit
     int tmem_cols;
@@ -756,6 +757,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     // programmatic dependent launch: everything above (barriers, TMEM, tensor-map prefetch, bias) touched nothing the
     // previous kernel of the stream produces; wait for it here, then let the next kernel start its own prologue
     if (p.pdl) {
+        // few-CTA layers (the coarse scales and the auto-regressive tail) are bound by how fast a handful of SMs can pull their
+        // weight slabs (K up to 4608) from HBM: the weights do not depend on the previous kernel, so the grid pulls the whole
+        // matrix into L2 NOW, underneath that kernel's tail -- each CTA an equal share, as bulk prefetches
+        if (p.w_prefetch_bytes && threadIdx.x == 32) {
+            const unsigned long long total = p.w_prefetch_bytes, per = ((total / gridDim.x) + 15ull) & ~15ull;
+            unsigned long long lo = per * blockIdx.x, hi = lo + per < total ? lo + per : total;
+            const char *wb = reinterpret_cast<const char *>(d.weight);
+            for (; lo < hi; lo += 32768ull) {
+                const unsigned n = (unsigned)(hi - lo < 32768ull ? hi - lo : 32768ull) & ~15u;
+                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wb + lo), "r"(n) : "memory");
+            }
+        }
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
@@ -1515,6 +1528,11 @@ static int launch_tc(const fusg_conv_desc &d, int Ho, int Wo, cudaStream_t st) {
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
     static const int pdl_on = getenv("FUSG_NO_PDL") ? 0 : 1;
     p.pdl = pdl_on;
+    {
+        static const int wpf_on = getenv("FUSG_NO_WPREFETCH") ? 0 : 1;
+        const unsigned long long wbytes = (unsigned long long)d.cout_pad * taps * (d.c0 + d.c1) * 2ull;
+        p.w_prefetch_bytes = (wpf_on && pdl_on && total_tiles * p.ksplit <= 64 && wbytes >= 65536ull && (reinterpret_cast<uintptr_t>(d.weight) & 15) == 0) ? wbytes : 0ull;
+    }
     // persistent CTAs own a STATIC share of the tiles, and one CTA fills an SM: if a co-tenant (the solver warps of the warp
     // stage that runs next to the VUNet in a pipeline step) holds even one SM, the CTA meant for it starts only when another
     // CTA has finished its whole share -- the layer takes twice as long.  g_sm_reserve SMs are therefore left to co-tenants.

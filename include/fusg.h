@@ -31,7 +31,7 @@
  *   FUSG_KSPLIT_MAX=<n>     conv: largest split-K cluster (default 8); FUSG_KSPLIT_MIN_KB=<n> smallest K (in
  *                           k-blocks) that is split (default 36)
  *   FUSG_EPI_DIRECT=1       conv: no warp-staged epilogue; FUSG_STAGED_1X1=0: not for the 1x1 layers
- *   FUSG_NO_PDL=1           conv: no programmatic dependent launch
+ *   FUSG_NO_PDL=1           conv: no programmatic dependent launch; FUSG_NO_WPREFETCH=1: no L2 weight prefetch ahead of the wait
  *   FUSG_SM_RESERVE=<n>     conv: initial value of fusg_conv2d_set_sm_reserve (default 0)
  */
 #ifndef FUSG_H_
