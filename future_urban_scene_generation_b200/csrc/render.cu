@@ -17,7 +17,7 @@
 //   k_render_vertices   (vertex, item): world position (optional rigid move), camera space, image-plane position; bounding box
 //   k_render_colours    (vertex, item): vertex normal from the incident triangles in ascending order (CSR), colour
 //   k_render_clear      z-buffer keys of the bounding box <- +inf
-//   k_render_raster     (triangle, item): edge-function coverage over the triangle's bounding box, 64-bit atomicMin of
+//   k_render_raster     warp per (triangle, item): edge-function coverage over the triangle's bounding box, 64-bit atomicMin of
 //                       (float32 depth bits << 32 | triangle index): nearest wins, ties go to the lower index
 //   k_render_resolve    (bounding-box pixel, item): winner triangle -> interpolated colour -> uint8 sketch + mask
 #include <cuda_runtime.h>
@@ -68,8 +68,14 @@ __global__ void __launch_bounds__(256) k_render_vertices(const double *__restric
 __global__ void __launch_bounds__(256) k_render_background(uint8_t *__restrict__ img, uint8_t *__restrict__ mask, int *__restrict__ bbox, size_t npix, int B) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = i0; i < npix * 3; i += stride) img[i] = 0;
-    for (size_t i = i0; i < npix; i += stride) mask[i] = 1;
+    // 16-byte stores where the buffers allow it (torch allocations do), bytes for the rest
+    const bool vec = ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+    const size_t n_img = vec ? (npix * 3) / 16 : 0, n_mask = vec ? npix / 16 : 0;
+    const int4 z4 = make_int4(0, 0, 0, 0), o4 = make_int4(0x01010101, 0x01010101, 0x01010101, 0x01010101);
+    for (size_t i = i0; i < n_img; i += stride) reinterpret_cast<int4 *>(img)[i] = z4;
+    for (size_t i = i0; i < n_mask; i += stride) reinterpret_cast<int4 *>(mask)[i] = o4;
+    for (size_t i = n_img * 16 + i0; i < npix * 3; i += stride) img[i] = 0;
+    for (size_t i = n_mask * 16 + i0; i < npix; i += stride) mask[i] = 1;
     if (i0 < (size_t)B) { bbox[4 * i0] = INT_MAX; bbox[4 * i0 + 1] = INT_MAX; bbox[4 * i0 + 2] = INT_MIN; bbox[4 * i0 + 3] = INT_MIN; }
 }
 
@@ -142,9 +148,12 @@ __device__ __forceinline__ TriSetup tri_setup(const double *__restrict__ uvz, co
 
 __device__ __forceinline__ bool top_left(double A, double B) { return A > 0 || (A == 0 && B < 0); }
 
+// One WARP per (triangle, item): the lanes tile the triangle's bounding box 8 x 4 pixels at a time.  (A thread per triangle
+// left the kernel waiting for the few threads that own large triangles: 79 % of the renderer's time.)  atomicMin is
+// commutative, so the result does not depend on how the pixels are dealt out.
 __global__ void __launch_bounds__(128) k_render_raster(const double *__restrict__ uvz_all, const int32_t *__restrict__ tris, unsigned long long *__restrict__ zbuf,
                                                        int Nv, int Nt, int H, int W) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), b = blockIdx.y, lane = threadIdx.x & 31;
     if (t >= Nt) return;
     const TriSetup s = tri_setup(uvz_all + (size_t)b * Nv * 3, tris, t);
     if (!s.ok) return;
@@ -155,9 +164,10 @@ __global__ void __launch_bounds__(128) k_render_raster(const double *__restrict_
     const int ymin = max((int)ceil(fmax(fy0, 0.0)), 0), ymax = min((int)floor(fmin(fy1, (double)(H - 1))), H - 1);
     const bool tl0 = top_left(s.y1 - s.y2, s.x2 - s.x1), tl1 = top_left(s.y2 - s.y0, s.x0 - s.x2), tl2 = top_left(s.y0 - s.y1, s.x1 - s.x0);
     unsigned long long *zb = zbuf + (size_t)b * H * W;
-    for (int y = ymin; y <= ymax; ++y) {
+    const int lx = lane & 7, ly = lane >> 3;
+    for (int y = ymin + ly; y <= ymax; y += 4) {
         const double py = (double)y;
-        for (int x = xmin; x <= xmax; ++x) {
+        for (int x = xmin + lx; x <= xmax; x += 8) {
             const double px = (double)x;
             const double e0 = (s.x2 - s.x1) * (py - s.y1) - (s.y2 - s.y1) * (px - s.x1);
             const double e1 = (s.x0 - s.x2) * (py - s.y2) - (s.y0 - s.y2) * (px - s.x2);
@@ -241,7 +251,7 @@ extern "C" int fusg_render_normals(const double *verts, const int32_t *tris, con
     // per item: enough blocks for a bounding box of a quarter of the frame in one sweep, grid-stride beyond
     const int pgrid = (H * W / 4 + 255) / 256 < 64 ? ((H * W / 4 + 255) / 256 > 0 ? (H * W / 4 + 255) / 256 : 1) : 64;
     k_render_clear<<<dim3(pgrid, B), 256, 0, st>>>(zbuf, bbox, H, W);
-    k_render_raster<<<dim3((Nt + 127) / 128, B), 128, 0, st>>>(uvz, tris, zbuf, Nv, Nt, H, W);
+    k_render_raster<<<dim3((Nt + 3) / 4, B), 128, 0, st>>>(uvz, tris, zbuf, Nv, Nt, H, W);
     k_render_resolve<<<dim3(pgrid, B), 256, 0, st>>>(uvz, col, tris, zbuf, bbox, normals, mask, Nv, H, W);
     fusg_count_launch(6);
     return fusg_check_launch();
