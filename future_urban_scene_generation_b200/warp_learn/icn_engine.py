@@ -18,6 +18,7 @@ floor of ~1.1e-2 under it (tests/test_icn_gpu.py; same tensor-core rate).  dtype
 bf16; dtype 'fp32' runs it on the CUDA-core direct kernel (verification build, <= 1e-4).
 """
 import ctypes as C
+import os
 
 from .. import _lib
 from ..vunet.engine import ConvDesc, DT_BF16, DT_F32, IMPL_AUTO, IMPL_TC, IMPL_DIRECT
@@ -97,12 +98,17 @@ class IcnEngine:
         if dev.type != "cuda":
             raise _lib.FusgError("G_Resnet: parameters are not on a CUDA device; the B200 path has no CPU fallback (call .to('cuda'))")
         self._w = {}
+        self._kwide = {}
         for path, blk in self.m.blocks.items():
             w = blk.conv.weight.detach().float()
             cout, cin, k, _ = w.shape
             cin_pad = 32 if cin < 32 else cin          # the 21-channel input: one 64-byte swizzle span
+            # K of a narrow-input layer is widened to 64 (TMA zero-fills beyond the 32 stored channels, fusg_conv_desc.cphys0):
+            # twice the tensor work, but a 64-channel k-block is what the sliding-window A tiles need -- one row-segment load
+            # per (tile, ky) instead of a load per tap (49 for the 7x7 first layer)
+            kwide = 64 if (cin_pad == 32 and k >= 5 and os.environ.get("FUSG_ICN_NO_KWIDE") is None) else cin_pad
             cout_pad = _pad16(cout)
-            wp = torch.zeros((cout_pad, k * k, cin_pad), dtype=torch.float32, device=dev)
+            wp = torch.zeros((cout_pad, k * k, kwide), dtype=torch.float32, device=dev)
             wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
             bias = torch.zeros((cout_pad,), dtype=torch.float32, device=dev)
             bias[:cout] = blk.conv.bias.detach().float()
@@ -110,6 +116,7 @@ class IcnEngine:
             if blk.norm is not None:
                 gamma, beta = blk.norm.gamma.detach().float().contiguous(), blk.norm.beta.detach().float().contiguous()
             self._w[path] = (wp.to(self.tdtype).contiguous(), bias, cout, cout_pad, cin, cin_pad, k, gamma, beta)
+            self._kwide[path] = kwide
         self._wkey = key
 
     # ------------------------------------------------------------------ launches
@@ -138,6 +145,8 @@ class IcnEngine:
         d = ConvDesc()
         d.in0 = x.t.data_ptr()
         d.c0, d.pitch0 = x.C, x.C
+        if self._kwide.get(path, x.C) > x.C:               # weights are 64 channels wide, the activation stores 32
+            d.c0, d.cphys0 = self._kwide[path], x.C
         d.B, d.H, d.W = B, x.H, x.W
         d.ksize, d.stride = k, stride
         d.pad_mode, d.pad, d.border = 1, pad, x.border
