@@ -1221,6 +1221,9 @@ __global__ void k_fold_weightnorm_paired(const float *__restrict__ v, const floa
 
 // NCHW fp32 -> NHWC (zero-padded channels, optional ELU).  One thread per pixel: the per-channel reads
 // are coalesced across the warp, the writes are 16-byte pieces of the thread's own contiguous pixel row.
+// gridDim.y > 1: one thread per (pixel, 8-channel group) instead -- the Sampler noise tensors are a few hundred pixels of
+// 128 channels, and a thread that walks all 16 groups of its pixel is one long chain of strided loads (20-40 us per
+// launch, ten launches at the head of every step).
 template <typename T>
 __global__ void k_nchw_to_nhwc(const float *__restrict__ in, T *__restrict__ out, int C, int HW, int cpad, int elu, size_t npix) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*HW
@@ -1228,7 +1231,8 @@ __global__ void k_nchw_to_nhwc(const float *__restrict__ in, T *__restrict__ out
     const size_t b = i / HW, pix = i - b * HW;
     const float *src = in + b * C * HW + pix;
     T *dst = out + i * cpad;
-    for (int c0 = 0; c0 < cpad; c0 += 8) {
+    const int c_lo = gridDim.y > 1 ? (int)blockIdx.y * 8 : 0, c_hi = gridDim.y > 1 ? c_lo + 8 : cpad;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -1735,9 +1739,12 @@ extern "C" int fusg_nchw_to_nhwc(const float *in, void *out, int B, int C, int H
     if (cpad % 8 != 0) return FUSG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t npix = (size_t)B * H * W;
-    const unsigned grid = (unsigned)((npix + 255) / 256);
-    if (dtype == FUSG_DTYPE_BF16) k_nchw_to_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16 *)out, C, H * W, cpad, elu, npix);
-    else k_nchw_to_nhwc<float><<<grid, 256, 0, st>>>(in, (float *)out, C, H * W, cpad, elu, npix);
+    // small tensors (the Sampler noise): a thread per (pixel, 8-channel group), 64-thread blocks
+    const bool split = npix < 16384 && cpad > 8;
+    const dim3 grid((unsigned)((npix + (split ? 63 : 255)) / (split ? 64 : 256)), split ? (unsigned)(cpad / 8) : 1u);
+    const unsigned threads = split ? 64 : 256;
+    if (dtype == FUSG_DTYPE_BF16) k_nchw_to_nhwc<__nv_bfloat16><<<grid, threads, 0, st>>>(in, (__nv_bfloat16 *)out, C, H * W, cpad, elu, npix);
+    else k_nchw_to_nhwc<float><<<grid, threads, 0, st>>>(in, (float *)out, C, H * W, cpad, elu, npix);
     fusg_count_launch(1);
     return fusg_check_launch();
 }
